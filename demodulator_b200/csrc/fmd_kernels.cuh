@@ -1,0 +1,393 @@
+/*
+ * fmd_kernels.cuh -- sm_100a device code of the FM demodulation hot path.
+ *
+ * Two kernels:
+ *
+ *  fmd_fast_kernel<NTI,NTO>   the bandwidth kernel.  One 16-byte load per lane per
+ *      pass (8 complex u8 samples = 4 discriminator pairs), one 16-byte store per
+ *      lane per pass (4 floats); every intermediate lives in registers.  A warp
+ *      walks a contiguous segment of a chunk; the stencil neighbours that fall
+ *      outside a lane come from the next lane by shuffle, and the ones that fall
+ *      outside the warp come from the SAME warp's next pass (the output stage
+ *      runs one pass behind the discriminator), so no value is computed twice,
+ *      nothing is exchanged through memory and there is no block-level barrier.
+ *      Computes, per chunk-local output k:
+ *          s[c]  = (int8)(u8 - 127)                       shiftOrigin   matrix.c:82-98
+ *          z[c]  = dc + sum_t tin[t]  * s[c+t]   (-L only) applyComplexFilter filter.c:233-259
+ *          x[k]  = atan2(Im, Re)(z[2k] * conj(z[2k+1]))   fmDemod       matrix.c:159-176
+ *          y[k]  = dco + sum_t tout[t] * x[k+t]           applyFilter   filter.c:212-231
+ *      with zero extension past the chunk end, i.e. the steady-state form of the
+ *      reference's section sweep (fmd_fold_taps).
+ *
+ *  fmd_exact_kernel            one thread per output, evaluates the reference's
+ *      section recurrence op for op (separately rounded mul/add, literal "+1",
+ *      head rules, and the x|y_c|y_o arena aliasing that seeds the first outputs
+ *      of every chunk when -L is on).  Used for the first few outputs of every
+ *      chunk (where the sweep is not in steady state), for ragged remainders, for
+ *      chunk sizes the fast kernel does not take, and for FMD_FLAG_EXACT audits.
+ */
+#ifndef FMD_KERNELS_CUH
+#define FMD_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fmdemod.h"
+
+#define FMD_BLOCK 256               /* threads per CTA: 8 warps, one segment each */
+#define FMD_WARPS (FMD_BLOCK / 32)
+#define FMD_PASS_OUT 128u           /* outputs per warp per pass (32 lanes x 4)   */
+
+#ifndef FMD_ATAN_TERMS
+#define FMD_ATAN_TERMS 7
+#endif
+
+struct FmdStencil {
+    float tin[FMD_MAX_TAPS];
+    float dci, dcq;
+    float tout[FMD_MAX_TAPS];
+    float dco;
+};
+
+struct FmdGeom {
+    unsigned long long chunk_stride; /* bytes between chunk starts                        */
+    unsigned chunk_out;              /* outputs per chunk (edge rule: zero beyond)        */
+    unsigned fast_out;               /* outputs per chunk the fast kernel covers (x128)   */
+    unsigned iters_per_seg;          /* passes per warp segment                           */
+    unsigned segs_per_chunk;
+    unsigned nchunks;
+};
+
+struct FmdSections {
+    float in[FMD_MAX_SECTIONS][6];
+    float out[FMD_MAX_SECTIONS][6];
+    int lin, lout;
+};
+
+/* ------------------------------------------------------------------ helpers */
+
+/* per-byte (u + 1) mod 256: s + 128 where s = (int8)(u - 127) */
+__device__ __forceinline__ uint32_t fmd_bias_bytes(uint32_t w) {
+    return ((w & 0x7f7f7f7fu) + 0x01010101u) ^ (w & 0x80808080u);
+}
+
+/* byte `i` of a biased word -> exact float in [-128, 127] */
+template <int I>
+__device__ __forceinline__ float fmd_byte_to_float(uint32_t wb) {
+    /* 0x4B0000uu = 8388608 + uu */
+    return __uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7540 | I)) - 8388736.0f;
+}
+
+__device__ __forceinline__ void fmd_unpack_word(uint32_t w, float *f) {
+    const uint32_t wb = fmd_bias_bytes(w);
+    f[0] = fmd_byte_to_float<0>(wb);
+    f[1] = fmd_byte_to_float<1>(wb);
+    f[2] = fmd_byte_to_float<2>(wb);
+    f[3] = fmd_byte_to_float<3>(wb);
+}
+
+/*
+ * atan2 with C99 Annex F zero/sign behaviour for finite inputs (what glibc's
+ * atan2f gives the reference): octant reduction, one MUFU.RCP, odd minimax
+ * polynomial on [0,1] (7 terms: 3.2e-7 max abs error in f32), sign-bit fix-ups.
+ */
+__device__ __forceinline__ float fmd_atan2(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mn = fminf(ax, ay);
+    float mx, rc;
+    /* max3 with a tiny floor: (0,0) gives t = 0 instead of 0/0 */
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(mx) : "f"(ax), "f"(ay), "f"(1.0e-30f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(mx));
+    const float t = mn * rc;
+    const float s = t * t;
+#if FMD_ATAN_TERMS == 8
+    float p = -4.0545672133e-03f;
+    p = fmaf(p, s, 2.1862957874e-02f);
+    p = fmaf(p, s, -5.5912326768e-02f);
+    p = fmaf(p, s, 9.6421973279e-02f);
+    p = fmaf(p, s, -1.3908629550e-01f);
+    p = fmaf(p, s, 1.9946565651e-01f);
+    p = fmaf(p, s, -3.3329860784e-01f);
+    p = fmaf(p, s, 9.9999933558e-01f);
+#elif FMD_ATAN_TERMS == 7
+    float p = 6.8117930109e-03f;
+    p = fmaf(p, s, -3.3604219717e-02f);
+    p = fmaf(p, s, 7.9623671389e-02f);
+    p = fmaf(p, s, -1.3233342042e-01f);
+    p = fmaf(p, s, 1.9807815551e-01f);
+    p = fmaf(p, s, -3.3317368053e-01f);
+    p = fmaf(p, s, 9.9999611155e-01f);
+#else
+    float p = -1.1719135407e-02f;
+    p = fmaf(p, s, 5.2647350619e-02f);
+    p = fmaf(p, s, -1.1642648119e-01f);
+    p = fmaf(p, s, 1.9354037577e-01f);
+    p = fmaf(p, s, -3.3262282784e-01f);
+    p = fmaf(p, s, 9.9997721908e-01f);
+#endif
+    float r = p * t;
+    if (ay > ax) r = 1.57079637f - r;
+    if (__float_as_int(x) < 0) r = 3.14159274f - r;
+    return __uint_as_float(__float_as_uint(r) | (__float_as_uint(y) & 0x80000000u));
+}
+
+/* --------------------------------------------------------------- fast kernel */
+
+#define FMD_FILL 0x7f7f7f7fu /* four bytes that shift to 0.0: the zero extension past a chunk */
+
+/*
+ * One pass of one lane: unpack `cur` (8 complex samples), input lowpass, four
+ * discriminator outputs into xcur; then the output lowpass over the PREVIOUS
+ * pass's xprev (neighbours: next lane's xprev, or lane 0's xcur for lane 31)
+ * and one 16-byte store.  `nxt` is the lane's raw input of the following pass:
+ * lane 0's copy is what lane 31 needs as its input-filter halo.
+ */
+template <int NTI, int NTO, bool STORE>
+__device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint4 &nxt, const float (&xprev)[4],
+                                         float (&xcur)[4], const bool zero_x, float *__restrict__ dst,
+                                         const unsigned lane, const unsigned nxt_lane, const FmdStencil &st) {
+    constexpr int HC = NTI > 1 ? NTI - 1 : 0; /* complex samples needed from the next lane */
+    constexpr int HW = (HC + 1) / 2;          /* ... as 4-byte words (2 complex each)      */
+    constexpr int NB = NTO - 1;               /* discriminator outputs needed from the next lane */
+
+    float f[16 + 4 * (HW > 0 ? HW : 1)];
+    fmd_unpack_word(cur.x, f + 0);
+    fmd_unpack_word(cur.y, f + 4);
+    fmd_unpack_word(cur.z, f + 8);
+    fmd_unpack_word(cur.w, f + 12);
+    if (HW >= 1) {
+        const uint32_t h = __shfl_sync(0xffffffffu, lane == 0 ? nxt.x : cur.x, nxt_lane);
+        fmd_unpack_word(h, f + 16);
+    }
+    if (HW >= 2) {
+        const uint32_t h = __shfl_sync(0xffffffffu, lane == 0 ? nxt.y : cur.y, nxt_lane);
+        fmd_unpack_word(h, f + 20);
+    }
+
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float a, b, c, d;
+        if (NTI == 0) {
+            a = f[4 * j + 0]; b = f[4 * j + 1]; c = f[4 * j + 2]; d = f[4 * j + 3];
+        } else {
+            a = st.dci; b = st.dcq; c = st.dci; d = st.dcq;
+#pragma unroll
+            for (int t = 0; t < NTI; ++t) {
+                a = fmaf(st.tin[t], f[4 * j + 2 * t + 0], a);
+                b = fmaf(st.tin[t], f[4 * j + 2 * t + 1], b);
+                c = fmaf(st.tin[t], f[4 * j + 2 * t + 2], c);
+                d = fmaf(st.tin[t], f[4 * j + 2 * t + 3], d);
+            }
+        }
+        /* s0 * conj(s1).  The fused forms keep the reference's signed-zero results: a sum of
+         * two exact-zero products takes the same sign fused or not. */
+        const float re = fmaf(a, c, b * d);
+        const float im = fmaf(-a, d, b * c);
+        xcur[j] = fmd_atan2(im, re);
+    }
+    if (zero_x) { /* past the end of the chunk the discriminator output is exactly 0 */
+        xcur[0] = 0.0f; xcur[1] = 0.0f; xcur[2] = 0.0f; xcur[3] = 0.0f;
+    }
+
+    float xn[4 + (NB > 0 ? NB : 1)];
+    xn[0] = xprev[0]; xn[1] = xprev[1]; xn[2] = xprev[2]; xn[3] = xprev[3];
+#pragma unroll
+    for (int t = 0; t < NB; ++t)
+        xn[4 + t] = __shfl_sync(0xffffffffu, lane == 0 ? xcur[t] : xprev[t], nxt_lane);
+    if (STORE) {
+        float4 y;
+        float *yy = reinterpret_cast<float *>(&y);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float acc = st.dco;
+#pragma unroll
+            for (int t = 0; t < NTO; ++t) acc = fmaf(st.tout[t], xn[j + t], acc);
+            yy[j] = acc;
+        }
+        *reinterpret_cast<float4 *>(dst) = y;
+    }
+}
+
+/*
+ * A warp owns one segment: n_it passes of 128 outputs (512 B in, 512 B out per pass),
+ * plus one "drain" pass that only feeds the last real pass its neighbours.  If the
+ * segment ends at the end of a chunk the drain pass is the zero extension (no load,
+ * x = 0); otherwise it re-reads the first 512 B of what follows.
+ */
+template <int NTI, int NTO>
+__global__ void __launch_bounds__(FMD_BLOCK)
+fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const FmdGeom g, const FmdStencil st) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long seg = (unsigned long long) blockIdx.x * FMD_WARPS + (threadIdx.x >> 5);
+    if (seg >= (unsigned long long) g.nchunks * g.segs_per_chunk) return;
+    const unsigned chunk = (unsigned) (seg / g.segs_per_chunk);
+    const unsigned sic = (unsigned) (seg - (unsigned long long) chunk * g.segs_per_chunk);
+    const unsigned it0 = sic * g.iters_per_seg;
+    const unsigned iters_chunk = g.fast_out >> 7;
+    const unsigned n_it = min(g.iters_per_seg, iters_chunk - it0);
+    /* does the drain pass fall off the end of the chunk? (fast_out == chunk_out there) */
+    const bool end_zero = (it0 + n_it == iters_chunk) && (g.fast_out == g.chunk_out);
+    const unsigned n_ld = end_zero ? n_it : n_it + 1u; /* positions that exist in memory */
+    const unsigned nxt_lane = (lane + 1u) & 31u;
+    const unsigned k0 = it0 * FMD_PASS_OUT + lane * 4u;
+
+    const uint4 *__restrict__ src =
+        reinterpret_cast<const uint4 *>(in + (unsigned long long) chunk * g.chunk_stride + 4ull * k0);
+    float *__restrict__ dst = out + (unsigned long long) chunk * g.chunk_out + k0;
+    const uint4 fill = make_uint4(FMD_FILL, FMD_FILL, FMD_FILL, FMD_FILL);
+
+    uint4 ra = __ldg(src), rb;
+    float xa[4] = {0.f, 0.f, 0.f, 0.f}, xb[4];
+
+    /* pass 0: nothing to store yet */
+    rb = (1u < n_ld) ? __ldg(src + 32) : fill;
+    fmd_pass<NTI, NTO, false>(ra, rb, xa, xb, false, dst, lane, nxt_lane, st);
+    src += 32;
+
+    /* passes 1 .. n_it-1 are all real: two per trip so the raw/x registers ping-pong
+     * without moves */
+    unsigned p = 1;
+    for (; p + 1 < n_it; p += 2) {
+        ra = __ldg(src + 32);
+        fmd_pass<NTI, NTO, true>(rb, ra, xb, xa, false, dst, lane, nxt_lane, st);
+        rb = (p + 2 < n_ld) ? __ldg(src + 64) : fill;
+        fmd_pass<NTI, NTO, true>(ra, rb, xa, xb, false, dst + FMD_PASS_OUT, lane, nxt_lane, st);
+        src += 64;
+        dst += 2 * FMD_PASS_OUT;
+    }
+    /* what is left: at most one real pass, then the drain pass (p == n_it) */
+    for (; p <= n_it; ++p) {
+        ra = (p + 1 < n_ld) ? __ldg(src + 32) : fill;
+        fmd_pass<NTI, NTO, true>(rb, ra, xb, xa, (p == n_it) && end_zero, dst, lane, nxt_lane, st);
+        rb = ra;
+        xb[0] = xa[0]; xb[1] = xa[1]; xb[2] = xa[2]; xb[3] = xa[3];
+        src += 32;
+        dst += FMD_PASS_OUT;
+    }
+}
+
+/* -------------------------------------------------------------- exact kernel */
+
+#define FMD_CONE_W (FMD_MAX_SECTIONS / 2 + 3)
+
+/*
+ * Value of index k after the reference's section sweep over a lane of n samples
+ * (filter.c:221-230 / 242-258), from the dependency cone of k alone:
+ *   Y_s[k] = ((b0*Y_{s+1}[k] + b1*Y_{s+2}[k+1]) [+ 1]) - ((a0 + a1*x[k]) + a2*x[k+1])
+ * if section s rewrites k (L+s <= k <= n-1+L+s), else Y_{s+1}[k]; every product
+ * and sum rounded separately.  getx(i) = lane input, init(i) = what the y region
+ * held before the sweep.
+ */
+template <class GetX, class Init>
+__device__ float fmd_sweep_cone(long long k, long long n, int L, const float (*sos)[6], bool bias,
+                                const GetX &getx, const Init &init) {
+    float p1[FMD_CONE_W], p2[FMD_CONE_W], xv[FMD_CONE_W + 1];
+    const int W = L / 2 + 3;
+    for (int j = 0; j <= W; ++j) xv[j] = getx(k + j);
+    for (int j = 0; j < W; ++j) p1[j] = p2[j] = init(k + j);
+    for (int s = L - 1; s >= 0; --s) {
+        const float b0 = sos[s][0], b1 = sos[s][1], a0 = sos[s][3], a1 = sos[s][4], a2 = sos[s][5];
+        const long long lo = L + s, hi = n - 1 + L + s;
+        float nw[FMD_CONE_W];
+        for (int j = 0; j + 1 < W; ++j) {
+            const long long kk = k + j;
+            if (kk >= lo && kk <= hi) {
+                float acc = __fadd_rn(__fmul_rn(b0, p1[j]), __fmul_rn(b1, p2[j + 1]));
+                if (bias) acc = __fadd_rn(acc, 1.0f);
+                const float rhs = __fadd_rn(__fadd_rn(a0, __fmul_rn(a1, xv[j])), __fmul_rn(a2, xv[j + 1]));
+                nw[j] = __fsub_rn(acc, rhs);
+            } else {
+                nw[j] = p1[j];
+            }
+        }
+        nw[W - 1] = p1[W - 1];
+        for (int j = 0; j < W; ++j) { p2[j] = p1[j]; p1[j] = nw[j]; }
+    }
+    return p1[0];
+}
+
+struct FmdZeroInit {
+    __device__ float operator()(long long) const { return 0.0f; }
+};
+
+/* shifted input lane q (0 = I, 1 = Q) of one chunk, zero past its end */
+struct FmdShiftedLane {
+    const uint8_t *cin;
+    long long nc;
+    int q;
+    __device__ float operator()(long long c) const {
+        if (c >= nc) return 0.0f;
+        return (float) (int8_t) (cin[2 * c + q] - 127);
+    }
+};
+
+/* final y_c lane value at complex index c < nc (input lowpass on), or the shifted sample */
+struct FmdComplexLane {
+    const uint8_t *cin;
+    long long nc;
+    const FmdSections *sec;
+    int q;
+    __device__ float operator()(long long c) const {
+        FmdShiftedLane sl{cin, nc, q};
+        if (sec->lin == 0) return sl(c);
+        return fmd_sweep_cone(c, nc, sec->lin, sec->in, q == 0, sl, FmdZeroInit());
+    }
+};
+
+/* what the complex sweep reads as x[nc + t]: the already-final head of y_c */
+struct FmdAliasedLane {
+    FmdComplexLane z;
+    __device__ float operator()(long long c) const { return z(c - z.nc); }
+};
+
+/* discriminator output j of the chunk, zero past its end (demodRet slack, matrix.c:184) */
+struct FmdDemodX {
+    const uint8_t *cin;
+    long long nc, n_out;
+    const FmdSections *sec;
+    __device__ float operator()(long long j) const {
+        if (j >= n_out) return 0.0f;
+        FmdComplexLane zi{cin, nc, sec, 0}, zq{cin, nc, sec, 1};
+        const float a = zi(2 * j), b = zq(2 * j), c = zi(2 * j + 1), d = zq(2 * j + 1);
+        const float re = __fadd_rn(__fmul_rn(a, c), __fmul_rn(b, d));
+        const float im = __fadd_rn(__fmul_rn(-a, d), __fmul_rn(b, c));
+        return fmd_atan2(im, re);
+    }
+};
+
+/* initial contents of the output accumulator region: what the complex sweep spilled past
+ * the end of y_c (matrix.c:260-267 + filter.c:242-258), zero elsewhere */
+struct FmdSpillInit {
+    const uint8_t *cin;
+    long long nc;
+    const FmdSections *sec;
+    __device__ float operator()(long long f) const {
+        const int L = sec->lin;
+        if (L == 0 || f >= 4 * L - 2) return 0.0f;
+        const int q = (int) (f & 1);
+        FmdAliasedLane al{FmdComplexLane{cin, nc, sec, q}};
+        return fmd_sweep_cone(nc + (f >> 1), nc, L, sec->in, q == 0, al, FmdZeroInit());
+    }
+};
+
+/*
+ * One thread per output: outputs [k_begin, k_begin + k_count) of every chunk.
+ */
+__global__ void __launch_bounds__(128)
+fmd_exact_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const FmdGeom g,
+                 const FmdSections sec, unsigned k_begin, unsigned k_count) {
+    const unsigned long long tid = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long total = (unsigned long long) g.nchunks * k_count;
+    if (tid >= total) return;
+    const unsigned chunk = (unsigned) (tid / k_count);
+    const unsigned k = k_begin + (unsigned) (tid - (unsigned long long) chunk * k_count);
+    if (k >= g.chunk_out) return;
+    const uint8_t *cin = in + (unsigned long long) chunk * g.chunk_stride;
+    const long long n_out = g.chunk_out, nc = 2ll * g.chunk_out;
+    FmdDemodX dx{cin, nc, n_out, &sec};
+    FmdSpillInit si{cin, nc, &sec};
+    out[(unsigned long long) chunk * g.chunk_out + k] =
+        fmd_sweep_cone((long long) k, n_out, sec.lout, sec.out, true, dx, si);
+}
+
+#endif /* FMD_KERNELS_CUH */

@@ -1,0 +1,507 @@
+/*
+ * fmdemod.cu -- the C ABI of include/fmdemod.h over the sm_100a kernels.
+ *
+ * What the reference does on its worker thread per 256 KiB chunk
+ * (/root/reference/src/matrix.c:236-273) this library does for an arbitrary
+ * number of chunks per launch; what the reference does with a 1-slot buffer, a
+ * mutex and two semaphores (src/main.c:72-91) is here a ring of pinned slots
+ * chained through three CUDA streams (copy-in, compute, copy-out) by events.
+ *
+ * There is no CPU implementation of the data path in this library.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "fmd_internal.h"
+#include "fmd_kernels.cuh"
+
+/* ------------------------------------------------------------------ errors */
+
+static thread_local char g_err[512] = "";
+
+extern "C" int fmd_set_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char *fmd_last_error(void) { return g_err; }
+
+#define FMD_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fmd_set_error(FMD_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                                 __FILE__, __LINE__);                                               \
+    } while (0)
+
+/* ----------------------------------------------------------------- context */
+
+struct fmd_slot {
+    uint8_t *d_in = nullptr;
+    float *d_out = nullptr;
+    cudaEvent_t ev_in = nullptr;   /* H2D landed              */
+    cudaEvent_t ev_k = nullptr;    /* kernels done            */
+    cudaEvent_t ev_out = nullptr;  /* D2H landed              */
+    bool busy = false;
+};
+
+struct fmd_ctx {
+    fmd_config cfg;
+    int device = 0;
+    unsigned lin = 0, lout = 0;
+    FmdSections sec;
+    FmdStencil st;
+    unsigned nti = 0, nto = 0;
+    unsigned head = 0; /* outputs at the start of every chunk that are not in steady state */
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    fmd_slot *slots = nullptr;
+    unsigned nslots = 0;
+    size_t slot_bytes = 0;
+    uint64_t launches = 0;
+    int sm_count = 148;
+    /* optional per-launch event timing of the fast kernel */
+    bool profile = false;
+    cudaEvent_t *pev = nullptr; /* pairs: [2*i] before, [2*i+1] after */
+    unsigned pev_used = 0, pev_cap = 0;
+    double prof_ms = 0.0;
+    uint64_t prof_n = 0;
+};
+
+static int prof_flush(fmd_ctx *c) {
+    for (unsigned i = 0; i < c->pev_used; ++i) {
+        float ms = 0.f;
+        FMD_CUDA(cudaEventSynchronize(c->pev[2 * i + 1]));
+        FMD_CUDA(cudaEventElapsedTime(&ms, c->pev[2 * i], c->pev[2 * i + 1]));
+        c->prof_ms += ms;
+        c->prof_n++;
+    }
+    c->pev_used = 0;
+    return FMD_OK;
+}
+
+extern "C" int fmd_profile_kernels(fmd_ctx *c, int enable) {
+    if (!c) return fmd_set_error(FMD_EINVAL, "null argument");
+    if (enable && !c->pev) {
+        c->pev_cap = 256;
+        c->pev = new (std::nothrow) cudaEvent_t[2 * c->pev_cap];
+        if (!c->pev) return fmd_set_error(FMD_ENOMEM, "out of host memory");
+        for (unsigned i = 0; i < 2 * c->pev_cap; ++i) FMD_CUDA(cudaEventCreate(&c->pev[i]));
+    }
+    if (!enable && c->profile) prof_flush(c);
+    c->profile = enable != 0;
+    return FMD_OK;
+}
+
+extern "C" int fmd_kernel_time(fmd_ctx *c, double *ms, uint64_t *launches) {
+    if (!c || !ms || !launches) return fmd_set_error(FMD_EINVAL, "null argument");
+    int rc = prof_flush(c);
+    if (rc) return rc;
+    *ms = c->prof_ms;
+    *launches = c->prof_n;
+    c->prof_ms = 0.0;
+    c->prof_n = 0;
+    return FMD_OK;
+}
+
+extern "C" void fmd_config_default(fmd_config *cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof *cfg);
+    cfg->sample_rate = 125000.0;
+    cfg->lowpass_in = 0.0;
+    cfg->lowpass_out = 12500.0;
+    cfg->epsilon = 0.3;
+    cfg->in_degree = 0;
+    cfg->out_degree = 3;
+    cfg->mode = 0x10;
+    cfg->flags = 0;
+    cfg->chunk_bytes = FMD_DEFAULT_CHUNK_BYTES;
+}
+
+extern "C" int fmd_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fmd_set_error(FMD_ENODEV, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+
+extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
+    if (!cfg_in || !out) return fmd_set_error(FMD_EINVAL, "fmd_create: null argument");
+    *out = nullptr;
+    fmd_config cfg = *cfg_in;
+    /* the reference's defaulting rule: -L without -D inherits the output degree (matrix.c:190-192) */
+    if (cfg.lowpass_in != 0.0 && cfg.in_degree == 0) cfg.in_degree = cfg.out_degree;
+    if (cfg.lowpass_in == 0.0 && cfg.in_degree != 0)
+        return fmd_set_error(FMD_EINVAL, "-D without -L: the reference applies an undesigned filter (undefined)");
+    if (cfg.out_degree == 0 || fmd_sections(cfg.out_degree) > FMD_MAX_SECTIONS ||
+        fmd_sections(cfg.in_degree) > FMD_MAX_SECTIONS)
+        return fmd_set_error(FMD_EINVAL, "filter degree outside 1..%d", 2 * FMD_MAX_SECTIONS);
+    if (cfg.chunk_bytes == 0 || (cfg.chunk_bytes & 3u) || cfg.chunk_bytes > (1ull << 34))
+        return fmd_set_error(FMD_EINVAL, "chunk_bytes must be a positive multiple of 4 (got %llu)",
+                             (unsigned long long) cfg.chunk_bytes);
+    if ((cfg.mode >> 2) & 3u)
+        return fmd_set_error(FMD_EINVAL, "input conditioner -q%u is outside the accelerated path (only -q0)",
+                             (cfg.mode >> 2) & 3u);
+    if (((cfg.mode >> 4) & 3u) == 0)
+        return fmd_set_error(FMD_EINVAL, "demodulation off (-c) is unreachable in the reference CLI and unsupported");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fmd_set_error(FMD_ENODEV, "no CUDA device: %s (this library has no CPU path)",
+                             e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev) return fmd_set_error(FMD_EINVAL, "device %d not in 0..%d", device, ndev - 1);
+    FMD_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FMD_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fmd_set_error(FMD_ENODEV, "device %d is sm_%d%d; this library ships sm_100a code only", device,
+                             prop.major, prop.minor);
+
+    fmd_ctx *c = new (std::nothrow) fmd_ctx();
+    if (!c) return fmd_set_error(FMD_ENOMEM, "out of host memory");
+    c->cfg = cfg;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->lout = fmd_sections(cfg.out_degree);
+    c->lin = fmd_sections(cfg.in_degree);
+    memset(&c->sec, 0, sizeof c->sec);
+    memset(&c->st, 0, sizeof c->st);
+    c->sec.lin = (int) c->lin;
+    c->sec.lout = (int) c->lout;
+
+    int rc = fmd_design_sos(cfg.mode & 1u, cfg.out_degree, cfg.lowpass_out, cfg.sample_rate, cfg.epsilon,
+                            &c->sec.out[0][0]);
+    if (!rc) rc = fmd_fold_taps(&c->sec.out[0][0], c->lout, 1, c->st.tout, &c->st.dco, &c->nto);
+    if (!rc && c->lin) {
+        float dci = 0.f;
+        unsigned nti_q = 0;
+        float taps_q[FMD_MAX_TAPS];
+        rc = fmd_design_sos((cfg.mode >> 1) & 1u, cfg.in_degree, cfg.lowpass_in, cfg.sample_rate, cfg.epsilon,
+                            &c->sec.in[0][0]);
+        if (!rc) rc = fmd_fold_taps(&c->sec.in[0][0], c->lin, 1, c->st.tin, &dci, &c->nti);
+        /* the Q lane lacks the "+1" (filter.c:255): same taps, different constant */
+        if (!rc) rc = fmd_fold_taps(&c->sec.in[0][0], c->lin, 0, taps_q, &c->st.dcq, &nti_q);
+        c->st.dci = dci;
+    }
+    if (rc) {
+        delete c;
+        return rc;
+    }
+    c->head = 2 * c->lout - 1;
+    if (c->lin && 4 * c->lin - 2 > c->head) c->head = 4 * c->lin - 2;
+    c->head = (c->head + 7u) & ~7u;
+
+    if (cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->s_k, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking) != cudaSuccess) {
+        fmd_destroy(c);
+        return fmd_set_error(FMD_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    *out = c;
+    return FMD_OK;
+}
+
+static void fmd_ring_free(fmd_ctx *c) {
+    if (!c->slots) return;
+    for (unsigned i = 0; i < c->nslots; ++i) {
+        fmd_slot &s = c->slots[i];
+        if (s.ev_out && s.busy) cudaEventSynchronize(s.ev_out);
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.ev_in) cudaEventDestroy(s.ev_in);
+        if (s.ev_k) cudaEventDestroy(s.ev_k);
+        if (s.ev_out) cudaEventDestroy(s.ev_out);
+    }
+    delete[] c->slots;
+    c->slots = nullptr;
+    c->nslots = 0;
+    c->slot_bytes = 0;
+}
+
+extern "C" void fmd_destroy(fmd_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    fmd_ring_free(c);
+    if (c->pev) {
+        for (unsigned i = 0; i < 2 * c->pev_cap; ++i) cudaEventDestroy(c->pev[i]);
+        delete[] c->pev;
+    }
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_k) cudaStreamDestroy(c->s_k);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
+    delete c;
+}
+
+extern "C" int fmd_get_config(const fmd_ctx *c, fmd_config *cfg) {
+    if (!c || !cfg) return fmd_set_error(FMD_EINVAL, "null argument");
+    *cfg = c->cfg;
+    return FMD_OK;
+}
+
+extern "C" int fmd_get_sos(const fmd_ctx *c, int which, float *sos) {
+    if (!c || !sos) return fmd_set_error(FMD_EINVAL, "null argument");
+    const unsigned rows = which ? c->lin : c->lout;
+    memcpy(sos, which ? &c->sec.in[0][0] : &c->sec.out[0][0], rows * 6 * sizeof(float));
+    return (int) rows;
+}
+
+extern "C" uint64_t fmd_launch_count(const fmd_ctx *c) { return c ? c->launches : 0; }
+
+/* ------------------------------------------------------------ pinned memory */
+
+extern "C" int fmd_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return fmd_set_error(FMD_EINVAL, "null argument");
+    *ptr = nullptr;
+    FMD_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+    return FMD_OK;
+}
+
+extern "C" int fmd_host_free(void *ptr) {
+    if (ptr) FMD_CUDA(cudaFreeHost(ptr));
+    return FMD_OK;
+}
+
+extern "C" int fmd_host_register(void *ptr, size_t bytes) {
+    FMD_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return FMD_OK;
+}
+
+extern "C" int fmd_host_unregister(void *ptr) {
+    FMD_CUDA(cudaHostUnregister(ptr));
+    return FMD_OK;
+}
+
+/* ---------------------------------------------------------------- launching */
+
+extern "C" size_t fmd_out_count(const fmd_ctx *c, size_t nbytes) {
+    (void) c;
+    return nbytes >> 2; /* whole chunks give B/4 each; the ragged tail gives r/4 */
+}
+
+typedef void (*fast_fn)(const uint8_t *, float *, const FmdGeom, const FmdStencil);
+
+template <int NTI>
+static fast_fn pick_out(unsigned nto) {
+    switch (nto) {
+        case 1: return fmd_fast_kernel<NTI, 1>;
+        case 2: return fmd_fast_kernel<NTI, 2>;
+        case 3: return fmd_fast_kernel<NTI, 3>;
+        case 4: return fmd_fast_kernel<NTI, 4>;
+        case 5: return fmd_fast_kernel<NTI, 5>;
+        default: return nullptr;
+    }
+}
+
+static fast_fn pick_fast(unsigned nti, unsigned nto) {
+    switch (nti) {
+        case 0: return pick_out<0>(nto);
+        case 1: return pick_out<1>(nto);
+        case 2: return pick_out<2>(nto);
+        case 3: return pick_out<3>(nto);
+        case 4: return pick_out<4>(nto);
+        case 5: return pick_out<5>(nto);
+        default: return nullptr;
+    }
+}
+
+static int launch_exact(fmd_ctx *c, const uint8_t *d_in, float *d_out, const FmdGeom &g, unsigned k_begin,
+                        unsigned k_count, cudaStream_t s) {
+    if (!k_count || !g.nchunks) return FMD_OK;
+    const unsigned long long total = (unsigned long long) g.nchunks * k_count;
+    const unsigned long long blocks = (total + 127) / 128;
+    if (blocks > 0x7fffffffull) return fmd_set_error(FMD_EINVAL, "exact kernel grid too large");
+    fmd_exact_kernel<<<(unsigned) blocks, 128, 0, s>>>(d_in, d_out, g, c->sec, k_begin, k_count);
+    FMD_CUDA(cudaGetLastError());
+    c->launches++;
+    return FMD_OK;
+}
+
+/* `nchunks` chunks of `chunk_out` outputs each, chunk starts `stride` bytes apart */
+static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned nchunks, unsigned chunk_out,
+                         unsigned long long stride, cudaStream_t s) {
+    if (!nchunks || !chunk_out) return FMD_OK;
+    FmdGeom g;
+    g.chunk_stride = stride;
+    g.chunk_out = chunk_out;
+    g.nchunks = nchunks;
+    g.fast_out = 0;
+    g.iters_per_seg = 1;
+    g.segs_per_chunk = 1;
+
+    fast_fn fn = pick_fast(c->nti, c->nto);
+    const bool aligned = ((uintptr_t) d_in % 16 == 0) && ((uintptr_t) d_out % 16 == 0) && (stride % 16 == 0) &&
+                         (nchunks == 1 || chunk_out % 4 == 0);
+    /* the fast kernel covers whole 128-output passes; if the chunk is not a multiple of 128
+     * outputs it stops one pass early so that its drain pass still reads real samples */
+    const unsigned fast_out = (chunk_out % FMD_PASS_OUT == 0)
+                                  ? chunk_out
+                                  : (chunk_out >= 2 * FMD_PASS_OUT ? (chunk_out / FMD_PASS_OUT - 1) * FMD_PASS_OUT : 0);
+    const bool fast_ok = fn && aligned && !(c->cfg.flags & FMD_FLAG_EXACT) && fast_out >= FMD_PASS_OUT &&
+                         fast_out > c->head;
+    if (!fast_ok) return launch_exact(c, d_in, d_out, g, 0, chunk_out, s);
+
+    g.fast_out = fast_out;
+    const unsigned iters_chunk = g.fast_out >> 7;
+    /* passes per warp segment: long enough to amortise the one extra (drain) pass, short
+     * enough that the grid still holds a few waves of warps for small inputs */
+    const unsigned long long total_iters = (unsigned long long) iters_chunk * nchunks;
+    const unsigned long long want_warps = (unsigned long long) c->sm_count * 64ull * 2ull;
+    unsigned ips = 64;
+    while (ips > 8 && total_iters / ips < want_warps) ips >>= 1;
+    if (ips > iters_chunk) ips = iters_chunk;
+    g.iters_per_seg = ips;
+    g.segs_per_chunk = (iters_chunk + ips - 1) / ips;
+    const unsigned long long nseg = (unsigned long long) g.segs_per_chunk * nchunks;
+    const unsigned long long blocks = (nseg + FMD_WARPS - 1) / FMD_WARPS;
+    if (blocks > 0x7fffffffull) return fmd_set_error(FMD_EINVAL, "fast kernel grid too large");
+    cudaEvent_t *pe = nullptr;
+    if (c->profile) {
+        if (c->pev_used == c->pev_cap) {
+            int rc = prof_flush(c);
+            if (rc) return rc;
+        }
+        pe = &c->pev[2 * c->pev_used++];
+        FMD_CUDA(cudaEventRecord(pe[0], s));
+    }
+    fn<<<(unsigned) blocks, FMD_BLOCK, 0, s>>>(d_in, d_out, g, c->st);
+    FMD_CUDA(cudaGetLastError());
+    if (pe) FMD_CUDA(cudaEventRecord(pe[1], s));
+    c->launches++;
+    /* chunk heads (sweep not in steady state, -L arena spill) and ragged remainder */
+    int rc = launch_exact(c, d_in, d_out, g, 0, c->head < chunk_out ? c->head : chunk_out, s);
+    if (!rc && g.fast_out < chunk_out) rc = launch_exact(c, d_in, d_out, g, g.fast_out, chunk_out - g.fast_out, s);
+    return rc;
+}
+
+extern "C" int fmd_demod_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, float *d_out, void *stream) {
+    if (!c || (!d_in && nbytes) || (!d_out && nbytes)) return fmd_set_error(FMD_EINVAL, "null argument");
+    cudaStream_t s = stream ? (cudaStream_t) stream : c->s_k;
+    const unsigned long long B = c->cfg.chunk_bytes;
+    const unsigned long long nfull = nbytes / B;
+    const unsigned long long rem = (nbytes - nfull * B) & ~3ull;
+    if (nfull > 0xffffffffull) return fmd_set_error(FMD_EINVAL, "too many chunks in one call");
+    int rc = launch_chunks(c, d_in, d_out, (unsigned) nfull, (unsigned) (B >> 2), B, s);
+    if (!rc && rem)
+        rc = launch_chunks(c, d_in + nfull * B, d_out + nfull * (B >> 2), 1u, (unsigned) (rem >> 2), B, s);
+    return rc;
+}
+
+extern "C" int fmd_time_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, float *d_out, void *stream,
+                               int reps, float *ms) {
+    if (!c || !ms || reps <= 0) return fmd_set_error(FMD_EINVAL, "bad argument");
+    cudaStream_t s = stream ? (cudaStream_t) stream : c->s_k;
+    cudaEvent_t a, b;
+    FMD_CUDA(cudaEventCreate(&a));
+    FMD_CUDA(cudaEventCreate(&b));
+    FMD_CUDA(cudaEventRecord(a, s));
+    int rc = FMD_OK;
+    for (int i = 0; i < reps && !rc; ++i) rc = fmd_demod_device(c, d_in, nbytes, d_out, s);
+    if (!rc) {
+        FMD_CUDA(cudaEventRecord(b, s));
+        FMD_CUDA(cudaEventSynchronize(b));
+        FMD_CUDA(cudaEventElapsedTime(ms, a, b));
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    return rc;
+}
+
+/* --------------------------------------------------------------------- ring */
+
+extern "C" int fmd_ring_create(fmd_ctx *c, unsigned slots, size_t slot_bytes) {
+    if (!c || slots == 0 || slots > 64 || slot_bytes == 0) return fmd_set_error(FMD_EINVAL, "bad ring geometry");
+    if (slot_bytes % c->cfg.chunk_bytes)
+        return fmd_set_error(FMD_EINVAL, "slot_bytes must be a multiple of chunk_bytes");
+    FMD_CUDA(cudaSetDevice(c->device));
+    fmd_ring_free(c);
+    c->slots = new (std::nothrow) fmd_slot[slots];
+    if (!c->slots) return fmd_set_error(FMD_ENOMEM, "out of host memory");
+    c->nslots = slots;
+    c->slot_bytes = slot_bytes;
+    for (unsigned i = 0; i < slots; ++i) {
+        fmd_slot &s = c->slots[i];
+        if (cudaMalloc(&s.d_in, slot_bytes) != cudaSuccess || cudaMalloc(&s.d_out, slot_bytes) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming) != cudaSuccess) {
+            const char *m = cudaGetErrorString(cudaGetLastError());
+            fmd_ring_free(c);
+            return fmd_set_error(FMD_ECUDA, "ring allocation failed: %s", m);
+        }
+    }
+    return FMD_OK;
+}
+
+extern "C" int fmd_submit(fmd_ctx *c, unsigned slot, const uint8_t *in, size_t nbytes, float *out) {
+    if (!c || slot >= c->nslots || !in || !out) return fmd_set_error(FMD_EINVAL, "bad slot or null buffer");
+    if (nbytes > c->slot_bytes) return fmd_set_error(FMD_EINVAL, "nbytes exceeds slot_bytes");
+    fmd_slot &s = c->slots[slot];
+    if (s.busy) return fmd_set_error(FMD_EBUSY, "slot %u still in flight: call fmd_wait first", slot);
+    FMD_CUDA(cudaSetDevice(c->device));
+    const size_t nout = fmd_out_count(c, nbytes);
+    /* the slot's device buffers are free: the previous occupant's D2H completed in fmd_wait */
+    FMD_CUDA(cudaMemcpyAsync(s.d_in, in, nbytes, cudaMemcpyHostToDevice, c->s_in));
+    FMD_CUDA(cudaEventRecord(s.ev_in, c->s_in));
+    FMD_CUDA(cudaStreamWaitEvent(c->s_k, s.ev_in, 0));
+    int rc = fmd_demod_device(c, s.d_in, nbytes, s.d_out, c->s_k);
+    if (rc) return rc;
+    FMD_CUDA(cudaEventRecord(s.ev_k, c->s_k));
+    FMD_CUDA(cudaStreamWaitEvent(c->s_out, s.ev_k, 0));
+    FMD_CUDA(cudaMemcpyAsync(out, s.d_out, nout * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
+    FMD_CUDA(cudaEventRecord(s.ev_out, c->s_out));
+    s.busy = true;
+    return FMD_OK;
+}
+
+extern "C" int fmd_wait(fmd_ctx *c, unsigned slot) {
+    if (!c || slot >= c->nslots) return fmd_set_error(FMD_EINVAL, "bad slot");
+    fmd_slot &s = c->slots[slot];
+    if (!s.busy) return FMD_OK;
+    FMD_CUDA(cudaEventSynchronize(s.ev_out));
+    s.busy = false;
+    return FMD_OK;
+}
+
+/* ------------------------------------------------------- host-buffer wrapper */
+
+extern "C" int fmd_demod_host(fmd_ctx *c, const uint8_t *in, size_t nbytes, float *out, size_t *nout) {
+    if (!c || (!in && nbytes) || (!out && nbytes)) return fmd_set_error(FMD_EINVAL, "null argument");
+    if (nout) *nout = 0;
+    const size_t B = c->cfg.chunk_bytes;
+    /* slice size: ~32 MiB rounded to whole chunks, 3 slices in flight */
+    size_t slice = (size_t) 32 << 20;
+    slice = slice / B * B;
+    if (slice == 0) slice = B;
+    if (slice > nbytes) slice = (nbytes + B - 1) / B * B;
+    if (slice == 0) slice = B;
+    if (c->nslots < 3 || c->slot_bytes < slice) {
+        int rc = fmd_ring_create(c, 3, slice);
+        if (rc) return rc;
+    }
+    const unsigned ns = c->nslots;
+    size_t off = 0;
+    unsigned n = 0;
+    while (off < nbytes) {
+        const unsigned slot = n % ns;
+        const size_t len = nbytes - off < c->slot_bytes ? nbytes - off : c->slot_bytes;
+        int rc = fmd_wait(c, slot);
+        if (!rc) rc = fmd_submit(c, slot, in + off, len, out + (off >> 2));
+        if (rc) return rc;
+        off += len;
+        ++n;
+    }
+    for (unsigned i = 0; i < ns; ++i) {
+        int rc = fmd_wait(c, i);
+        if (rc) return rc;
+    }
+    if (nout) *nout = fmd_out_count(c, nbytes);
+    return FMD_OK;
+}
