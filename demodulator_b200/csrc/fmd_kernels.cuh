@@ -19,7 +19,8 @@
  *      with zero extension past the chunk end, i.e. the steady-state form of the
  *      reference's section sweep (fmd_fold_taps).
  *
- *  fmd_exact_kernel            one thread per output, evaluates the reference's
+ *  exact path (leading CTAs of the fast kernel, or fmd_exact_kernel stand-alone)
+ *      one thread per output, evaluates the reference's
  *      section recurrence op for op (separately rounded mul/add, literal "+1",
  *      head rules, and the x|y_c|y_o arena aliasing that seeds the first outputs
  *      of every chunk when -L is on).  Used for the first few outputs of every
@@ -56,6 +57,8 @@ struct FmdGeom {
     unsigned iters_per_seg;          /* passes per warp segment                           */
     unsigned segs_per_chunk;
     unsigned nchunks;
+    unsigned head;                   /* outputs [0, head) of every chunk: exact path (x4)   */
+    unsigned exact_blocks;           /* leading CTAs of the fast kernel that run that path  */
 };
 
 struct FmdSections {
@@ -84,6 +87,96 @@ __device__ __forceinline__ void fmd_unpack_word(uint32_t w, float *f) {
     f[1] = fmd_byte_to_float<1>(wb);
     f[2] = fmd_byte_to_float<2>(wb);
     f[3] = fmd_byte_to_float<3>(wb);
+}
+
+/* ---- packed f32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, one issue slot for two lanes) ---- */
+typedef unsigned long long fmd_f2;
+
+__device__ __forceinline__ fmd_f2 fmd_pk(float lo, float hi) {
+    fmd_f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void fmd_upk(fmd_f2 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ fmd_f2 fmd_fma2(fmd_f2 a, fmd_f2 b, fmd_f2 c) {
+    fmd_f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ fmd_f2 fmd_mul2(fmd_f2 a, fmd_f2 b) {
+    fmd_f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ fmd_f2 fmd_add2(fmd_f2 a, fmd_f2 b) {
+    fmd_f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ fmd_f2 fmd_bc(float v) { return fmd_pk(v, v); }
+__device__ __forceinline__ fmd_f2 fmd_neg2(fmd_f2 v) {
+    float lo, hi;
+    fmd_upk(v, lo, hi);
+    return fmd_pk(-lo, -hi); /* ptxas folds this into the consumer's operand modifier */
+}
+
+/* bytes `I` of two biased words -> the exact pair (s_a, s_b), each in [-128, 127] */
+template <int I>
+__device__ __forceinline__ fmd_f2 fmd_bytes_to_f2(uint32_t wa, uint32_t wb) {
+    return fmd_add2(fmd_pk(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7540 | I)),
+                           __uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7540 | I))),
+                    fmd_bc(-8388736.0f));
+}
+
+__device__ __forceinline__ float fmd_max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float fmd_rcp(float a) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
+
+#if FMD_ATAN_TERMS == 8
+#define FMD_ATAN_COEFFS {9.9999933558e-01f, -3.3329860784e-01f, 1.9946565651e-01f, -1.3908629550e-01f, \
+                         9.6421973279e-02f, -5.5912326768e-02f, 2.1862957874e-02f, -4.0545672133e-03f}
+#elif FMD_ATAN_TERMS == 7
+#define FMD_ATAN_COEFFS {9.9999611155e-01f, -3.3317368053e-01f, 1.9807815551e-01f, -1.3233342042e-01f, \
+                         7.9623671389e-02f, -3.3604219717e-02f, 6.8117930109e-03f}
+#else
+#define FMD_ATAN_COEFFS {9.9997721908e-01f, -3.3262282784e-01f, 1.9354037577e-01f, -1.1642648119e-01f, \
+                         5.2647350619e-02f, -1.1719135407e-02f}
+#endif
+
+/* quadrant / sign fix-ups shared by the scalar and the packed atan2 */
+__device__ __forceinline__ float fmd_atan2_finish(float r, float y, float x) {
+    if (fabsf(y) > fabsf(x)) r = 1.57079637f - r;
+    if (__float_as_int(x) < 0) r = 3.14159274f - r;
+    return __uint_as_float(__float_as_uint(r) | (__float_as_uint(y) & 0x80000000u));
+}
+
+/* two atan2 at once: the reductions, reciprocals and fix-ups are per lane, the polynomial is packed */
+__device__ __forceinline__ void fmd_atan2_x2(fmd_f2 im2, fmd_f2 re2, float &out_lo, float &out_hi) {
+    constexpr float cf[FMD_ATAN_TERMS] = FMD_ATAN_COEFFS;
+    float yl, yh, xl, xh;
+    fmd_upk(im2, yl, yh);
+    fmd_upk(re2, xl, xh);
+    const float mnl = fminf(fabsf(xl), fabsf(yl)), mnh = fminf(fabsf(xh), fabsf(yh));
+    const float rcl = fmd_rcp(fmd_max3(fabsf(xl), fabsf(yl), 1.0e-30f));
+    const float rch = fmd_rcp(fmd_max3(fabsf(xh), fabsf(yh), 1.0e-30f));
+    const fmd_f2 t = fmd_mul2(fmd_pk(mnl, mnh), fmd_pk(rcl, rch));
+    const fmd_f2 s = fmd_mul2(t, t);
+    fmd_f2 p = fmd_fma2(fmd_bc(cf[FMD_ATAN_TERMS - 1]), s, fmd_bc(cf[FMD_ATAN_TERMS - 2]));
+#pragma unroll
+    for (int i = FMD_ATAN_TERMS - 3; i >= 0; --i) p = fmd_fma2(p, s, fmd_bc(cf[i]));
+    float rl, rh;
+    fmd_upk(fmd_mul2(p, t), rl, rh);
+    out_lo = fmd_atan2_finish(rl, yl, xl);
+    out_hi = fmd_atan2_finish(rh, yh, xh);
 }
 
 /*
@@ -129,141 +222,6 @@ __device__ __forceinline__ float fmd_atan2(float y, float x) {
     if (ay > ax) r = 1.57079637f - r;
     if (__float_as_int(x) < 0) r = 3.14159274f - r;
     return __uint_as_float(__float_as_uint(r) | (__float_as_uint(y) & 0x80000000u));
-}
-
-/* --------------------------------------------------------------- fast kernel */
-
-#define FMD_FILL 0x7f7f7f7fu /* four bytes that shift to 0.0: the zero extension past a chunk */
-
-/*
- * One pass of one lane: unpack `cur` (8 complex samples), input lowpass, four
- * discriminator outputs into xcur; then the output lowpass over the PREVIOUS
- * pass's xprev (neighbours: next lane's xprev, or lane 0's xcur for lane 31)
- * and one 16-byte store.  `nxt` is the lane's raw input of the following pass:
- * lane 0's copy is what lane 31 needs as its input-filter halo.
- */
-template <int NTI, int NTO, bool STORE>
-__device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint4 &nxt, const float (&xprev)[4],
-                                         float (&xcur)[4], const bool zero_x, float *__restrict__ dst,
-                                         const unsigned lane, const unsigned nxt_lane, const FmdStencil &st) {
-    constexpr int HC = NTI > 1 ? NTI - 1 : 0; /* complex samples needed from the next lane */
-    constexpr int HW = (HC + 1) / 2;          /* ... as 4-byte words (2 complex each)      */
-    constexpr int NB = NTO - 1;               /* discriminator outputs needed from the next lane */
-
-    float f[16 + 4 * (HW > 0 ? HW : 1)];
-    fmd_unpack_word(cur.x, f + 0);
-    fmd_unpack_word(cur.y, f + 4);
-    fmd_unpack_word(cur.z, f + 8);
-    fmd_unpack_word(cur.w, f + 12);
-    if (HW >= 1) {
-        const uint32_t h = __shfl_sync(0xffffffffu, lane == 0 ? nxt.x : cur.x, nxt_lane);
-        fmd_unpack_word(h, f + 16);
-    }
-    if (HW >= 2) {
-        const uint32_t h = __shfl_sync(0xffffffffu, lane == 0 ? nxt.y : cur.y, nxt_lane);
-        fmd_unpack_word(h, f + 20);
-    }
-
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float a, b, c, d;
-        if (NTI == 0) {
-            a = f[4 * j + 0]; b = f[4 * j + 1]; c = f[4 * j + 2]; d = f[4 * j + 3];
-        } else {
-            a = st.dci; b = st.dcq; c = st.dci; d = st.dcq;
-#pragma unroll
-            for (int t = 0; t < NTI; ++t) {
-                a = fmaf(st.tin[t], f[4 * j + 2 * t + 0], a);
-                b = fmaf(st.tin[t], f[4 * j + 2 * t + 1], b);
-                c = fmaf(st.tin[t], f[4 * j + 2 * t + 2], c);
-                d = fmaf(st.tin[t], f[4 * j + 2 * t + 3], d);
-            }
-        }
-        /* s0 * conj(s1).  The fused forms keep the reference's signed-zero results: a sum of
-         * two exact-zero products takes the same sign fused or not. */
-        const float re = fmaf(a, c, b * d);
-        const float im = fmaf(-a, d, b * c);
-        xcur[j] = fmd_atan2(im, re);
-    }
-    if (zero_x) { /* past the end of the chunk the discriminator output is exactly 0 */
-        xcur[0] = 0.0f; xcur[1] = 0.0f; xcur[2] = 0.0f; xcur[3] = 0.0f;
-    }
-
-    float xn[4 + (NB > 0 ? NB : 1)];
-    xn[0] = xprev[0]; xn[1] = xprev[1]; xn[2] = xprev[2]; xn[3] = xprev[3];
-#pragma unroll
-    for (int t = 0; t < NB; ++t)
-        xn[4 + t] = __shfl_sync(0xffffffffu, lane == 0 ? xcur[t] : xprev[t], nxt_lane);
-    if (STORE) {
-        float4 y;
-        float *yy = reinterpret_cast<float *>(&y);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float acc = st.dco;
-#pragma unroll
-            for (int t = 0; t < NTO; ++t) acc = fmaf(st.tout[t], xn[j + t], acc);
-            yy[j] = acc;
-        }
-        *reinterpret_cast<float4 *>(dst) = y;
-    }
-}
-
-/*
- * A warp owns one segment: n_it passes of 128 outputs (512 B in, 512 B out per pass),
- * plus one "drain" pass that only feeds the last real pass its neighbours.  If the
- * segment ends at the end of a chunk the drain pass is the zero extension (no load,
- * x = 0); otherwise it re-reads the first 512 B of what follows.
- */
-template <int NTI, int NTO>
-__global__ void __launch_bounds__(FMD_BLOCK)
-fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const FmdGeom g, const FmdStencil st) {
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned long long seg = (unsigned long long) blockIdx.x * FMD_WARPS + (threadIdx.x >> 5);
-    if (seg >= (unsigned long long) g.nchunks * g.segs_per_chunk) return;
-    const unsigned chunk = (unsigned) (seg / g.segs_per_chunk);
-    const unsigned sic = (unsigned) (seg - (unsigned long long) chunk * g.segs_per_chunk);
-    const unsigned it0 = sic * g.iters_per_seg;
-    const unsigned iters_chunk = g.fast_out >> 7;
-    const unsigned n_it = min(g.iters_per_seg, iters_chunk - it0);
-    /* does the drain pass fall off the end of the chunk? (fast_out == chunk_out there) */
-    const bool end_zero = (it0 + n_it == iters_chunk) && (g.fast_out == g.chunk_out);
-    const unsigned n_ld = end_zero ? n_it : n_it + 1u; /* positions that exist in memory */
-    const unsigned nxt_lane = (lane + 1u) & 31u;
-    const unsigned k0 = it0 * FMD_PASS_OUT + lane * 4u;
-
-    const uint4 *__restrict__ src =
-        reinterpret_cast<const uint4 *>(in + (unsigned long long) chunk * g.chunk_stride + 4ull * k0);
-    float *__restrict__ dst = out + (unsigned long long) chunk * g.chunk_out + k0;
-    const uint4 fill = make_uint4(FMD_FILL, FMD_FILL, FMD_FILL, FMD_FILL);
-
-    uint4 ra = __ldg(src), rb;
-    float xa[4] = {0.f, 0.f, 0.f, 0.f}, xb[4];
-
-    /* pass 0: nothing to store yet */
-    rb = (1u < n_ld) ? __ldg(src + 32) : fill;
-    fmd_pass<NTI, NTO, false>(ra, rb, xa, xb, false, dst, lane, nxt_lane, st);
-    src += 32;
-
-    /* passes 1 .. n_it-1 are all real: two per trip so the raw/x registers ping-pong
-     * without moves */
-    unsigned p = 1;
-    for (; p + 1 < n_it; p += 2) {
-        ra = __ldg(src + 32);
-        fmd_pass<NTI, NTO, true>(rb, ra, xb, xa, false, dst, lane, nxt_lane, st);
-        rb = (p + 2 < n_ld) ? __ldg(src + 64) : fill;
-        fmd_pass<NTI, NTO, true>(ra, rb, xa, xb, false, dst + FMD_PASS_OUT, lane, nxt_lane, st);
-        src += 64;
-        dst += 2 * FMD_PASS_OUT;
-    }
-    /* what is left: at most one real pass, then the drain pass (p == n_it) */
-    for (; p <= n_it; ++p) {
-        ra = (p + 1 < n_ld) ? __ldg(src + 32) : fill;
-        fmd_pass<NTI, NTO, true>(rb, ra, xb, xa, (p == n_it) && end_zero, dst, lane, nxt_lane, st);
-        rb = ra;
-        xb[0] = xa[0]; xb[1] = xa[1]; xb[2] = xa[2]; xb[3] = xa[3];
-        src += 32;
-        dst += FMD_PASS_OUT;
-    }
 }
 
 /* -------------------------------------------------------------- exact kernel */
@@ -370,24 +328,202 @@ struct FmdSpillInit {
     }
 };
 
+/* output k of one chunk, op for op */
+__device__ __noinline__ float fmd_exact_output(const uint8_t *cin, unsigned chunk_out, const FmdSections *sec,
+                                               unsigned k) {
+    const long long n_out = chunk_out, nc = 2ll * chunk_out;
+    FmdDemodX dx{cin, nc, n_out, sec};
+    FmdSpillInit si{cin, nc, sec};
+    return fmd_sweep_cone((long long) k, n_out, sec->lout, sec->out, true, dx, si);
+}
+
 /*
- * One thread per output: outputs [k_begin, k_begin + k_count) of every chunk.
+ * Thread `tid` of the exact path: outputs [0, head) and [fast_out, chunk_out) of every chunk
+ * (the chunk heads, where the sweep is not in steady state, and the ragged remainder).
  */
-__global__ void __launch_bounds__(128)
-fmd_exact_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const FmdGeom g,
-                 const FmdSections sec, unsigned k_begin, unsigned k_count) {
-    const unsigned long long tid = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned long long total = (unsigned long long) g.nchunks * k_count;
-    if (tid >= total) return;
-    const unsigned chunk = (unsigned) (tid / k_count);
-    const unsigned k = k_begin + (unsigned) (tid - (unsigned long long) chunk * k_count);
+__device__ __forceinline__ void fmd_exact_thread(const uint8_t *__restrict__ in, float *__restrict__ out,
+                                                 const FmdGeom &g, const FmdSections *sec,
+                                                 unsigned long long tid) {
+    const unsigned per_chunk = g.head + (g.chunk_out - g.fast_out);
+    if (tid >= (unsigned long long) g.nchunks * per_chunk) return;
+    const unsigned chunk = (unsigned) (tid / per_chunk);
+    const unsigned r = (unsigned) (tid - (unsigned long long) chunk * per_chunk);
+    const unsigned k = r < g.head ? r : g.fast_out + (r - g.head);
     if (k >= g.chunk_out) return;
-    const uint8_t *cin = in + (unsigned long long) chunk * g.chunk_stride;
-    const long long n_out = g.chunk_out, nc = 2ll * g.chunk_out;
-    FmdDemodX dx{cin, nc, n_out, &sec};
-    FmdSpillInit si{cin, nc, &sec};
     out[(unsigned long long) chunk * g.chunk_out + k] =
-        fmd_sweep_cone((long long) k, n_out, sec.lout, sec.out, true, dx, si);
+        fmd_exact_output(in + (unsigned long long) chunk * g.chunk_stride, g.chunk_out, sec, k);
+}
+
+/* stand-alone exact kernel: every output of every chunk (geometry: head = chunk_out, fast_out = chunk_out) */
+__global__ void __launch_bounds__(FMD_BLOCK)
+fmd_exact_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const FmdGeom g,
+                 const FmdSections *__restrict__ sec) {
+    fmd_exact_thread(in, out, g, sec, (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+
+/* --------------------------------------------------------------- fast kernel */
+
+#define FMD_FILL 0x7f7f7f7fu /* four bytes that shift to 0.0: the zero extension past a chunk */
+
+/*
+ * One pass of one lane: unpack `cur` (8 complex samples), input lowpass, four
+ * discriminator outputs into xcur; then the output lowpass over the PREVIOUS
+ * pass's xprev (neighbours: next lane's xprev, or lane 0's xcur for lane 31)
+ * and one 16-byte store.  `nxt` is the lane's raw input of the following pass:
+ * lane 0's copy is what lane 31 needs as its input-filter halo.
+ */
+template <int NTI, int NTO, bool STORE>
+__device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint4 &nxt, const float (&xprev)[4],
+                                         float (&xcur)[4], const bool zero_x, float *__restrict__ dst,
+                                         const bool do_store, const unsigned lane, const unsigned nxt_lane,
+                                         const FmdStencil &st) {
+    constexpr int HC = NTI > 1 ? NTI - 1 : 0; /* complex samples needed from the next lane */
+    constexpr int HW = (HC + 1) / 2;          /* ... as 4-byte words (2 complex each)      */
+    constexpr int NB = NTO - 1;               /* discriminator outputs needed from the next lane */
+
+    /* biased words: own four, then the halo from the next lane (lane 31: lane 0's next pass) */
+    uint32_t w[6];
+    w[0] = fmd_bias_bytes(cur.x);
+    w[1] = fmd_bias_bytes(cur.y);
+    w[2] = fmd_bias_bytes(cur.z);
+    w[3] = fmd_bias_bytes(cur.w);
+    w[4] = w[5] = 0u;
+    if (HW >= 1) w[4] = fmd_bias_bytes(__shfl_sync(0xffffffffu, lane == 0 ? nxt.x : cur.x, nxt_lane));
+    if (HW >= 2) w[5] = fmd_bias_bytes(__shfl_sync(0xffffffffu, lane == 0 ? nxt.y : cur.y, nxt_lane));
+
+    /* vi[k] = (I_k, I_{k+4}), vq[k] = (Q_k, Q_{k+4}): complex samples k and k+4 of this lane feed
+     * outputs j and j+2, so every later step runs two outputs per instruction (FADD2/FFMA2) */
+    constexpr int NK = 4 + HC;
+    fmd_f2 vi[NK], vq[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        if (k & 1) {
+            vi[k] = fmd_bytes_to_f2<2>(w[k >> 1], w[(k >> 1) + 2]);
+            vq[k] = fmd_bytes_to_f2<3>(w[k >> 1], w[(k >> 1) + 2]);
+        } else {
+            vi[k] = fmd_bytes_to_f2<0>(w[k >> 1], w[(k >> 1) + 2]);
+            vq[k] = fmd_bytes_to_f2<1>(w[k >> 1], w[(k >> 1) + 2]);
+        }
+    }
+
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { /* outputs j and j+2 */
+        fmd_f2 a, b, c, d;
+        if (NTI == 0) {
+            a = vi[2 * j]; b = vq[2 * j]; c = vi[2 * j + 1]; d = vq[2 * j + 1];
+        } else {
+            a = c = fmd_bc(st.dci);
+            b = d = fmd_bc(st.dcq);
+#pragma unroll
+            for (int t = 0; t < NTI; ++t) {
+                const fmd_f2 tap = fmd_bc(st.tin[t]);
+                a = fmd_fma2(tap, vi[2 * j + t], a);
+                b = fmd_fma2(tap, vq[2 * j + t], b);
+                c = fmd_fma2(tap, vi[2 * j + 1 + t], c);
+                d = fmd_fma2(tap, vq[2 * j + 1 + t], d);
+            }
+        }
+        /* s0 * conj(s1).  The fused forms keep the reference's signed-zero results: a sum of
+         * two exact-zero products takes the same sign fused or not. */
+        const fmd_f2 re = fmd_fma2(a, c, fmd_mul2(b, d));
+        const fmd_f2 im = fmd_fma2(fmd_neg2(a), d, fmd_mul2(b, c));
+        fmd_atan2_x2(im, re, xcur[j], xcur[j + 2]);
+    }
+    if (zero_x) { /* past the end of the chunk the discriminator output is exactly 0 */
+        xcur[0] = 0.0f; xcur[1] = 0.0f; xcur[2] = 0.0f; xcur[3] = 0.0f;
+    }
+
+    float xn[4 + (NB > 0 ? NB : 1)];
+    xn[0] = xprev[0]; xn[1] = xprev[1]; xn[2] = xprev[2]; xn[3] = xprev[3];
+#pragma unroll
+    for (int t = 0; t < NB; ++t)
+        xn[4 + t] = __shfl_sync(0xffffffffu, lane == 0 ? xcur[t] : xprev[t], nxt_lane);
+    if (STORE) {
+        float4 y;
+        float *yy = reinterpret_cast<float *>(&y);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float acc = st.dco;
+#pragma unroll
+            for (int t = 0; t < NTO; ++t) acc = fmaf(st.tout[t], xn[j + t], acc);
+            yy[j] = acc;
+        }
+        if (do_store) *reinterpret_cast<float4 *>(dst) = y;
+    }
+}
+
+/*
+ * A warp owns one segment: n_it passes of 128 outputs (512 B in, 512 B out per pass),
+ * plus one "drain" pass that only feeds the last real pass its neighbours.  If the
+ * segment ends at the end of a chunk the drain pass is the zero extension (no load,
+ * x = 0); otherwise it re-reads the first 512 B of what follows.
+ */
+template <int NTI, int NTO>
+__global__ void __launch_bounds__(FMD_BLOCK, (NTI == 0 ? 8 : 5))
+fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const FmdGeom g, const FmdStencil st,
+                const FmdSections *__restrict__ sec) {
+    /* The first CTAs do the op-for-op work (chunk heads, ragged remainder): they start with the
+     * grid and finish long before the streaming CTAs do, so that work costs no extra launch and
+     * hides behind the bandwidth-bound part. */
+    if (blockIdx.x < g.exact_blocks) {
+        fmd_exact_thread(in, out, g, sec, (unsigned long long) blockIdx.x * FMD_BLOCK + threadIdx.x);
+        return;
+    }
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long seg =
+        (unsigned long long) (blockIdx.x - g.exact_blocks) * FMD_WARPS + (threadIdx.x >> 5);
+    if (seg >= (unsigned long long) g.nchunks * g.segs_per_chunk) return;
+    const unsigned chunk = (unsigned) (seg / g.segs_per_chunk);
+    const unsigned sic = (unsigned) (seg - (unsigned long long) chunk * g.segs_per_chunk);
+    const unsigned it0 = sic * g.iters_per_seg;
+    const unsigned iters_chunk = g.fast_out >> 7;
+    const unsigned n_it = min(g.iters_per_seg, iters_chunk - it0);
+    /* does the drain pass fall off the end of the chunk? (fast_out == chunk_out there) */
+    const bool end_zero = (it0 + n_it == iters_chunk) && (g.fast_out == g.chunk_out);
+    const unsigned n_ld = end_zero ? n_it : n_it + 1u; /* positions that exist in memory */
+    const unsigned nxt_lane = (lane + 1u) & 31u;
+    const unsigned k0 = it0 * FMD_PASS_OUT + lane * 4u;
+
+    const uint4 *__restrict__ src =
+        reinterpret_cast<const uint4 *>(in + (unsigned long long) chunk * g.chunk_stride + 4ull * k0);
+    float *__restrict__ dst = out + (unsigned long long) chunk * g.chunk_out + k0;
+    const uint4 fill = make_uint4(FMD_FILL, FMD_FILL, FMD_FILL, FMD_FILL);
+
+    uint4 ra = __ldg(src), rb;
+    float xa[4] = {0.f, 0.f, 0.f, 0.f}, xb[4];
+
+    /* pass 0: nothing to store yet */
+    rb = (1u < n_ld) ? __ldg(src + 32) : fill;
+    fmd_pass<NTI, NTO, false>(ra, rb, xa, xb, false, dst, false, lane, nxt_lane, st);
+    src += 32;
+
+    /* the chunk head [0, head) belongs to the exact path: those lanes of the very first store
+     * of a chunk's first segment keep quiet */
+    bool keep = !(it0 == 0 && k0 < g.head);
+
+    /* passes 1 .. n_it-1 are all real: two per trip so the raw/x registers ping-pong
+     * without moves */
+    unsigned p = 1;
+    for (; p + 1 < n_it; p += 2) {
+        ra = __ldg(src + 32);
+        fmd_pass<NTI, NTO, true>(rb, ra, xb, xa, false, dst, keep, lane, nxt_lane, st);
+        rb = (p + 2 < n_ld) ? __ldg(src + 64) : fill;
+        fmd_pass<NTI, NTO, true>(ra, rb, xa, xb, false, dst + FMD_PASS_OUT, true, lane, nxt_lane, st);
+        keep = true;
+        src += 64;
+        dst += 2 * FMD_PASS_OUT;
+    }
+    /* what is left: at most one real pass, then the drain pass (p == n_it) */
+    for (; p <= n_it; ++p) {
+        ra = (p + 1 < n_ld) ? __ldg(src + 32) : fill;
+        fmd_pass<NTI, NTO, true>(rb, ra, xb, xa, (p == n_it) && end_zero, dst, keep, lane, nxt_lane, st);
+        keep = true;
+        rb = ra;
+        xb[0] = xa[0]; xb[1] = xa[1]; xb[2] = xa[2]; xb[3] = xa[3];
+        src += 32;
+        dst += FMD_PASS_OUT;
+    }
 }
 
 #endif /* FMD_KERNELS_CUH */

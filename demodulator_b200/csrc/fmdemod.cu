@@ -58,6 +58,7 @@ struct fmd_ctx {
     int device = 0;
     unsigned lin = 0, lout = 0;
     FmdSections sec;
+    FmdSections *d_sec = nullptr; /* device copy, read by the exact path */
     FmdStencil st;
     unsigned nti = 0, nto = 0;
     unsigned head = 0; /* outputs at the start of every chunk that are not in steady state */
@@ -205,6 +206,11 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
         fmd_destroy(c);
         return fmd_set_error(FMD_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
+    if (cudaMalloc(&c->d_sec, sizeof(FmdSections)) != cudaSuccess ||
+        cudaMemcpy(c->d_sec, &c->sec, sizeof(FmdSections), cudaMemcpyHostToDevice) != cudaSuccess) {
+        fmd_destroy(c);
+        return fmd_set_error(FMD_ECUDA, "coefficient upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     *out = c;
     return FMD_OK;
 }
@@ -234,6 +240,7 @@ extern "C" void fmd_destroy(fmd_ctx *c) {
         for (unsigned i = 0; i < 2 * c->pev_cap; ++i) cudaEventDestroy(c->pev[i]);
         delete[] c->pev;
     }
+    if (c->d_sec) cudaFree(c->d_sec);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_k) cudaStreamDestroy(c->s_k);
     if (c->s_out) cudaStreamDestroy(c->s_out);
@@ -286,7 +293,7 @@ extern "C" size_t fmd_out_count(const fmd_ctx *c, size_t nbytes) {
     return nbytes >> 2; /* whole chunks give B/4 each; the ragged tail gives r/4 */
 }
 
-typedef void (*fast_fn)(const uint8_t *, float *, const FmdGeom, const FmdStencil);
+typedef void (*fast_fn)(const uint8_t *, float *, const FmdGeom, const FmdStencil, const FmdSections *);
 
 template <int NTI>
 static fast_fn pick_out(unsigned nto) {
@@ -312,13 +319,16 @@ static fast_fn pick_fast(unsigned nti, unsigned nto) {
     }
 }
 
-static int launch_exact(fmd_ctx *c, const uint8_t *d_in, float *d_out, const FmdGeom &g, unsigned k_begin,
-                        unsigned k_count, cudaStream_t s) {
-    if (!k_count || !g.nchunks) return FMD_OK;
-    const unsigned long long total = (unsigned long long) g.nchunks * k_count;
-    const unsigned long long blocks = (total + 127) / 128;
+/* every output of every chunk through the op-for-op path */
+static int launch_exact(fmd_ctx *c, const uint8_t *d_in, float *d_out, FmdGeom g, cudaStream_t s) {
+    if (!g.chunk_out || !g.nchunks) return FMD_OK;
+    g.head = g.chunk_out;
+    g.fast_out = g.chunk_out;
+    const unsigned long long total = (unsigned long long) g.nchunks * g.chunk_out;
+    const unsigned long long blocks = (total + FMD_BLOCK - 1) / FMD_BLOCK;
     if (blocks > 0x7fffffffull) return fmd_set_error(FMD_EINVAL, "exact kernel grid too large");
-    fmd_exact_kernel<<<(unsigned) blocks, 128, 0, s>>>(d_in, d_out, g, c->sec, k_begin, k_count);
+    g.exact_blocks = (unsigned) blocks;
+    fmd_exact_kernel<<<(unsigned) blocks, FMD_BLOCK, 0, s>>>(d_in, d_out, g, c->d_sec);
     FMD_CUDA(cudaGetLastError());
     c->launches++;
     return FMD_OK;
@@ -335,6 +345,8 @@ static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned
     g.fast_out = 0;
     g.iters_per_seg = 1;
     g.segs_per_chunk = 1;
+    g.head = 0;
+    g.exact_blocks = 0;
 
     fast_fn fn = pick_fast(c->nti, c->nto);
     const bool aligned = ((uintptr_t) d_in % 16 == 0) && ((uintptr_t) d_out % 16 == 0) && (stride % 16 == 0) &&
@@ -346,7 +358,7 @@ static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned
                                   : (chunk_out >= 2 * FMD_PASS_OUT ? (chunk_out / FMD_PASS_OUT - 1) * FMD_PASS_OUT : 0);
     const bool fast_ok = fn && aligned && !(c->cfg.flags & FMD_FLAG_EXACT) && fast_out >= FMD_PASS_OUT &&
                          fast_out > c->head;
-    if (!fast_ok) return launch_exact(c, d_in, d_out, g, 0, chunk_out, s);
+    if (!fast_ok) return launch_exact(c, d_in, d_out, g, s);
 
     g.fast_out = fast_out;
     const unsigned iters_chunk = g.fast_out >> 7;
@@ -360,7 +372,11 @@ static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned
     g.iters_per_seg = ips;
     g.segs_per_chunk = (iters_chunk + ips - 1) / ips;
     const unsigned long long nseg = (unsigned long long) g.segs_per_chunk * nchunks;
-    const unsigned long long blocks = (nseg + FMD_WARPS - 1) / FMD_WARPS;
+    /* chunk heads and the ragged remainder ride along as the first CTAs of the same launch */
+    g.head = c->head;
+    const unsigned long long exact_threads = (unsigned long long) nchunks * (g.head + (chunk_out - fast_out));
+    g.exact_blocks = (unsigned) ((exact_threads + FMD_BLOCK - 1) / FMD_BLOCK);
+    const unsigned long long blocks = (nseg + FMD_WARPS - 1) / FMD_WARPS + g.exact_blocks;
     if (blocks > 0x7fffffffull) return fmd_set_error(FMD_EINVAL, "fast kernel grid too large");
     cudaEvent_t *pe = nullptr;
     if (c->profile) {
@@ -371,14 +387,11 @@ static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned
         pe = &c->pev[2 * c->pev_used++];
         FMD_CUDA(cudaEventRecord(pe[0], s));
     }
-    fn<<<(unsigned) blocks, FMD_BLOCK, 0, s>>>(d_in, d_out, g, c->st);
+    fn<<<(unsigned) blocks, FMD_BLOCK, 0, s>>>(d_in, d_out, g, c->st, c->d_sec);
     FMD_CUDA(cudaGetLastError());
     if (pe) FMD_CUDA(cudaEventRecord(pe[1], s));
     c->launches++;
-    /* chunk heads (sweep not in steady state, -L arena spill) and ragged remainder */
-    int rc = launch_exact(c, d_in, d_out, g, 0, c->head < chunk_out ? c->head : chunk_out, s);
-    if (!rc && g.fast_out < chunk_out) rc = launch_exact(c, d_in, d_out, g, g.fast_out, chunk_out - g.fast_out, s);
-    return rc;
+    return FMD_OK;
 }
 
 extern "C" int fmd_demod_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, float *d_out, void *stream) {

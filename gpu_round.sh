@@ -1,0 +1,31 @@
+#!/bin/bash
+# one GPU-box session: parity tests, benches, ncu captures -> gpurun_out/
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -30 > gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
+for c in cfg2 cfg1 cfg3; do
+  timeout 300 python bench.py --steps 10 --warmup 3 --config $c $( [ $c != cfg2 ] && echo --no-cpu ) > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err
+  python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/bench_$c.json"))
+    print("$c", d["value"], "MS/s  roofline", d["roofline"]["frac"], "kernel_ms", d["roofline"]["kernel_ms_avg"], "share", d["roofline"]["kernel_share_of_step"], "e2e", d["e2e"]["value"], "cpu", d["cpu_baseline"] and d["cpu_baseline"]["value"], "clk", d["clocks"])
+except Exception as e:
+    print("$c failed", e); print(open("gpurun_out/bench_$c.err").read()[-2000:])
+PY
+done
+if [ "$1" = "ref" ]; then
+  timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json
+fi
+if [ "$2" = "ncu" ]; then
+  CMD="python bench.py --steps 2 --warmup 3 --no-cpu"
+  $CMD > gpurun_out/plain.log 2>&1 && \
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
+  $CMD > gpurun_out/plain2.log 2>&1 && \
+  ncu --set full --clock-control none --import-source on -k regex:fmd_fast -s 30 -c 2 -f -o gpurun_out/prof_cfg2 $CMD > gpurun_out/ncu_full.log 2>&1
+  tail -3 gpurun_out/ncu_full.log
+  CMD1="python bench.py --steps 2 --warmup 3 --no-cpu --config cfg1"
+  $CMD1 > gpurun_out/plain3.log 2>&1 && \
+  ncu --set full --clock-control none --import-source on -k regex:fmd_fast -s 30 -c 2 -f -o gpurun_out/prof_cfg1 $CMD1 > gpurun_out/ncu_full1.log 2>&1
+  tail -3 gpurun_out/ncu_full1.log
+fi
