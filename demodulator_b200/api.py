@@ -32,7 +32,8 @@ class _Config(C.Structure):
 
 
 def lib_path() -> str:
-    return os.path.join(HERE, "lib", "libfmdemod.so")
+    # FMD_LIB: kernel-tuning experiments point this at an alternative build of the same library
+    return os.environ.get("FMD_LIB") or os.path.join(HERE, "lib", "libfmdemod.so")
 
 
 _lib = None

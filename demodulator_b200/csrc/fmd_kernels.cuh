@@ -370,11 +370,11 @@ fmd_exact_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const 
  * One pass of one lane: unpack `cur` (8 complex samples), input lowpass, four
  * discriminator outputs into xcur; then the output lowpass over the PREVIOUS
  * pass's xprev (neighbours: next lane's xprev, or lane 0's xcur for lane 31)
- * and one 16-byte store.  `nxt` is the lane's raw input of the following pass:
- * lane 0's copy is what lane 31 needs as its input-filter halo.
+ * and one 16-byte store.  `nxt` is the first 8 bytes of the lane's raw input of the
+ * following pass: lane 0's copy is what lane 31 needs as its input-filter halo.
  */
 template <int NTI, int NTO, bool STORE>
-__device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint4 &nxt, const float (&xprev)[4],
+__device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, const float (&xprev)[4],
                                          float (&xcur)[4], const bool zero_x, float *__restrict__ dst,
                                          const bool do_store, const unsigned lane, const unsigned nxt_lane,
                                          const FmdStencil &st) {
@@ -382,6 +382,41 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint4 &nxt, con
     constexpr int HW = (HC + 1) / 2;          /* ... as 4-byte words (2 complex each)      */
     constexpr int NB = NTO - 1;               /* discriminator outputs needed from the next lane */
 
+#ifdef FMD_SCALAR
+    float f[16 + 4 * (HW > 0 ? HW : 1)];
+    fmd_unpack_word(cur.x, f + 0);
+    fmd_unpack_word(cur.y, f + 4);
+    fmd_unpack_word(cur.z, f + 8);
+    fmd_unpack_word(cur.w, f + 12);
+    if (HW >= 1) {
+        const uint32_t h = __shfl_sync(0xffffffffu, lane == 0 ? nxt.x : cur.x, nxt_lane);
+        fmd_unpack_word(h, f + 16);
+    }
+    if (HW >= 2) {
+        const uint32_t h = __shfl_sync(0xffffffffu, lane == 0 ? nxt.y : cur.y, nxt_lane);
+        fmd_unpack_word(h, f + 20);
+    }
+
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float a, b, c, d;
+        if (NTI == 0) {
+            a = f[4 * j + 0]; b = f[4 * j + 1]; c = f[4 * j + 2]; d = f[4 * j + 3];
+        } else {
+            a = st.dci; b = st.dcq; c = st.dci; d = st.dcq;
+#pragma unroll
+            for (int t = 0; t < NTI; ++t) {
+                a = fmaf(st.tin[t], f[4 * j + 2 * t + 0], a);
+                b = fmaf(st.tin[t], f[4 * j + 2 * t + 1], b);
+                c = fmaf(st.tin[t], f[4 * j + 2 * t + 2], c);
+                d = fmaf(st.tin[t], f[4 * j + 2 * t + 3], d);
+            }
+        }
+        const float re = fmaf(a, c, b * d);
+        const float im = fmaf(-a, d, b * c);
+        xcur[j] = fmd_atan2(im, re);
+    }
+#else
     /* biased words: own four, then the halo from the next lane (lane 31: lane 0's next pass) */
     uint32_t w[6];
     w[0] = fmd_bias_bytes(cur.x);
@@ -430,6 +465,7 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint4 &nxt, con
         const fmd_f2 im = fmd_fma2(fmd_neg2(a), d, fmd_mul2(b, c));
         fmd_atan2_x2(im, re, xcur[j], xcur[j + 2]);
     }
+#endif
     if (zero_x) { /* past the end of the chunk the discriminator output is exactly 0 */
         xcur[0] = 0.0f; xcur[1] = 0.0f; xcur[2] = 0.0f; xcur[3] = 0.0f;
     }
@@ -453,14 +489,49 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint4 &nxt, con
     }
 }
 
+/* ---- cp.async (LDGSTS) ring: global -> shared without staging registers ---- */
+__device__ __forceinline__ void fmd_cp_async16(uint32_t smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void fmd_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void fmd_cp_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint4 fmd_lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 fmd_lds64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void fmd_sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+#ifndef FMD_MINB
+#define FMD_MINB(NTI) ((NTI) == 0 ? 5 : 4) /* resident CTAs per SM the register budget is cut for */
+#endif
+#ifndef FMD_STAGES
+#define FMD_STAGES 8 /* ring depth per lane (power of two): 16 B x FMD_STAGES in flight or landed */
+#endif
+
 /*
  * A warp owns one segment: n_it passes of 128 outputs (512 B in, 512 B out per pass),
  * plus one "drain" pass that only feeds the last real pass its neighbours.  If the
  * segment ends at the end of a chunk the drain pass is the zero extension (no load,
  * x = 0); otherwise it re-reads the first 512 B of what follows.
+ *
+ * Input reaches the lanes through a per-lane ring in shared memory filled by cp.async
+ * (LDGSTS, L2-only): every lane copies its own 16 bytes FMD_STAGES-1 passes ahead and
+ * reads them back with one LDS.128, so the loads in flight per SM do not depend on the
+ * register budget or on occupancy, and no lane ever reads another lane's slot (no barrier).
  */
 template <int NTI, int NTO>
-__global__ void __launch_bounds__(FMD_BLOCK, (NTI == 0 ? 8 : 5))
+__global__ void __launch_bounds__(FMD_BLOCK, FMD_MINB(NTI))
 fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const FmdGeom g, const FmdStencil st,
                 const FmdSections *__restrict__ sec) {
     /* The first CTAs do the op-for-op work (chunk heads, ragged remainder): they start with the
@@ -470,6 +541,11 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
         fmd_exact_thread(in, out, g, sec, (unsigned long long) blockIdx.x * FMD_BLOCK + threadIdx.x);
         return;
     }
+    constexpr int S = FMD_STAGES;
+    constexpr bool HALO = NTI > 1;               /* lane 31 needs lane 0's next pass */
+    constexpr int PENDING = HALO ? S - 2 : S - 1; /* groups allowed in flight at the wait */
+    __shared__ uint4 ring[S * FMD_BLOCK];
+
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long seg =
         (unsigned long long) (blockIdx.x - g.exact_blocks) * FMD_WARPS + (threadIdx.x >> 5);
@@ -485,45 +561,62 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     const unsigned nxt_lane = (lane + 1u) & 31u;
     const unsigned k0 = it0 * FMD_PASS_OUT + lane * 4u;
 
-    const uint4 *__restrict__ src =
-        reinterpret_cast<const uint4 *>(in + (unsigned long long) chunk * g.chunk_stride + 4ull * k0);
+    const uint8_t *__restrict__ src = in + (unsigned long long) chunk * g.chunk_stride + 4ull * k0;
     float *__restrict__ dst = out + (unsigned long long) chunk * g.chunk_out + k0;
     const uint4 fill = make_uint4(FMD_FILL, FMD_FILL, FMD_FILL, FMD_FILL);
+    const uint32_t sbase = (uint32_t) __cvta_generic_to_shared(&ring[threadIdx.x]);
+    constexpr uint32_t SLOT = FMD_BLOCK * 16u;
 
-    uint4 ra = __ldg(src), rb;
+    /* position q of the segment -> ring slot q % S; past the data: the zero extension */
+    auto issue = [&](unsigned q) {
+        if (q < n_ld) fmd_cp_async16(sbase + (q & (S - 1)) * SLOT, src + 512ull * q);
+        fmd_cp_commit();
+    };
+#pragma unroll
+    for (int q = 0; q < S - 1; ++q) issue((unsigned) q);
+
     float xa[4] = {0.f, 0.f, 0.f, 0.f}, xb[4];
-
-    /* pass 0: nothing to store yet */
-    rb = (1u < n_ld) ? __ldg(src + 32) : fill;
-    fmd_pass<NTI, NTO, false>(ra, rb, xa, xb, false, dst, false, lane, nxt_lane, st);
-    src += 32;
-
+    uint4 cur;
+    uint2 nx = make_uint2(FMD_FILL, FMD_FILL);
     /* the chunk head [0, head) belongs to the exact path: those lanes of the very first store
      * of a chunk's first segment keep quiet */
     bool keep = !(it0 == 0 && k0 < g.head);
 
-    /* passes 1 .. n_it-1 are all real: two per trip so the raw/x registers ping-pong
-     * without moves */
+#define FMD_FETCH(P)                                                     \
+    issue((P) + S - 1);                                                  \
+    fmd_cp_wait<PENDING>();                                              \
+    cur = fmd_lds128(sbase + ((P) & (S - 1)) * SLOT);                    \
+    if (HALO) nx = fmd_lds64(sbase + (((P) + 1) & (S - 1)) * SLOT);
+
+    /* pass 0: nothing to store yet */
+    FMD_FETCH(0u)
+    if (HALO && 1u >= n_ld) nx = make_uint2(FMD_FILL, FMD_FILL);
+    fmd_pass<NTI, NTO, false>(cur, nx, xa, xb, false, dst, false, lane, nxt_lane, st);
+
+    /* passes 1 .. n_it-2 are real and have a real successor: two per trip so the x registers
+     * ping-pong without moves */
     unsigned p = 1;
-    for (; p + 1 < n_it; p += 2) {
-        ra = __ldg(src + 32);
-        fmd_pass<NTI, NTO, true>(rb, ra, xb, xa, false, dst, keep, lane, nxt_lane, st);
-        rb = (p + 2 < n_ld) ? __ldg(src + 64) : fill;
-        fmd_pass<NTI, NTO, true>(ra, rb, xa, xb, false, dst + FMD_PASS_OUT, true, lane, nxt_lane, st);
+    for (; p + 2 < n_it; p += 2) {
+        FMD_FETCH(p)
+        fmd_pass<NTI, NTO, true>(cur, nx, xb, xa, false, dst, keep, lane, nxt_lane, st);
+        FMD_FETCH(p + 1)
+        fmd_pass<NTI, NTO, true>(cur, nx, xa, xb, false, dst + FMD_PASS_OUT, true, lane, nxt_lane, st);
         keep = true;
-        src += 64;
         dst += 2 * FMD_PASS_OUT;
     }
-    /* what is left: at most one real pass, then the drain pass (p == n_it) */
+    /* what is left: one or two real passes, then the drain pass (p == n_it); positions past
+     * the data are the zero extension */
     for (; p <= n_it; ++p) {
-        ra = (p + 1 < n_ld) ? __ldg(src + 32) : fill;
-        fmd_pass<NTI, NTO, true>(rb, ra, xb, xa, (p == n_it) && end_zero, dst, keep, lane, nxt_lane, st);
+        FMD_FETCH(p)
+        if (p >= n_ld) cur = fill;
+        if (HALO && p + 1 >= n_ld) nx = make_uint2(FMD_FILL, FMD_FILL);
+        fmd_pass<NTI, NTO, true>(cur, nx, xb, xa, (p == n_it) && end_zero, dst, keep, lane, nxt_lane, st);
         keep = true;
-        rb = ra;
         xb[0] = xa[0]; xb[1] = xa[1]; xb[2] = xa[2]; xb[3] = xa[3];
-        src += 32;
         dst += FMD_PASS_OUT;
     }
+#undef FMD_FETCH
+    fmd_cp_wait<0>();
 }
 
 #endif /* FMD_KERNELS_CUH */

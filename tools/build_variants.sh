@@ -1,0 +1,16 @@
+#!/bin/bash
+# Build tuning variants of libfmdemod.so into variants/<name>/libfmdemod.so (kernel experiments).
+# usage: tools/build_variants.sh name:"-DFMD_STAGES=4 -DFMD_ATAN_TERMS=6" ...
+set -e
+cd "$(dirname "$0")/.."
+NVCC=/usr/local/cuda/bin/nvcc
+for spec in "$@"; do
+  name="${spec%%:*}"; flags="${spec#*:}"
+  d=variants/$name; mkdir -p $d
+  gcc -O2 -std=gnu99 -fPIC -ffp-contract=off -Iinclude -Idemodulator_b200/csrc -c -o $d/fmd_design.o demodulator_b200/csrc/fmd_design.c
+  $NVCC -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC $flags -Iinclude -Idemodulator_b200/csrc \
+      -c -o $d/fmdemod.o demodulator_b200/csrc/fmdemod.cu
+  $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $d/libfmdemod.so $d/fmdemod.o $d/fmd_design.o -lm
+  rm -f $d/*.o
+  echo "built $d ($flags)"
+done
