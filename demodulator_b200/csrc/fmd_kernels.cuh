@@ -373,7 +373,7 @@ fmd_exact_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const 
  * and one 16-byte store.  `nxt` is the first 8 bytes of the lane's raw input of the
  * following pass: lane 0's copy is what lane 31 needs as its input-filter halo.
  */
-template <int NTI, int NTO, bool STORE>
+template <int NTI, int NTO, bool STORE, bool LITE = false>
 __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, const float (&xprev)[4],
                                          float (&xcur)[4], const bool zero_x, float *__restrict__ dst,
                                          const bool do_store, const unsigned lane, const unsigned nxt_lane,
@@ -443,7 +443,7 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, con
     }
 
 #pragma unroll
-    for (int j = 0; j < 2; ++j) { /* outputs j and j+2 */
+    for (int j = 0; j < (LITE ? 1 : 2); ++j) { /* outputs j and j+2 */
         fmd_f2 a, b, c, d;
         if (NTI == 0) {
             a = vi[2 * j]; b = vq[2 * j]; c = vi[2 * j + 1]; d = vq[2 * j + 1];
@@ -466,6 +466,7 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, con
         fmd_atan2_x2(im, re, xcur[j], xcur[j + 2]);
     }
 #endif
+    if (LITE) xcur[1] = xcur[3] = 0.0f; /* drain pass: only lane 0's first output is ever read */
     if (zero_x) { /* past the end of the chunk the discriminator output is exactly 0 */
         xcur[0] = 0.0f; xcur[1] = 0.0f; xcur[2] = 0.0f; xcur[3] = 0.0f;
     }
@@ -489,34 +490,8 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, con
     }
 }
 
-/* ---- cp.async (LDGSTS) ring: global -> shared without staging registers ---- */
-__device__ __forceinline__ void fmd_cp_async16(uint32_t smem_dst, const void *gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void fmd_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void fmd_cp_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ uint4 fmd_lds128(uint32_t a) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ uint2 fmd_lds64(uint32_t a) {
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void fmd_sts128(uint32_t a, uint4 v) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
 #ifndef FMD_MINB
 #define FMD_MINB(NTI) ((NTI) == 0 ? 5 : 4) /* resident CTAs per SM the register budget is cut for */
-#endif
-#ifndef FMD_STAGES
-#define FMD_STAGES 8 /* ring depth per lane (power of two): 16 B x FMD_STAGES in flight or landed */
 #endif
 
 /*
@@ -525,10 +500,9 @@ __device__ __forceinline__ void fmd_sts128(uint32_t a, uint4 v) {
  * segment ends at the end of a chunk the drain pass is the zero extension (no load,
  * x = 0); otherwise it re-reads the first 512 B of what follows.
  *
- * Input reaches the lanes through a per-lane ring in shared memory filled by cp.async
- * (LDGSTS, L2-only): every lane copies its own 16 bytes FMD_STAGES-1 passes ahead and
- * reads them back with one LDS.128, so the loads in flight per SM do not depend on the
- * register budget or on occupancy, and no lane ever reads another lane's slot (no barrier).
+ * Input is prefetched three passes ahead into a ring of four 16-byte register quads
+ * (one LDG.128 per pass, no staging instructions); the loop is unrolled by four so that
+ * the ring and the x ping-pong are register renames, not moves.
  */
 template <int NTI, int NTO>
 __global__ void __launch_bounds__(FMD_BLOCK, FMD_MINB(NTI))
@@ -541,17 +515,13 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
         fmd_exact_thread(in, out, g, sec, (unsigned long long) blockIdx.x * FMD_BLOCK + threadIdx.x);
         return;
     }
-    constexpr int S = FMD_STAGES;
-    constexpr bool HALO = NTI > 1;               /* lane 31 needs lane 0's next pass */
-    constexpr int PENDING = HALO ? S - 2 : S - 1; /* groups allowed in flight at the wait */
-    __shared__ uint4 ring[S * FMD_BLOCK];
-
+    constexpr bool HALO = NTI > 1; /* lane 31 needs lane 0's next pass */
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned long long seg =
-        (unsigned long long) (blockIdx.x - g.exact_blocks) * FMD_WARPS + (threadIdx.x >> 5);
-    if (seg >= (unsigned long long) g.nchunks * g.segs_per_chunk) return;
-    const unsigned chunk = (unsigned) (seg / g.segs_per_chunk);
-    const unsigned sic = (unsigned) (seg - (unsigned long long) chunk * g.segs_per_chunk);
+    /* the host keeps nchunks * segs_per_chunk below 2^32 per launch */
+    const unsigned seg = (blockIdx.x - g.exact_blocks) * FMD_WARPS + (threadIdx.x >> 5);
+    if (seg >= g.nchunks * g.segs_per_chunk) return;
+    const unsigned chunk = seg / g.segs_per_chunk;
+    const unsigned sic = seg - chunk * g.segs_per_chunk;
     const unsigned it0 = sic * g.iters_per_seg;
     const unsigned iters_chunk = g.fast_out >> 7;
     const unsigned n_it = min(g.iters_per_seg, iters_chunk - it0);
@@ -561,62 +531,61 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     const unsigned nxt_lane = (lane + 1u) & 31u;
     const unsigned k0 = it0 * FMD_PASS_OUT + lane * 4u;
 
-    const uint8_t *__restrict__ src = in + (unsigned long long) chunk * g.chunk_stride + 4ull * k0;
+    /* src[32 * q] is this lane's 16 bytes of position q; dst[128 * q] its 4 outputs */
+    const uint4 *__restrict__ src =
+        reinterpret_cast<const uint4 *>(in + (unsigned long long) chunk * g.chunk_stride + 4ull * k0);
     float *__restrict__ dst = out + (unsigned long long) chunk * g.chunk_out + k0;
-    const uint4 fill = make_uint4(FMD_FILL, FMD_FILL, FMD_FILL, FMD_FILL);
-    const uint32_t sbase = (uint32_t) __cvta_generic_to_shared(&ring[threadIdx.x]);
-    constexpr uint32_t SLOT = FMD_BLOCK * 16u;
+    const uint2 fill2 = make_uint2(FMD_FILL, FMD_FILL);
 
-    /* position q of the segment -> ring slot q % S; past the data: the zero extension */
-    auto issue = [&](unsigned q) {
-        if (q < n_ld) fmd_cp_async16(sbase + (q & (S - 1)) * SLOT, src + 512ull * q);
-        fmd_cp_commit();
-    };
-#pragma unroll
-    for (int q = 0; q < S - 1; ++q) issue((unsigned) q);
+    uint4 r0, r1, r2, r3, rd;
+    r0 = __ldg(src);
+    r1 = r2 = r3 = rd = r0;
+    if (1u < n_ld) r1 = __ldg(src + 32);
+    if (2u < n_ld) r2 = __ldg(src + 64);
+    float x0[4], x1[4] = {0.f, 0.f, 0.f, 0.f}, xd[4];
+    /* store predicates of the first two passes: pass 0 has nothing to store; the first store of
+     * a chunk's first segment skips the chunk head [0, head), which belongs to the exact path */
+    bool st_a = false, st_b = !(it0 == 0 && k0 < g.head);
 
-    float xa[4] = {0.f, 0.f, 0.f, 0.f}, xb[4];
-    uint4 cur;
-    uint2 nx = make_uint2(FMD_FILL, FMD_FILL);
-    /* the chunk head [0, head) belongs to the exact path: those lanes of the very first store
-     * of a chunk's first segment keep quiet */
-    bool keep = !(it0 == 0 && k0 < g.head);
-
-#define FMD_FETCH(P)                                                     \
-    issue((P) + S - 1);                                                  \
-    fmd_cp_wait<PENDING>();                                              \
-    cur = fmd_lds128(sbase + ((P) & (S - 1)) * SLOT);                    \
-    if (HALO) nx = fmd_lds64(sbase + (((P) + 1) & (S - 1)) * SLOT);
-
-    /* pass 0: nothing to store yet */
-    FMD_FETCH(0u)
-    if (HALO && 1u >= n_ld) nx = make_uint2(FMD_FILL, FMD_FILL);
-    fmd_pass<NTI, NTO, false>(cur, nx, xa, xb, false, dst, false, lane, nxt_lane, st);
-
-    /* passes 1 .. n_it-2 are real and have a real successor: two per trip so the x registers
-     * ping-pong without moves */
-    unsigned p = 1;
-    for (; p + 2 < n_it; p += 2) {
-        FMD_FETCH(p)
-        fmd_pass<NTI, NTO, true>(cur, nx, xb, xa, false, dst, keep, lane, nxt_lane, st);
-        FMD_FETCH(p + 1)
-        fmd_pass<NTI, NTO, true>(cur, nx, xa, xb, false, dst + FMD_PASS_OUT, true, lane, nxt_lane, st);
-        keep = true;
-        dst += 2 * FMD_PASS_OUT;
+#define FMD_STEP(U, CUR, NXT, LOADINTO, XPREV, XCUR, STOREPRED)                                       \
+    {                                                                                                 \
+        const unsigned p = base + (U);                                                                \
+        if (p >= n_it) {                                                                              \
+            rd = CUR;                                                                                 \
+            xd[0] = XPREV[0]; xd[1] = XPREV[1]; xd[2] = XPREV[2]; xd[3] = XPREV[3];                   \
+            break;                                                                                    \
+        }                                                                                             \
+        if (p + 3u < n_ld) LOADINTO = __ldg(src + 32 * ((U) + 3));                                    \
+        uint2 nx = make_uint2(NXT.x, NXT.y);                                                          \
+        if (HALO && p + 1u >= n_ld) nx = fill2;                                                       \
+        fmd_pass<NTI, NTO, true>(CUR, nx, XPREV, XCUR, false, dst + 128 * ((U) - 1), STOREPRED, lane, \
+                                 nxt_lane, st);                                                       \
     }
-    /* what is left: one or two real passes, then the drain pass (p == n_it); positions past
-     * the data are the zero extension */
-    for (; p <= n_it; ++p) {
-        FMD_FETCH(p)
-        if (p >= n_ld) cur = fill;
-        if (HALO && p + 1 >= n_ld) nx = make_uint2(FMD_FILL, FMD_FILL);
-        fmd_pass<NTI, NTO, true>(cur, nx, xb, xa, (p == n_it) && end_zero, dst, keep, lane, nxt_lane, st);
-        keep = true;
-        xb[0] = xa[0]; xb[1] = xa[1]; xb[2] = xa[2]; xb[3] = xa[3];
-        dst += FMD_PASS_OUT;
+
+    for (unsigned base = 0;; base += 4) {
+        FMD_STEP(0, r0, r1, r3, x1, x0, st_a)
+        FMD_STEP(1, r1, r2, r0, x0, x1, st_b)
+        FMD_STEP(2, r2, r3, r1, x1, x0, true)
+        FMD_STEP(3, r3, r0, r2, x0, x1, true)
+        st_a = st_b = true;
+        src += 128;
+        dst += 512;
     }
-#undef FMD_FETCH
-    fmd_cp_wait<0>();
+#undef FMD_STEP
+    /* drain pass (position n_it): rd / xd were parked by the step that left the loop; src and
+     * dst still point at that trip's base, so recompute from the segment start */
+    {
+        const unsigned long long off = (unsigned long long) (n_it & ~3u);
+        (void) off;
+        float xl[4];
+        const uint4 fill = make_uint4(FMD_FILL, FMD_FILL, FMD_FILL, FMD_FILL);
+        const uint4 cur = end_zero ? fill : rd;
+        float *ddst = out + (unsigned long long) chunk * g.chunk_out + k0 + (unsigned long long) (n_it - 1u) * 128u;
+        const bool keep = !(n_it == 1u && it0 == 0 && k0 < g.head);
+        /* only lane 0's first NTO-1 outputs of this pass are consumed (by lane 31, through the
+         * shuffle): with a 2-tap output stencil half the pass is enough */
+        fmd_pass<NTI, NTO, true, (NTO <= 2)>(cur, fill2, xd, xl, end_zero, ddst, keep, lane, nxt_lane, st);
+    }
 }
 
 #endif /* FMD_KERNELS_CUH */

@@ -366,12 +366,15 @@ static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned
      * enough that the grid still holds a few waves of warps for small inputs */
     const unsigned long long total_iters = (unsigned long long) iters_chunk * nchunks;
     const unsigned long long want_warps = (unsigned long long) c->sm_count * 64ull * 2ull;
-    unsigned ips = 64;
-    while (ips > 8 && total_iters / ips < want_warps) ips >>= 1;
+    unsigned ips = 16;
+    if (const char *e = getenv("FMD_IPS")) ips = (unsigned) atoi(e); /* tuning experiments only */
+    if (ips < 1) ips = 1;
+    while (ips > 4 && total_iters / ips < want_warps) ips >>= 1;
     if (ips > iters_chunk) ips = iters_chunk;
     g.iters_per_seg = ips;
     g.segs_per_chunk = (iters_chunk + ips - 1) / ips;
     const unsigned long long nseg = (unsigned long long) g.segs_per_chunk * nchunks;
+    if (nseg > 0xffffffffull) return fmd_set_error(FMD_EINVAL, "too many segments in one launch");
     /* chunk heads and the ragged remainder ride along as the first CTAs of the same launch */
     g.head = c->head;
     const unsigned long long exact_threads = (unsigned long long) nchunks * (g.head + (chunk_out - fast_out));

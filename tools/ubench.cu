@@ -39,6 +39,12 @@ template<int MODE> __global__ void __launch_bounds__(512) k(float* out, float se
       if (MODE==13) { a[i]=fmaf(a[i],c1,c2); a[i]=fmaf(a[i],c2,c1); u[i]=__byte_perm(u[i],0x4B000000u,0x7541);} // 2 FFMA + PRMT
       if (MODE==14) { a[i]=fmaf(a[i],c1,c2); asm volatile("lop3.b32 %0,%0,%1,%2,0x78;":"+r"(u[i]):"r"(0x80808080u),"r"(u[(i+1)%NCH])); u[i]=__byte_perm(u[i],0x4B000000u,0x7541);} // FFMA + 2 ALU
       if (MODE==15) asm volatile("mul.rn.f32x2 %0,%0,%1;":"+l"(p[i]):"l"(q1));      // FMUL2
+      if (MODE==16) { float t; asm volatile("{.reg .b8 b0,b1,b2,b3; mov.b32 {b0,b1,b2,b3}, %1; cvt.rn.f32.s8 %0, b1;}":"=f"(t):"r"(u[i])); a[i]=t; u[i]=__float_as_uint(t); } // I2F.S8 chain
+      if (MODE==17) { float t; asm volatile("{.reg .b8 b0,b1,b2,b3; mov.b32 {b0,b1,b2,b3}, %1; cvt.rn.f32.s8 %0, b1;}":"=f"(t):"r"(u[i])); a[i]+=t; } // I2F.S8 (indep) + FADD
+      if (MODE==18) { float t; asm volatile("{.reg .b8 b0,b1,b2,b3; mov.b32 {b0,b1,b2,b3}, %1; cvt.rn.f32.s8 %0, b2;}":"=f"(t):"r"(u[i])); a[i]+=t; u[i]=__byte_perm(u[i],0x4B000000u,0x7541);} // I2F + FADD + PRMT
+      if (MODE==19) { float t; asm volatile("{.reg .b8 b0,b1,b2,b3; mov.b32 {b0,b1,b2,b3}, %1; cvt.rn.f32.s8 %0, b2;}":"=f"(t):"r"(u[i])); a[i]=fmaf(a[i],c1,t); a[i]=fmaf(a[i],c2,c1); a[i]=fmaf(a[i],c1,c2); } // I2F + 3 FFMA
+      if (MODE==20) { a[i]=fmaf(a[i],c1,c2); a[i]=fmaf(a[i],c2,c1); a[i]=fmaf(a[i],c1,c2); a[i]=fmaf(a[i],c2,c1); u[i]=__byte_perm(u[i],0x4B000000u,0x7541);} // 4 FFMA + PRMT
+      if (MODE==21) { asm volatile("fma.rn.f32x2 %0,%0,%1,%2;":"+l"(p[i]):"l"(q1),"l"(q2)); u[i]=__byte_perm(u[i],0x4B000000u,0x7541); asm volatile("lop3.b32 %0,%0,%1,%2,0x78;":"+r"(u[(i+4)%NCH]):"r"(0x80808080u),"r"(u[(i+1)%NCH])); } // FFMA2 + PRMT + LOP3 (indep)
     }
   }
   long long t1=clock64();
@@ -62,9 +68,10 @@ template<int MODE> void run(const char* name, int instr_per_chain) {
 
 int main(){
   run<0>("FFMA",1); run<1>("FFMA2",1); run<15>("FMUL2",1); run<8>("FADD2",1); run<9>("FADD",1);
-  run<2>("PRMT",1); run<3>("LOP3",1); run<4>("FMNMX",1); run<10>("IADD3",1); run<11>("MUFU.RCP",1);
+  run<2>("PRMT",1); run<3>("LOP3",1); run<4>("FMNMX",1); run<10>("IADD3",1);
   run<5>("FFMA+PRMT",2); run<6>("FFMA2+PRMT",2); run<7>("FFMA2+FFMA",2);
-  run<12>("FFMA2+PRMT+LOP/SHF",3); run<13>("2FFMA+PRMT",3); run<14>("FFMA+LOP3+PRMT",3);
+  run<12>("FFMA2+PRMT+LOP/SHF",3); run<21>("FFMA2+PRMT+LOP3 indep",3);
+  run<16>("I2F.S8 chain",1); run<17>("I2F.S8+FADD",2); run<18>("I2F.S8+FADD+PRMT",3); run<19>("I2F.S8+3FFMA",4); run<20>("4FFMA+PRMT",5); run<13>("2FFMA+PRMT",3); run<14>("FFMA+LOP3+PRMT",3);
   cudaError_t e=cudaGetLastError(); if(e!=cudaSuccess){printf("err %s\n",cudaGetErrorString(e));return 1;}
   return 0;
 }
