@@ -54,8 +54,9 @@ struct FmdGeom {
     unsigned long long chunk_stride; /* bytes between chunk starts                        */
     unsigned chunk_out;              /* outputs per chunk (edge rule: zero beyond)        */
     unsigned fast_out;               /* outputs per chunk the fast kernel covers (x128)   */
-    unsigned iters_per_seg;          /* passes per warp segment                           */
-    unsigned segs_per_chunk;
+    unsigned iters_chunk;            /* fast_out / 128: passes per chunk                  */
+    unsigned total_passes;           /* nchunks * iters_chunk                             */
+    unsigned passes_per_warp;        /* contiguous run of passes each streaming warp owns */
     unsigned nchunks;
     unsigned head;                   /* outputs [0, head) of every chunk: exact path (x4)   */
     unsigned exact_blocks;           /* leading CTAs of the fast kernel that run that path  */
@@ -375,9 +376,9 @@ fmd_exact_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const 
  */
 template <int NTI, int NTO, bool STORE, bool LITE = false>
 __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, const float (&xprev)[4],
-                                         float (&xcur)[4], const bool zero_x, float *__restrict__ dst,
-                                         const bool do_store, const unsigned lane, const unsigned nxt_lane,
-                                         const FmdStencil &st) {
+                                         float (&xcur)[4], const bool zero_x, const bool prev_last,
+                                         float *__restrict__ dst, const bool do_store, const unsigned lane,
+                                         const unsigned nxt_lane, const FmdStencil &st) {
     constexpr int HC = NTI > 1 ? NTI - 1 : 0; /* complex samples needed from the next lane */
     constexpr int HW = (HC + 1) / 2;          /* ... as 4-byte words (2 complex each)      */
     constexpr int NB = NTO - 1;               /* discriminator outputs needed from the next lane */
@@ -474,8 +475,10 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, con
     float xn[4 + (NB > 0 ? NB : 1)];
     xn[0] = xprev[0]; xn[1] = xprev[1]; xn[2] = xprev[2]; xn[3] = xprev[3];
 #pragma unroll
-    for (int t = 0; t < NB; ++t)
-        xn[4 + t] = __shfl_sync(0xffffffffu, lane == 0 ? xcur[t] : xprev[t], nxt_lane);
+    for (int t = 0; t < NB; ++t) { /* lane 31 looks into this pass, unless the previous one closed a chunk */
+        const float from_next_pass = prev_last ? 0.0f : xcur[t];
+        xn[4 + t] = __shfl_sync(0xffffffffu, lane == 0 ? from_next_pass : xprev[t], nxt_lane);
+    }
     if (STORE) {
         float4 y;
         float *yy = reinterpret_cast<float *>(&y);
@@ -493,16 +496,42 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, con
 #ifndef FMD_MINB
 #define FMD_MINB(NTI) ((NTI) == 0 ? 5 : 4) /* resident CTAs per SM the register budget is cut for */
 #endif
+#ifndef FMD_STAGES
+#define FMD_STAGES 8 /* cp.async ring depth per lane (power of two) */
+#endif
+
+/* ---- cp.async (LDGSTS) ring: global -> shared without staging registers ---- */
+__device__ __forceinline__ void fmd_cp_async16(uint32_t smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void fmd_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void fmd_cp_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint4 fmd_lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 fmd_lds64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
 
 /*
- * A warp owns one segment: n_it passes of 128 outputs (512 B in, 512 B out per pass),
- * plus one "drain" pass that only feeds the last real pass its neighbours.  If the
- * segment ends at the end of a chunk the drain pass is the zero extension (no load,
- * x = 0); otherwise it re-reads the first 512 B of what follows.
+ * The streaming kernel.  The launch is ONE resident wave: every warp owns a contiguous run of
+ * `passes_per_warp` passes of the whole input (a pass = 128 outputs = 512 B in, 512 B out per
+ * warp), walks it front to back, and may cross chunk boundaries on the way.  Because the output
+ * stage runs one pass behind the discriminator, the stencil neighbours of a lane's last outputs
+ * come from the same warp's next pass; at a chunk's last pass they are the zero extension, and
+ * at the end of the warp's run one extra half pass (the "drain") looks at what follows.
  *
- * Input is prefetched three passes ahead into a ring of four 16-byte register quads
- * (one LDG.128 per pass, no staging instructions); the loop is unrolled by four so that
- * the ring and the x ping-pong are register renames, not moves.
+ * Input reaches the lanes through a per-lane ring in shared memory filled by cp.async (LDGSTS,
+ * L2 only): every lane copies its own 16 bytes FMD_STAGES-1 passes ahead and reads them back
+ * with one LDS.128, so the bytes in flight do not depend on the register budget and no lane ever
+ * reads another lane's slot (no barrier anywhere in the kernel).
  */
 template <int NTI, int NTO>
 __global__ void __launch_bounds__(FMD_BLOCK, FMD_MINB(NTI))
@@ -515,76 +544,100 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
         fmd_exact_thread(in, out, g, sec, (unsigned long long) blockIdx.x * FMD_BLOCK + threadIdx.x);
         return;
     }
-    constexpr bool HALO = NTI > 1; /* lane 31 needs lane 0's next pass */
-    const unsigned lane = threadIdx.x & 31u;
-    /* the host keeps nchunks * segs_per_chunk below 2^32 per launch */
-    const unsigned seg = (blockIdx.x - g.exact_blocks) * FMD_WARPS + (threadIdx.x >> 5);
-    if (seg >= g.nchunks * g.segs_per_chunk) return;
-    const unsigned chunk = seg / g.segs_per_chunk;
-    const unsigned sic = seg - chunk * g.segs_per_chunk;
-    const unsigned it0 = sic * g.iters_per_seg;
-    const unsigned iters_chunk = g.fast_out >> 7;
-    const unsigned n_it = min(g.iters_per_seg, iters_chunk - it0);
-    /* does the drain pass fall off the end of the chunk? (fast_out == chunk_out there) */
-    const bool end_zero = (it0 + n_it == iters_chunk) && (g.fast_out == g.chunk_out);
-    const unsigned n_ld = end_zero ? n_it : n_it + 1u; /* positions that exist in memory */
-    const unsigned nxt_lane = (lane + 1u) & 31u;
-    const unsigned k0 = it0 * FMD_PASS_OUT + lane * 4u;
+    constexpr int S = FMD_STAGES;
+    constexpr bool HALO = NTI > 1;                /* lane 31 needs lane 0's next pass */
+    constexpr int PENDING = HALO ? S - 2 : S - 1; /* groups allowed in flight at the wait */
+    constexpr uint32_t SLOT = FMD_BLOCK * 16u;
+    __shared__ uint4 ring[S * FMD_BLOCK];
 
-    /* src[32 * q] is this lane's 16 bytes of position q; dst[128 * q] its 4 outputs */
-    const uint4 *__restrict__ src =
-        reinterpret_cast<const uint4 *>(in + (unsigned long long) chunk * g.chunk_stride + 4ull * k0);
-    float *__restrict__ dst = out + (unsigned long long) chunk * g.chunk_out + k0;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned nxt_lane = (lane + 1u) & 31u;
+    const unsigned warp = (blockIdx.x - g.exact_blocks) * FMD_WARPS + (threadIdx.x >> 5);
+    const unsigned p_begin = warp * g.passes_per_warp;
+    if (p_begin >= g.total_passes) return;
+    const unsigned n_mine = min(g.passes_per_warp, g.total_passes - p_begin);
+    const unsigned chunk0 = p_begin / g.iters_chunk;
+    const unsigned it0 = p_begin - chunk0 * g.iters_chunk;
+    /* what follows this warp's run: more of the same chunk (half a pass of look-ahead) or a chunk end */
+    const bool has_drain = ((it0 + n_mine) % g.iters_chunk) != 0u || g.fast_out != g.chunk_out;
+    /* (ragged: the look-ahead pass [fast_out, fast_out + 128) exists, the host stops one pass early) */
+    const unsigned n_ld = n_mine + (has_drain ? 1u : 0u); /* positions to fetch */
+    /* a chunk ends after its last pass; chunks are laid out chunk_stride / chunk_out apart */
+    /* (a ragged chunk, fast_out < chunk_out, is always the only chunk of its launch: no jumps) */
+    const bool whole = g.fast_out == g.chunk_out;
+    const unsigned long long gap_in = whole ? g.chunk_stride - 4ull * g.fast_out : 0ull;
+    const unsigned gap_out = 0u * (whole ? 1u : 0u); /* outputs of consecutive chunks are contiguous */
+    const bool head_lane = 4u * lane < g.head;
+
+    const uint8_t *gsrc = in + (unsigned long long) chunk0 * g.chunk_stride + 512ull * it0 + 16u * lane;
+    float *dst = out + (unsigned long long) chunk0 * g.chunk_out + 128u * it0 + 4u * lane;
+    const uint32_t sbase = (uint32_t) __cvta_generic_to_shared(&ring[threadIdx.x]);
     const uint2 fill2 = make_uint2(FMD_FILL, FMD_FILL);
 
-    uint4 r0, r1, r2, r3, rd;
-    r0 = __ldg(src);
-    r1 = r2 = r3 = rd = r0;
-    if (1u < n_ld) r1 = __ldg(src + 32);
-    if (2u < n_ld) r2 = __ldg(src + 64);
-    float x0[4], x1[4] = {0.f, 0.f, 0.f, 0.f}, xd[4];
-    /* store predicates of the first two passes: pass 0 has nothing to store; the first store of
-     * a chunk's first segment skips the chunk head [0, head), which belongs to the exact path */
-    bool st_a = false, st_b = !(it0 == 0 && k0 < g.head);
+    unsigned it_issue = it0; /* chunk-local pass index of the next position to fetch */
+    unsigned q_issue = 0;
+    auto issue = [&]() {
+        if (q_issue < n_ld) {
+            fmd_cp_async16(sbase + (q_issue & (S - 1)) * SLOT, gsrc);
+            gsrc += 512;
+            if (++it_issue == g.iters_chunk) {
+                it_issue = 0;
+                gsrc += gap_in;
+            }
+        }
+        ++q_issue;
+        fmd_cp_commit();
+    };
+#pragma unroll
+    for (int q = 0; q < S - 1; ++q) issue();
 
-#define FMD_STEP(U, CUR, NXT, LOADINTO, XPREV, XCUR, STOREPRED)                                       \
-    {                                                                                                 \
-        const unsigned p = base + (U);                                                                \
-        if (p >= n_it) {                                                                              \
-            rd = CUR;                                                                                 \
-            xd[0] = XPREV[0]; xd[1] = XPREV[1]; xd[2] = XPREV[2]; xd[3] = XPREV[3];                   \
-            break;                                                                                    \
-        }                                                                                             \
-        if (p + 3u < n_ld) LOADINTO = __ldg(src + 32 * ((U) + 3));                                    \
-        uint2 nx = make_uint2(NXT.x, NXT.y);                                                          \
-        if (HALO && p + 1u >= n_ld) nx = fill2;                                                       \
-        fmd_pass<NTI, NTO, true>(CUR, nx, XPREV, XCUR, false, dst + 128 * ((U) - 1), STOREPRED, lane, \
-                                 nxt_lane, st);                                                       \
+    float xa[4] = {0.f, 0.f, 0.f, 0.f}, xb[4];
+    unsigned it = it0;       /* chunk-local index of the pass being computed */
+    bool prev_last = false;  /* previous pass was the last of its chunk */
+    bool prev_keep = false;  /* store predicate of the previous pass (pass -1: nothing to store) */
+    float *pdst = dst;       /* where the previous pass's outputs go */
+
+    /* one pass: fetch, discriminate, finish the previous pass */
+#define FMD_STEP(P, XPREV, XCUR)                                                                        \
+    {                                                                                                   \
+        issue();                                                                                        \
+        fmd_cp_wait<PENDING>();                                                                         \
+        const uint4 cur = fmd_lds128(sbase + ((P) & (S - 1)) * SLOT);                                   \
+        uint2 nx = fill2;                                                                               \
+        const bool last = (it + 1u == g.iters_chunk) && (g.fast_out == g.chunk_out);                    \
+        if (HALO && !last) nx = fmd_lds64(sbase + (((P) + 1u) & (S - 1)) * SLOT);                       \
+        fmd_pass<NTI, NTO, true>(cur, nx, XPREV, XCUR, false, prev_last, pdst, prev_keep, lane, nxt_lane, st); \
+        prev_keep = !(it == 0u && head_lane);                                                           \
+        prev_last = last;                                                                               \
+        pdst = dst;                                                                                     \
+        dst += 128;                                                                                     \
+        if (++it == g.iters_chunk) {                                                                    \
+            it = 0;                                                                                     \
+            dst += gap_out;                                                                             \
+        }                                                                                               \
     }
 
-    for (unsigned base = 0;; base += 4) {
-        FMD_STEP(0, r0, r1, r3, x1, x0, st_a)
-        FMD_STEP(1, r1, r2, r0, x0, x1, st_b)
-        FMD_STEP(2, r2, r3, r1, x1, x0, true)
-        FMD_STEP(3, r3, r0, r2, x0, x1, true)
-        st_a = st_b = true;
-        src += 128;
-        dst += 512;
+    unsigned p = 0;
+    for (; p + 1 < n_mine; p += 2) {
+        FMD_STEP(p, xa, xb)
+        FMD_STEP(p + 1u, xb, xa)
+    }
+    if (p < n_mine) {
+        FMD_STEP(p, xa, xb)
+        xa[0] = xb[0]; xa[1] = xb[1]; xa[2] = xb[2]; xa[3] = xb[3];
+        ++p;
     }
 #undef FMD_STEP
-    /* drain pass (position n_it): rd / xd were parked by the step that left the loop; src and
-     * dst still point at that trip's base, so recompute from the segment start */
+    /* finish the last pass: its neighbours are the zero extension (chunk end) or the first outputs
+     * of whatever follows (half a pass is enough for a 2-tap output stencil) */
     {
-        const unsigned long long off = (unsigned long long) (n_it & ~3u);
-        (void) off;
+        fmd_cp_wait<0>();
         float xl[4];
-        const uint4 fill = make_uint4(FMD_FILL, FMD_FILL, FMD_FILL, FMD_FILL);
-        const uint4 cur = end_zero ? fill : rd;
-        float *ddst = out + (unsigned long long) chunk * g.chunk_out + k0 + (unsigned long long) (n_it - 1u) * 128u;
-        const bool keep = !(n_it == 1u && it0 == 0 && k0 < g.head);
-        /* only lane 0's first NTO-1 outputs of this pass are consumed (by lane 31, through the
-         * shuffle): with a 2-tap output stencil half the pass is enough */
-        fmd_pass<NTI, NTO, true, (NTO <= 2)>(cur, fill2, xd, xl, end_zero, ddst, keep, lane, nxt_lane, st);
+        uint4 cur = make_uint4(FMD_FILL, FMD_FILL, FMD_FILL, FMD_FILL);
+        if (has_drain) cur = fmd_lds128(sbase + (p & (S - 1)) * SLOT);
+        /* the drain position's own halo (for lane 0's input filter) comes from lane 1 by shuffle */
+        fmd_pass<NTI, NTO, true, (NTO <= 2)>(cur, fill2, xa, xl, !has_drain, prev_last, pdst, prev_keep, lane,
+                                             nxt_lane, st);
     }
 }
 
