@@ -54,9 +54,8 @@ struct FmdGeom {
     unsigned long long chunk_stride; /* bytes between chunk starts                        */
     unsigned chunk_out;              /* outputs per chunk (edge rule: zero beyond)        */
     unsigned fast_out;               /* outputs per chunk the fast kernel covers (x128)   */
-    unsigned iters_chunk;            /* fast_out / 128: passes per chunk                  */
-    unsigned total_passes;           /* nchunks * iters_chunk                             */
-    unsigned passes_per_warp;        /* contiguous run of passes each streaming warp owns */
+    unsigned iters_per_seg;          /* passes per warp segment                           */
+    unsigned segs_per_chunk;
     unsigned nchunks;
     unsigned head;                   /* outputs [0, head) of every chunk: exact path (x4)   */
     unsigned exact_blocks;           /* leading CTAs of the fast kernel that run that path  */
@@ -376,9 +375,9 @@ fmd_exact_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const 
  */
 template <int NTI, int NTO, bool STORE, bool LITE = false>
 __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, const float (&xprev)[4],
-                                         float (&xcur)[4], const bool zero_x, const bool prev_last,
-                                         float *__restrict__ dst, const bool do_store, const unsigned lane,
-                                         const unsigned nxt_lane, const FmdStencil &st) {
+                                         float (&xcur)[4], const bool zero_x, float *__restrict__ dst,
+                                         const bool do_store, const unsigned lane, const unsigned nxt_lane,
+                                         const FmdStencil &st) {
     constexpr int HC = NTI > 1 ? NTI - 1 : 0; /* complex samples needed from the next lane */
     constexpr int HW = (HC + 1) / 2;          /* ... as 4-byte words (2 complex each)      */
     constexpr int NB = NTO - 1;               /* discriminator outputs needed from the next lane */
@@ -475,10 +474,8 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, con
     float xn[4 + (NB > 0 ? NB : 1)];
     xn[0] = xprev[0]; xn[1] = xprev[1]; xn[2] = xprev[2]; xn[3] = xprev[3];
 #pragma unroll
-    for (int t = 0; t < NB; ++t) { /* lane 31 looks into this pass, unless the previous one closed a chunk */
-        const float from_next_pass = prev_last ? 0.0f : xcur[t];
-        xn[4 + t] = __shfl_sync(0xffffffffu, lane == 0 ? from_next_pass : xprev[t], nxt_lane);
-    }
+    for (int t = 0; t < NB; ++t)
+        xn[4 + t] = __shfl_sync(0xffffffffu, lane == 0 ? xcur[t] : xprev[t], nxt_lane);
     if (STORE) {
         float4 y;
         float *yy = reinterpret_cast<float *>(&y);
@@ -492,13 +489,6 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, con
         if (do_store) *reinterpret_cast<float4 *>(dst) = y;
     }
 }
-
-#ifndef FMD_MINB
-#define FMD_MINB(NTI) ((NTI) == 0 ? 5 : 4) /* resident CTAs per SM the register budget is cut for */
-#endif
-#ifndef FMD_STAGES
-#define FMD_STAGES 8 /* cp.async ring depth per lane (power of two) */
-#endif
 
 /* ---- cp.async (LDGSTS) ring: global -> shared without staging registers ---- */
 __device__ __forceinline__ void fmd_cp_async16(uint32_t smem_dst, const void *gsrc) {
@@ -519,19 +509,27 @@ __device__ __forceinline__ uint2 fmd_lds64(uint32_t a) {
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
     return v;
 }
+__device__ __forceinline__ void fmd_sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+#ifndef FMD_MINB
+#define FMD_MINB(NTI) ((NTI) == 0 ? 5 : 4) /* resident CTAs per SM the register budget is cut for */
+#endif
+#ifndef FMD_STAGES
+#define FMD_STAGES 8 /* ring depth per lane (power of two): 16 B x FMD_STAGES in flight or landed */
+#endif
 
 /*
- * The streaming kernel.  The launch is ONE resident wave: every warp owns a contiguous run of
- * `passes_per_warp` passes of the whole input (a pass = 128 outputs = 512 B in, 512 B out per
- * warp), walks it front to back, and may cross chunk boundaries on the way.  Because the output
- * stage runs one pass behind the discriminator, the stencil neighbours of a lane's last outputs
- * come from the same warp's next pass; at a chunk's last pass they are the zero extension, and
- * at the end of the warp's run one extra half pass (the "drain") looks at what follows.
+ * A warp owns one segment: n_it passes of 128 outputs (512 B in, 512 B out per pass),
+ * plus one "drain" pass that only feeds the last real pass its neighbours.  If the
+ * segment ends at the end of a chunk the drain pass is the zero extension (no load,
+ * x = 0); otherwise it re-reads the first 512 B of what follows.
  *
- * Input reaches the lanes through a per-lane ring in shared memory filled by cp.async (LDGSTS,
- * L2 only): every lane copies its own 16 bytes FMD_STAGES-1 passes ahead and reads them back
- * with one LDS.128, so the bytes in flight do not depend on the register budget and no lane ever
- * reads another lane's slot (no barrier anywhere in the kernel).
+ * Input reaches the lanes through a per-lane ring in shared memory filled by cp.async
+ * (LDGSTS, L2-only): every lane copies its own 16 bytes FMD_STAGES-1 passes ahead and
+ * reads them back with one LDS.128, so the loads in flight per SM do not depend on the
+ * register budget or on occupancy, and no lane ever reads another lane's slot (no barrier).
  */
 template <int NTI, int NTO>
 __global__ void __launch_bounds__(FMD_BLOCK, FMD_MINB(NTI))
@@ -545,100 +543,87 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
         return;
     }
     constexpr int S = FMD_STAGES;
-    constexpr bool HALO = NTI > 1;                /* lane 31 needs lane 0's next pass */
+    constexpr bool HALO = NTI > 1;               /* lane 31 needs lane 0's next pass */
     constexpr int PENDING = HALO ? S - 2 : S - 1; /* groups allowed in flight at the wait */
-    constexpr uint32_t SLOT = FMD_BLOCK * 16u;
     __shared__ uint4 ring[S * FMD_BLOCK];
 
     const unsigned lane = threadIdx.x & 31u;
+    /* the host keeps nchunks * segs_per_chunk below 2^32 per launch */
+    const unsigned seg = (blockIdx.x - g.exact_blocks) * FMD_WARPS + (threadIdx.x >> 5);
+    if (seg >= g.nchunks * g.segs_per_chunk) return;
+    const unsigned chunk = seg / g.segs_per_chunk;
+    const unsigned sic = seg - chunk * g.segs_per_chunk;
+    const unsigned it0 = sic * g.iters_per_seg;
+    const unsigned iters_chunk = g.fast_out >> 7;
+    const unsigned n_it = min(g.iters_per_seg, iters_chunk - it0);
+    /* does the drain pass fall off the end of the chunk? (fast_out == chunk_out there) */
+    const bool end_zero = (it0 + n_it == iters_chunk) && (g.fast_out == g.chunk_out);
+    const unsigned n_ld = end_zero ? n_it : n_it + 1u; /* positions that exist in memory */
     const unsigned nxt_lane = (lane + 1u) & 31u;
-    const unsigned warp = (blockIdx.x - g.exact_blocks) * FMD_WARPS + (threadIdx.x >> 5);
-    const unsigned p_begin = warp * g.passes_per_warp;
-    if (p_begin >= g.total_passes) return;
-    const unsigned n_mine = min(g.passes_per_warp, g.total_passes - p_begin);
-    const unsigned chunk0 = p_begin / g.iters_chunk;
-    const unsigned it0 = p_begin - chunk0 * g.iters_chunk;
-    /* what follows this warp's run: more of the same chunk (half a pass of look-ahead) or a chunk end */
-    const bool has_drain = ((it0 + n_mine) % g.iters_chunk) != 0u || g.fast_out != g.chunk_out;
-    /* (ragged: the look-ahead pass [fast_out, fast_out + 128) exists, the host stops one pass early) */
-    const unsigned n_ld = n_mine + (has_drain ? 1u : 0u); /* positions to fetch */
-    /* a chunk ends after its last pass; chunks are laid out chunk_stride / chunk_out apart */
-    /* (a ragged chunk, fast_out < chunk_out, is always the only chunk of its launch: no jumps) */
-    const bool whole = g.fast_out == g.chunk_out;
-    const unsigned long long gap_in = whole ? g.chunk_stride - 4ull * g.fast_out : 0ull;
-    const unsigned gap_out = 0u * (whole ? 1u : 0u); /* outputs of consecutive chunks are contiguous */
-    const bool head_lane = 4u * lane < g.head;
+    const unsigned k0 = it0 * FMD_PASS_OUT + lane * 4u;
 
-    const uint8_t *gsrc = in + (unsigned long long) chunk0 * g.chunk_stride + 512ull * it0 + 16u * lane;
-    float *dst = out + (unsigned long long) chunk0 * g.chunk_out + 128u * it0 + 4u * lane;
+    const uint8_t *__restrict__ src = in + (unsigned long long) chunk * g.chunk_stride + 4ull * k0;
+    float *__restrict__ dst = out + (unsigned long long) chunk * g.chunk_out + k0;
+    const uint4 fill = make_uint4(FMD_FILL, FMD_FILL, FMD_FILL, FMD_FILL);
     const uint32_t sbase = (uint32_t) __cvta_generic_to_shared(&ring[threadIdx.x]);
-    const uint2 fill2 = make_uint2(FMD_FILL, FMD_FILL);
+    constexpr uint32_t SLOT = FMD_BLOCK * 16u;
 
-    unsigned it_issue = it0; /* chunk-local pass index of the next position to fetch */
-    unsigned q_issue = 0;
-    auto issue = [&]() {
-        if (q_issue < n_ld) {
-            fmd_cp_async16(sbase + (q_issue & (S - 1)) * SLOT, gsrc);
-            gsrc += 512;
-            if (++it_issue == g.iters_chunk) {
-                it_issue = 0;
-                gsrc += gap_in;
-            }
-        }
-        ++q_issue;
+    /* position q of the segment -> ring slot q % S; past the data: the zero extension */
+    auto issue = [&](unsigned q) {
+        if (q < n_ld) fmd_cp_async16(sbase + (q & (S - 1)) * SLOT, src + 512ull * q);
         fmd_cp_commit();
     };
 #pragma unroll
-    for (int q = 0; q < S - 1; ++q) issue();
+    for (int q = 0; q < S - 1; ++q) issue((unsigned) q);
 
     float xa[4] = {0.f, 0.f, 0.f, 0.f}, xb[4];
-    unsigned it = it0;       /* chunk-local index of the pass being computed */
-    bool prev_last = false;  /* previous pass was the last of its chunk */
-    bool prev_keep = false;  /* store predicate of the previous pass (pass -1: nothing to store) */
-    float *pdst = dst;       /* where the previous pass's outputs go */
+    uint4 cur;
+    uint2 nx = make_uint2(FMD_FILL, FMD_FILL);
+    /* the chunk head [0, head) belongs to the exact path: those lanes of the very first store
+     * of a chunk's first segment keep quiet */
+    bool keep = !(it0 == 0 && k0 < g.head);
 
-    /* one pass: fetch, discriminate, finish the previous pass */
-#define FMD_STEP(P, XPREV, XCUR)                                                                        \
-    {                                                                                                   \
-        issue();                                                                                        \
-        fmd_cp_wait<PENDING>();                                                                         \
-        const uint4 cur = fmd_lds128(sbase + ((P) & (S - 1)) * SLOT);                                   \
-        uint2 nx = fill2;                                                                               \
-        const bool last = (it + 1u == g.iters_chunk) && (g.fast_out == g.chunk_out);                    \
-        if (HALO && !last) nx = fmd_lds64(sbase + (((P) + 1u) & (S - 1)) * SLOT);                       \
-        fmd_pass<NTI, NTO, true>(cur, nx, XPREV, XCUR, false, prev_last, pdst, prev_keep, lane, nxt_lane, st); \
-        prev_keep = !(it == 0u && head_lane);                                                           \
-        prev_last = last;                                                                               \
-        pdst = dst;                                                                                     \
-        dst += 128;                                                                                     \
-        if (++it == g.iters_chunk) {                                                                    \
-            it = 0;                                                                                     \
-            dst += gap_out;                                                                             \
-        }                                                                                               \
-    }
+#define FMD_FETCH(P)                                                     \
+    issue((P) + S - 1);                                                  \
+    fmd_cp_wait<PENDING>();                                              \
+    cur = fmd_lds128(sbase + ((P) & (S - 1)) * SLOT);                    \
+    if (HALO) nx = fmd_lds64(sbase + (((P) + 1) & (S - 1)) * SLOT);
 
-    unsigned p = 0;
-    for (; p + 1 < n_mine; p += 2) {
-        FMD_STEP(p, xa, xb)
-        FMD_STEP(p + 1u, xb, xa)
+    /* pass 0: nothing to store yet */
+    FMD_FETCH(0u)
+    if (HALO && 1u >= n_ld) nx = make_uint2(FMD_FILL, FMD_FILL);
+    fmd_pass<NTI, NTO, false>(cur, nx, xa, xb, false, dst, false, lane, nxt_lane, st);
+
+    /* passes 1 .. n_it-2 are real and have a real successor: two per trip so the x registers
+     * ping-pong without moves */
+    unsigned p = 1;
+    for (; p + 2 < n_it; p += 2) {
+        FMD_FETCH(p)
+        fmd_pass<NTI, NTO, true>(cur, nx, xb, xa, false, dst, keep, lane, nxt_lane, st);
+        FMD_FETCH(p + 1)
+        fmd_pass<NTI, NTO, true>(cur, nx, xa, xb, false, dst + FMD_PASS_OUT, true, lane, nxt_lane, st);
+        keep = true;
+        dst += 2 * FMD_PASS_OUT;
     }
-    if (p < n_mine) {
-        FMD_STEP(p, xa, xb)
-        xa[0] = xb[0]; xa[1] = xb[1]; xa[2] = xb[2]; xa[3] = xb[3];
-        ++p;
+    /* what is left: one or two real passes ... */
+    for (; p < n_it; ++p) {
+        FMD_FETCH(p)
+        if (HALO && p + 1 >= n_ld) nx = make_uint2(FMD_FILL, FMD_FILL);
+        fmd_pass<NTI, NTO, true>(cur, nx, xb, xa, false, dst, keep, lane, nxt_lane, st);
+        keep = true;
+        xb[0] = xa[0]; xb[1] = xa[1]; xb[2] = xa[2]; xb[3] = xa[3];
+        dst += FMD_PASS_OUT;
     }
-#undef FMD_STEP
-    /* finish the last pass: its neighbours are the zero extension (chunk end) or the first outputs
-     * of whatever follows (half a pass is enough for a 2-tap output stencil) */
+    /* ... then the drain pass (position n_it): only lane 0's first NTO-1 outputs of it are consumed
+     * (by lane 31, through the shuffle), so with a 2-tap output stencil half a pass is enough */
     {
-        fmd_cp_wait<0>();
-        float xl[4];
-        uint4 cur = make_uint4(FMD_FILL, FMD_FILL, FMD_FILL, FMD_FILL);
-        if (has_drain) cur = fmd_lds128(sbase + (p & (S - 1)) * SLOT);
-        /* the drain position's own halo (for lane 0's input filter) comes from lane 1 by shuffle */
-        fmd_pass<NTI, NTO, true, (NTO <= 2)>(cur, fill2, xa, xl, !has_drain, prev_last, pdst, prev_keep, lane,
+        FMD_FETCH(p)
+        if (p >= n_ld) cur = fill;
+        fmd_pass<NTI, NTO, true, (NTO <= 2)>(cur, make_uint2(FMD_FILL, FMD_FILL), xb, xa, end_zero, dst, keep, lane,
                                              nxt_lane, st);
     }
+#undef FMD_FETCH
+    fmd_cp_wait<0>();
 }
 
 #endif /* FMD_KERNELS_CUH */

@@ -44,9 +44,6 @@ extern "C" const char *fmd_last_error(void) { return g_err; }
 
 /* ----------------------------------------------------------------- context */
 
-typedef void (*fast_fn)(const uint8_t *, float *, const FmdGeom, const FmdStencil, const FmdSections *);
-static fast_fn pick_fast(unsigned nti, unsigned nto);
-
 struct fmd_slot {
     uint8_t *d_in = nullptr;
     float *d_out = nullptr;
@@ -71,7 +68,6 @@ struct fmd_ctx {
     size_t slot_bytes = 0;
     uint64_t launches = 0;
     int sm_count = 148;
-    int resident_blocks = 148; /* CTAs of the selected streaming kernel that fit on the device at once */
     /* optional per-launch event timing of the fast kernel */
     bool profile = false;
     cudaEvent_t *pev = nullptr; /* pairs: [2*i] before, [2*i+1] after */
@@ -215,14 +211,6 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
         fmd_destroy(c);
         return fmd_set_error(FMD_ECUDA, "coefficient upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    {
-        int per_sm = 0;
-        fast_fn fn = pick_fast(c->nti, c->nto);
-        if (fn && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, FMD_BLOCK, 0) == cudaSuccess && per_sm > 0)
-            c->resident_blocks = per_sm * c->sm_count;
-        else
-            c->resident_blocks = c->sm_count;
-    }
     *out = c;
     return FMD_OK;
 }
@@ -305,6 +293,7 @@ extern "C" size_t fmd_out_count(const fmd_ctx *c, size_t nbytes) {
     return nbytes >> 2; /* whole chunks give B/4 each; the ragged tail gives r/4 */
 }
 
+typedef void (*fast_fn)(const uint8_t *, float *, const FmdGeom, const FmdStencil, const FmdSections *);
 
 template <int NTI>
 static fast_fn pick_out(unsigned nto) {
@@ -350,47 +339,48 @@ static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned
                          unsigned long long stride, cudaStream_t s) {
     if (!nchunks || !chunk_out) return FMD_OK;
     FmdGeom g;
-    memset(&g, 0, sizeof g);
     g.chunk_stride = stride;
     g.chunk_out = chunk_out;
     g.nchunks = nchunks;
+    g.fast_out = 0;
+    g.iters_per_seg = 1;
+    g.segs_per_chunk = 1;
+    g.head = 0;
+    g.exact_blocks = 0;
 
     fast_fn fn = pick_fast(c->nti, c->nto);
-    const bool aligned = ((uintptr_t) d_in % 16 == 0) && ((uintptr_t) d_out % 16 == 0) && (stride % 16 == 0);
-    /* the streaming kernel covers whole 128-output passes.  A chunk that is not a multiple of 128
-     * outputs can only be the single (ragged tail) chunk of its launch; the kernel then stops one
-     * pass early so that its look-ahead still reads real samples, and the exact path finishes. */
-    unsigned fast_out = 0;
-    if (chunk_out % FMD_PASS_OUT == 0) fast_out = chunk_out;
-    else if (nchunks == 1 && chunk_out >= 2 * FMD_PASS_OUT) fast_out = (chunk_out / FMD_PASS_OUT - 1) * FMD_PASS_OUT;
-    const unsigned long long total = (unsigned long long) (fast_out / FMD_PASS_OUT) * nchunks;
+    const bool aligned = ((uintptr_t) d_in % 16 == 0) && ((uintptr_t) d_out % 16 == 0) && (stride % 16 == 0) &&
+                         (nchunks == 1 || chunk_out % 4 == 0);
+    /* the fast kernel covers whole 128-output passes; if the chunk is not a multiple of 128
+     * outputs it stops one pass early so that its drain pass still reads real samples */
+    const unsigned fast_out = (chunk_out % FMD_PASS_OUT == 0)
+                                  ? chunk_out
+                                  : (chunk_out >= 2 * FMD_PASS_OUT ? (chunk_out / FMD_PASS_OUT - 1) * FMD_PASS_OUT : 0);
     const bool fast_ok = fn && aligned && !(c->cfg.flags & FMD_FLAG_EXACT) && fast_out >= FMD_PASS_OUT &&
-                         fast_out > c->head && stride >= 4ull * chunk_out && total <= 0xffffffffull &&
-                         (nchunks == 1 || stride == 4ull * chunk_out || fast_out == chunk_out);
+                         fast_out > c->head;
     if (!fast_ok) return launch_exact(c, d_in, d_out, g, s);
 
     g.fast_out = fast_out;
-    g.iters_chunk = fast_out / FMD_PASS_OUT;
-    g.total_passes = (unsigned) total;
-    g.head = c->head;
+    const unsigned iters_chunk = g.fast_out >> 7;
+    /* passes per warp segment: long enough to amortise the one extra (drain) pass, short
+     * enough that the grid still holds a few waves of warps for small inputs */
+    const unsigned long long total_iters = (unsigned long long) iters_chunk * nchunks;
+    const unsigned long long want_warps = (unsigned long long) c->sm_count * 64ull * 2ull;
+    unsigned ips = 16;
+    if (const char *e = getenv("FMD_IPS")) ips = (unsigned) atoi(e); /* tuning experiments only */
+    if (ips < 1) ips = 1;
+    while (ips > 4 && total_iters / ips < want_warps / 4) ips >>= 1;
+    if (ips > iters_chunk) ips = iters_chunk;
+    g.iters_per_seg = ips;
+    g.segs_per_chunk = (iters_chunk + ips - 1) / ips;
+    const unsigned long long nseg = (unsigned long long) g.segs_per_chunk * nchunks;
+    if (nseg > 0xffffffffull) return fmd_set_error(FMD_EINVAL, "too many segments in one launch");
     /* chunk heads and the ragged remainder ride along as the first CTAs of the same launch */
+    g.head = c->head;
     const unsigned long long exact_threads = (unsigned long long) nchunks * (g.head + (chunk_out - fast_out));
     g.exact_blocks = (unsigned) ((exact_threads + FMD_BLOCK - 1) / FMD_BLOCK);
-    /* one resident wave: as many streaming CTAs as fit next to the exact ones, each warp owning an
-     * equal contiguous run of passes (at least 4, so that tiny inputs do not pay 5920 prologues) */
-    unsigned resident = (unsigned) c->resident_blocks;
-    unsigned fast_blocks = resident > g.exact_blocks + 8u ? resident - g.exact_blocks : 8u;
-    const unsigned long long min_ppw = 4;
-    const unsigned long long need_blocks = (total + min_ppw * FMD_WARPS - 1) / (min_ppw * FMD_WARPS);
-    if (need_blocks < fast_blocks) fast_blocks = (unsigned) need_blocks;
-    if (const char *e = getenv("FMD_BLOCKS")) fast_blocks = (unsigned) atoi(e); /* tuning experiments only */
-    if (fast_blocks < 1) fast_blocks = 1;
-    const unsigned long long warps = (unsigned long long) fast_blocks * FMD_WARPS;
-    g.passes_per_warp = (unsigned) ((total + warps - 1) / warps);
-    /* drop CTAs that the rounding left without work */
-    fast_blocks = (unsigned) ((total + (unsigned long long) g.passes_per_warp * FMD_WARPS - 1) /
-                              ((unsigned long long) g.passes_per_warp * FMD_WARPS));
-
+    const unsigned long long blocks = (nseg + FMD_WARPS - 1) / FMD_WARPS + g.exact_blocks;
+    if (blocks > 0x7fffffffull) return fmd_set_error(FMD_EINVAL, "fast kernel grid too large");
     cudaEvent_t *pe = nullptr;
     if (c->profile) {
         if (c->pev_used == c->pev_cap) {
@@ -400,7 +390,7 @@ static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned
         pe = &c->pev[2 * c->pev_used++];
         FMD_CUDA(cudaEventRecord(pe[0], s));
     }
-    fn<<<g.exact_blocks + fast_blocks, FMD_BLOCK, 0, s>>>(d_in, d_out, g, c->st, c->d_sec);
+    fn<<<(unsigned) blocks, FMD_BLOCK, 0, s>>>(d_in, d_out, g, c->st, c->d_sec);
     FMD_CUDA(cudaGetLastError());
     if (pe) FMD_CUDA(cudaEventRecord(pe[1], s));
     c->launches++;
