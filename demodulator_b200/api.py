@@ -184,7 +184,7 @@ class Demodulator:
         return int(got.value)
 
     def process_device(self, d_in: int, nbytes: int, d_out: int, stream: int = 0) -> None:
-        """Device pointers; asynchronous on `stream` (a cudaStream_t as int, 0 = context stream)."""
+        """Device pointers; asynchronous on `stream` (a cudaStream_t as int, 0 = the default stream)."""
         _check(self._L.fmd_demod_device(self._ctx, d_in, nbytes, d_out, stream))
 
     def time_device(self, d_in: int, nbytes: int, d_out: int, stream: int, reps: int) -> float:

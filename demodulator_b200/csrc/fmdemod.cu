@@ -399,7 +399,7 @@ static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned
 
 extern "C" int fmd_demod_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, float *d_out, void *stream) {
     if (!c || (!d_in && nbytes) || (!d_out && nbytes)) return fmd_set_error(FMD_EINVAL, "null argument");
-    cudaStream_t s = stream ? (cudaStream_t) stream : c->s_k;
+    cudaStream_t s = (cudaStream_t) stream; /* NULL is CUDA's default stream, as everywhere in CUDA */
     const unsigned long long B = c->cfg.chunk_bytes;
     const unsigned long long nfull = nbytes / B;
     const unsigned long long rem = (nbytes - nfull * B) & ~3ull;
@@ -413,7 +413,7 @@ extern "C" int fmd_demod_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, 
 extern "C" int fmd_time_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, float *d_out, void *stream,
                                int reps, float *ms) {
     if (!c || !ms || reps <= 0) return fmd_set_error(FMD_EINVAL, "bad argument");
-    cudaStream_t s = stream ? (cudaStream_t) stream : c->s_k;
+    cudaStream_t s = (cudaStream_t) stream;
     cudaEvent_t a, b;
     FMD_CUDA(cudaEventCreate(&a));
     FMD_CUDA(cudaEventCreate(&b));

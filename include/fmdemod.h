@@ -6,7 +6,7 @@
  * "floats written" (src/matrix.c:236-273), plus the set-up it does once
  * (src/matrix.c:181-234).  Plain C: pointers, sizes, ints.  No CUDA, C++ or
  * torch types appear in any signature; `stream` arguments are an opaque
- * cudaStream_t passed as void* (NULL = the context's own compute stream).
+ * cudaStream_t passed as void* (NULL = CUDA's default stream).
  *
  * Every entry point returns 0 on success or a negative FMD_E* code and leaves
  * a human-readable message for fmd_last_error() (thread-local).  There is no
