@@ -1,5 +1,6 @@
 #!/bin/bash
 # one GPU-box session: parity tests, benches, ncu captures -> gpurun_out/
+# usage: ./gpu_round.sh [ref] [ncu]
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -30 > gpurun_out/pytest_gpu.log
 tail -3 gpurun_out/pytest_gpu.log
@@ -14,18 +15,17 @@ except Exception as e:
     print("$c failed", e); print(open("gpurun_out/bench_$c.err").read()[-2000:])
 PY
 done
-if [ "$1" = "ref" ]; then
+if [[ " $* " == *" ref "* ]]; then
   timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json
 fi
-if [ "$2" = "ncu" ]; then
+if [[ " $* " == *" ncu "* ]]; then
   CMD="python bench.py --steps 2 --warmup 3 --no-cpu"
   $CMD > gpurun_out/plain.log 2>&1 && \
   ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
-  $CMD > gpurun_out/plain2.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k regex:fmd_fast -s 30 -c 2 -f -o gpurun_out/prof_cfg2 $CMD > gpurun_out/ncu_full.log 2>&1
-  tail -3 gpurun_out/ncu_full.log
-  CMD1="python bench.py --steps 2 --warmup 3 --no-cpu --config cfg1"
-  $CMD1 > gpurun_out/plain3.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k regex:fmd_fast -s 30 -c 2 -f -o gpurun_out/prof_cfg1 $CMD1 > gpurun_out/ncu_full1.log 2>&1
-  tail -3 gpurun_out/ncu_full1.log
+  for c in cfg2 cfg1; do
+    CMDC="python bench.py --steps 2 --warmup 3 --no-cpu --config $c"
+    $CMDC > gpurun_out/plain_$c.log 2>&1 && \
+    ncu --set full --clock-control none --import-source on -k regex:fmd_fast -s 3 -c 1 -f -o gpurun_out/prof_$c $CMDC > gpurun_out/ncu_full_$c.log 2>&1
+    tail -2 gpurun_out/ncu_full_$c.log
+  done
 fi
