@@ -39,9 +39,6 @@
 #define FMD_WARPS (FMD_BLOCK / 32)
 #define FMD_PASS_OUT 128u           /* outputs per warp per pass (32 lanes x 4)   */
 
-#ifndef FMD_ATAN_TERMS
-#define FMD_ATAN_TERMS 7
-#endif
 
 struct FmdStencil {
     float tin[FMD_MAX_TAPS];
@@ -141,16 +138,20 @@ __device__ __forceinline__ float fmd_rcp(float a) {
     return r;
 }
 
-#if FMD_ATAN_TERMS == 8
-#define FMD_ATAN_COEFFS {9.9999933558e-01f, -3.3329860784e-01f, 1.9946565651e-01f, -1.3908629550e-01f, \
-                         9.6421973279e-02f, -5.5912326768e-02f, 2.1862957874e-02f, -4.0545672133e-03f}
-#elif FMD_ATAN_TERMS == 7
-#define FMD_ATAN_COEFFS {9.9999611155e-01f, -3.3317368053e-01f, 1.9807815551e-01f, -1.3233342042e-01f, \
-                         7.9623671389e-02f, -3.3604219717e-02f, 6.8117930109e-03f}
-#else
-#define FMD_ATAN_COEFFS {9.9997721908e-01f, -3.3262282784e-01f, 1.9354037577e-01f, -1.1642648119e-01f, \
-                         5.2647350619e-02f, -1.1719135407e-02f}
-#endif
+/* odd minimax polynomials for atan on [0,1] (Remez, evaluated in f32): max abs error
+ * 6 terms 1.75e-6, 7 terms 3.2e-7, 8 terms 1.35e-7 */
+#define FMD_ATAN_C6 {9.9997721908e-01f, -3.3262282784e-01f, 1.9354037577e-01f, -1.1642648119e-01f, \
+                     5.2647350619e-02f, -1.1719135407e-02f, 0.f, 0.f}
+#define FMD_ATAN_C7 {9.9999611155e-01f, -3.3317368053e-01f, 1.9807815551e-01f, -1.3233342042e-01f, \
+                     7.9623671389e-02f, -3.3604219717e-02f, 6.8117930109e-03f, 0.f}
+#define FMD_ATAN_C8 {9.9999933558e-01f, -3.3329860784e-01f, 1.9946565651e-01f, -1.3908629550e-01f, \
+                     9.6421973279e-02f, -5.5912326768e-02f, 2.1862957874e-02f, -4.0545672133e-03f}
+/* coefficient i of the AT-term polynomial (compile-time indices only) */
+template <int AT>
+__device__ __forceinline__ constexpr float fmd_atan_c(int i) {
+    constexpr float c6[8] = FMD_ATAN_C6, c7[8] = FMD_ATAN_C7, c8[8] = FMD_ATAN_C8;
+    return AT == 6 ? c6[i] : (AT == 7 ? c7[i] : c8[i]);
+}
 
 /* quadrant / sign fix-ups shared by the scalar and the packed atan2 */
 __device__ __forceinline__ float fmd_atan2_finish(float r, float y, float x) {
@@ -160,8 +161,8 @@ __device__ __forceinline__ float fmd_atan2_finish(float r, float y, float x) {
 }
 
 /* two atan2 at once: the reductions, reciprocals and fix-ups are per lane, the polynomial is packed */
+template <int AT>
 __device__ __forceinline__ void fmd_atan2_x2(fmd_f2 im2, fmd_f2 re2, float &out_lo, float &out_hi) {
-    constexpr float cf[FMD_ATAN_TERMS] = FMD_ATAN_COEFFS;
     float yl, yh, xl, xh;
     fmd_upk(im2, yl, yh);
     fmd_upk(re2, xl, xh);
@@ -170,9 +171,9 @@ __device__ __forceinline__ void fmd_atan2_x2(fmd_f2 im2, fmd_f2 re2, float &out_
     const float rch = fmd_rcp(fmd_max3(fabsf(xh), fabsf(yh), 1.0e-30f));
     const fmd_f2 t = fmd_mul2(fmd_pk(mnl, mnh), fmd_pk(rcl, rch));
     const fmd_f2 s = fmd_mul2(t, t);
-    fmd_f2 p = fmd_fma2(fmd_bc(cf[FMD_ATAN_TERMS - 1]), s, fmd_bc(cf[FMD_ATAN_TERMS - 2]));
+    fmd_f2 p = fmd_fma2(fmd_bc(fmd_atan_c<AT>(AT - 1)), s, fmd_bc(fmd_atan_c<AT>(AT - 2)));
 #pragma unroll
-    for (int i = FMD_ATAN_TERMS - 3; i >= 0; --i) p = fmd_fma2(p, s, fmd_bc(cf[i]));
+    for (int i = AT - 3; i >= 0; --i) p = fmd_fma2(p, s, fmd_bc(fmd_atan_c<AT>(i)));
     float rl, rh;
     fmd_upk(fmd_mul2(p, t), rl, rh);
     out_lo = fmd_atan2_finish(rl, yl, xl);
@@ -182,7 +183,7 @@ __device__ __forceinline__ void fmd_atan2_x2(fmd_f2 im2, fmd_f2 re2, float &out_
 /*
  * atan2 with C99 Annex F zero/sign behaviour for finite inputs (what glibc's
  * atan2f gives the reference): octant reduction, one MUFU.RCP, odd minimax
- * polynomial on [0,1] (7 terms: 3.2e-7 max abs error in f32), sign-bit fix-ups.
+ * polynomial on [0,1], sign-bit fix-ups.  Scalar form, 8 terms: the exact path.
  */
 __device__ __forceinline__ float fmd_atan2(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
@@ -193,31 +194,9 @@ __device__ __forceinline__ float fmd_atan2(float y, float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(mx));
     const float t = mn * rc;
     const float s = t * t;
-#if FMD_ATAN_TERMS == 8
-    float p = -4.0545672133e-03f;
-    p = fmaf(p, s, 2.1862957874e-02f);
-    p = fmaf(p, s, -5.5912326768e-02f);
-    p = fmaf(p, s, 9.6421973279e-02f);
-    p = fmaf(p, s, -1.3908629550e-01f);
-    p = fmaf(p, s, 1.9946565651e-01f);
-    p = fmaf(p, s, -3.3329860784e-01f);
-    p = fmaf(p, s, 9.9999933558e-01f);
-#elif FMD_ATAN_TERMS == 7
-    float p = 6.8117930109e-03f;
-    p = fmaf(p, s, -3.3604219717e-02f);
-    p = fmaf(p, s, 7.9623671389e-02f);
-    p = fmaf(p, s, -1.3233342042e-01f);
-    p = fmaf(p, s, 1.9807815551e-01f);
-    p = fmaf(p, s, -3.3317368053e-01f);
-    p = fmaf(p, s, 9.9999611155e-01f);
-#else
-    float p = -1.1719135407e-02f;
-    p = fmaf(p, s, 5.2647350619e-02f);
-    p = fmaf(p, s, -1.1642648119e-01f);
-    p = fmaf(p, s, 1.9354037577e-01f);
-    p = fmaf(p, s, -3.3262282784e-01f);
-    p = fmaf(p, s, 9.9997721908e-01f);
-#endif
+    float p = fmd_atan_c<8>(7);
+#pragma unroll
+    for (int i = 6; i >= 0; --i) p = fmaf(p, s, fmd_atan_c<8>(i));
     float r = p * t;
     if (ay > ax) r = 1.57079637f - r;
     if (__float_as_int(x) < 0) r = 3.14159274f - r;
@@ -373,7 +352,7 @@ fmd_exact_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const 
  * and one 16-byte store.  `nxt` is the first 8 bytes of the lane's raw input of the
  * following pass: lane 0's copy is what lane 31 needs as its input-filter halo.
  */
-template <int NTI, int NTO, bool STORE, bool LITE = false>
+template <int NTI, int NTO, int AT, bool STORE, bool LITE = false>
 __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, const float (&xprev)[4],
                                          float (&xcur)[4], const bool zero_x, float *__restrict__ dst,
                                          const bool do_store, const unsigned lane, const unsigned nxt_lane,
@@ -463,7 +442,7 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, con
          * two exact-zero products takes the same sign fused or not. */
         const fmd_f2 re = fmd_fma2(a, c, fmd_mul2(b, d));
         const fmd_f2 im = fmd_fma2(fmd_neg2(a), d, fmd_mul2(b, c));
-        fmd_atan2_x2(im, re, xcur[j], xcur[j + 2]);
+        fmd_atan2_x2<AT>(im, re, xcur[j], xcur[j + 2]);
     }
 #endif
     if (LITE) xcur[1] = xcur[3] = 0.0f; /* drain pass: only lane 0's first output is ever read */
@@ -531,7 +510,7 @@ __device__ __forceinline__ void fmd_sts128(uint32_t a, uint4 v) {
  * reads them back with one LDS.128, so the loads in flight per SM do not depend on the
  * register budget or on occupancy, and no lane ever reads another lane's slot (no barrier).
  */
-template <int NTI, int NTO>
+template <int NTI, int NTO, int AT>
 __global__ void __launch_bounds__(FMD_BLOCK, FMD_MINB(NTI))
 fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const FmdGeom g, const FmdStencil st,
                 const FmdSections *__restrict__ sec) {
@@ -592,16 +571,16 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     /* pass 0: nothing to store yet */
     FMD_FETCH(0u)
     if (HALO && 1u >= n_ld) nx = make_uint2(FMD_FILL, FMD_FILL);
-    fmd_pass<NTI, NTO, false>(cur, nx, xa, xb, false, dst, false, lane, nxt_lane, st);
+    fmd_pass<NTI, NTO, AT, false>(cur, nx, xa, xb, false, dst, false, lane, nxt_lane, st);
 
     /* passes 1 .. n_it-2 are real and have a real successor: two per trip so the x registers
      * ping-pong without moves */
     unsigned p = 1;
     for (; p + 2 < n_it; p += 2) {
         FMD_FETCH(p)
-        fmd_pass<NTI, NTO, true>(cur, nx, xb, xa, false, dst, keep, lane, nxt_lane, st);
+        fmd_pass<NTI, NTO, AT, true>(cur, nx, xb, xa, false, dst, keep, lane, nxt_lane, st);
         FMD_FETCH(p + 1)
-        fmd_pass<NTI, NTO, true>(cur, nx, xa, xb, false, dst + FMD_PASS_OUT, true, lane, nxt_lane, st);
+        fmd_pass<NTI, NTO, AT, true>(cur, nx, xa, xb, false, dst + FMD_PASS_OUT, true, lane, nxt_lane, st);
         keep = true;
         dst += 2 * FMD_PASS_OUT;
     }
@@ -609,7 +588,7 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     for (; p < n_it; ++p) {
         FMD_FETCH(p)
         if (HALO && p + 1 >= n_ld) nx = make_uint2(FMD_FILL, FMD_FILL);
-        fmd_pass<NTI, NTO, true>(cur, nx, xb, xa, false, dst, keep, lane, nxt_lane, st);
+        fmd_pass<NTI, NTO, AT, true>(cur, nx, xb, xa, false, dst, keep, lane, nxt_lane, st);
         keep = true;
         xb[0] = xa[0]; xb[1] = xa[1]; xb[2] = xa[2]; xb[3] = xa[3];
         dst += FMD_PASS_OUT;
@@ -619,7 +598,7 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     {
         FMD_FETCH(p)
         if (p >= n_ld) cur = fill;
-        fmd_pass<NTI, NTO, true, (NTO <= 2)>(cur, make_uint2(FMD_FILL, FMD_FILL), xb, xa, end_zero, dst, keep, lane,
+        fmd_pass<NTI, NTO, AT, true, (NTO <= 2)>(cur, make_uint2(FMD_FILL, FMD_FILL), xb, xa, end_zero, dst, keep, lane,
                                              nxt_lane, st);
     }
 #undef FMD_FETCH
