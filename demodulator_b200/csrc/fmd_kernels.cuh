@@ -14,6 +14,7 @@
  *      Computes, per chunk-local output k:
  *          s[c]  = (int8)(u8 - 127)                       shiftOrigin   matrix.c:82-98
  *          z[c]  = dc + sum_t tin[t]  * s[c+t]   (-L only) applyComplexFilter filter.c:233-259
+ *                  (evaluated as z/tin[0]: the common factor cancels in the atan2 below)
  *          x[k]  = atan2(Im, Re)(z[2k] * conj(z[2k+1]))   fmDemod       matrix.c:159-176
  *          y[k]  = dco + sum_t tout[t] * x[k+t]           applyFilter   filter.c:212-231
  *      with zero extension past the chunk end, i.e. the steady-state form of the
@@ -427,10 +428,16 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, con
         if (NTI == 0) {
             a = vi[2 * j]; b = vq[2 * j]; c = vi[2 * j + 1]; d = vq[2 * j + 1];
         } else {
-            a = c = fmd_bc(st.dci);
-            b = d = fmd_bc(st.dcq);
+            /* The input stencil is applied up to its (positive) common factor tin[0]^2, which the
+             * atan2 of the product does not see: z'[c] = s[c] + sum_{t>=1} (tin[t]/tin[0]) s[c+t],
+             * plus dcq/tin[0] on the Q lane (the host normalises; dci is 0 for every design). */
+            const fmd_f2 dq = fmd_bc(st.dcq);
+            a = vi[2 * j];
+            b = fmd_add2(vq[2 * j], dq);
+            c = vi[2 * j + 1];
+            d = fmd_add2(vq[2 * j + 1], dq);
 #pragma unroll
-            for (int t = 0; t < NTI; ++t) {
+            for (int t = 1; t < NTI; ++t) {
                 const fmd_f2 tap = fmd_bc(st.tin[t]);
                 a = fmd_fma2(tap, vi[2 * j + t], a);
                 b = fmd_fma2(tap, vq[2 * j + t], b);

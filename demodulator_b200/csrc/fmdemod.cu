@@ -63,6 +63,7 @@ struct fmd_ctx {
     FmdStencil st;
     unsigned nti = 0, nto = 0;
     unsigned atan_terms = 6;
+    bool fast_in_ok = true; /* input stencil could be normalised by its first tap */
     unsigned head = 0; /* outputs at the start of every chunk that are not in steady state */
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
     fmd_slot *slots = nullptr;
@@ -193,6 +194,16 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
         /* the Q lane lacks the "+1" (filter.c:255): same taps, different constant */
         if (!rc) rc = fmd_fold_taps(&c->sec.in[0][0], c->lin, 0, taps_q, &c->st.dcq, &nti_q);
         c->st.dci = dci;
+        /* the streaming kernel applies the input stencil divided by its first tap (the factor
+         * cancels in atan2 of s0*conj(s1)); designs where that is impossible use the exact path */
+        const float c0 = c->st.tin[0];
+        if (!rc && c->nti >= 1 && std::isfinite(c0) && c0 != 0.0f && dci == 0.0f && std::isfinite(c->st.dcq)) {
+            for (unsigned t = 1; t < c->nti; ++t) c->st.tin[t] = (float) ((double) c->st.tin[t] / (double) c0);
+            c->st.dcq = (float) ((double) c->st.dcq / (double) c0);
+            c->st.tin[0] = 1.0f;
+        } else if (!rc) {
+            c->fast_in_ok = false;
+        }
     }
     if (rc) {
         delete c;
@@ -371,7 +382,7 @@ static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned
     const unsigned fast_out = (chunk_out % FMD_PASS_OUT == 0)
                                   ? chunk_out
                                   : (chunk_out >= 2 * FMD_PASS_OUT ? (chunk_out / FMD_PASS_OUT - 1) * FMD_PASS_OUT : 0);
-    const bool fast_ok = fn && aligned && !(c->cfg.flags & FMD_FLAG_EXACT) && fast_out >= FMD_PASS_OUT &&
+    const bool fast_ok = fn && aligned && c->fast_in_ok && !(c->cfg.flags & FMD_FLAG_EXACT) && fast_out >= FMD_PASS_OUT &&
                          fast_out > c->head;
     if (!fast_ok) return launch_exact(c, d_in, d_out, g, s);
 
