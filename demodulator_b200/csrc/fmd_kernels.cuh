@@ -503,7 +503,7 @@ __device__ __forceinline__ void fmd_sts128(uint32_t a, uint4 v) {
 #define FMD_MINB(NTI) ((NTI) == 0 ? 5 : 4) /* resident CTAs per SM the register budget is cut for */
 #endif
 #ifndef FMD_STAGES
-#define FMD_STAGES 8 /* ring depth per lane (power of two): 16 B x FMD_STAGES in flight or landed */
+#define FMD_STAGES 4 /* ring depth per lane: 16 B x FMD_STAGES in flight or landed */
 #endif
 
 /*
@@ -553,62 +553,76 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     const uint4 fill = make_uint4(FMD_FILL, FMD_FILL, FMD_FILL, FMD_FILL);
     const uint32_t sbase = (uint32_t) __cvta_generic_to_shared(&ring[threadIdx.x]);
     constexpr uint32_t SLOT = FMD_BLOCK * 16u;
+    static_assert(S == 4, "the main loop is unrolled by the ring depth");
 
-    /* position q of the segment -> ring slot q % S; past the data: the zero extension */
-    auto issue = [&](unsigned q) {
-        if (q < n_ld) fmd_cp_async16(sbase + (q & (S - 1)) * SLOT, src + 512ull * q);
-        fmd_cp_commit();
-    };
+    /* position q of the segment lives in ring slot q % S; positions >= n_ld do not exist in memory */
 #pragma unroll
-    for (int q = 0; q < S - 1; ++q) issue((unsigned) q);
+    for (int q = 0; q < S - 1; ++q) {
+        if ((unsigned) q < n_ld) fmd_cp_async16(sbase + q * SLOT, src + 512 * q);
+        fmd_cp_commit();
+    }
 
-    float xa[4] = {0.f, 0.f, 0.f, 0.f}, xb[4];
-    uint4 cur;
-    uint2 nx = make_uint2(FMD_FILL, FMD_FILL);
+    float x0[4], x1[4] = {0.f, 0.f, 0.f, 0.f};
+    const uint2 fill2 = make_uint2(FMD_FILL, FMD_FILL);
     /* the chunk head [0, head) belongs to the exact path: those lanes of the very first store
      * of a chunk's first segment keep quiet */
-    bool keep = !(it0 == 0 && k0 < g.head);
+    const bool head_keep = !(it0 == 0 && k0 < g.head);
 
-#define FMD_FETCH(P)                                                     \
-    issue((P) + S - 1);                                                  \
-    fmd_cp_wait<PENDING>();                                              \
-    cur = fmd_lds128(sbase + ((P) & (S - 1)) * SLOT);                    \
-    if (HALO) nx = fmd_lds64(sbase + (((P) + 1) & (S - 1)) * SLOT);
-
-    /* pass 0: nothing to store yet */
-    FMD_FETCH(0u)
-    if (HALO && 1u >= n_ld) nx = make_uint2(FMD_FILL, FMD_FILL);
-    fmd_pass<NTI, NTO, AT, false>(cur, nx, xa, xb, false, dst, false, lane, nxt_lane, st);
-
-    /* passes 1 .. n_it-2 are real and have a real successor: two per trip so the x registers
-     * ping-pong without moves */
-    unsigned p = 1;
-    for (; p + 2 < n_it; p += 2) {
-        FMD_FETCH(p)
-        fmd_pass<NTI, NTO, AT, true>(cur, nx, xb, xa, false, dst, keep, lane, nxt_lane, st);
-        FMD_FETCH(p + 1)
-        fmd_pass<NTI, NTO, AT, true>(cur, nx, xa, xb, false, dst + FMD_PASS_OUT, true, lane, nxt_lane, st);
-        keep = true;
-        dst += 2 * FMD_PASS_OUT;
+    /* pass p = base + U: fetch position p + S - 1 into the slot pass p - 1 just released, wait for
+     * position p (and p + 1 when the input filter needs lane 0's next word), discriminate, and
+     * finish pass p - 1 (store predicate STP).  Slots, source and destination offsets are
+     * immediates because the loop is unrolled by the ring depth. */
+#define FMD_STEP(U, XPREV, XCUR, STP)                                                                   \
+    {                                                                                                   \
+        if (base + (U) + S - 1 < n_ld)                                                                  \
+            fmd_cp_async16(sbase + (((U) + S - 1) & (S - 1)) * SLOT, src + 512 * ((U) + S - 1));        \
+        fmd_cp_commit();                                                                                \
+        fmd_cp_wait<PENDING>();                                                                         \
+        const uint4 cur = fmd_lds128(sbase + (U) * SLOT);                                               \
+        uint2 nx = fill2;                                                                               \
+        if (HALO) nx = fmd_lds64(sbase + (((U) + 1) & (S - 1)) * SLOT);                                 \
+        if (HALO && (U) == S - 1 && base + S >= n_ld) nx = fill2;                                       \
+        fmd_pass<NTI, NTO, AT, true>(cur, nx, XPREV, XCUR, false, dst + 128 * ((U) - 1), STP, lane, nxt_lane, st); \
     }
-    /* what is left: one or two real passes ... */
+
+    unsigned base = 0;
+    for (; base + S <= n_it; base += S) {
+        const bool later = base != 0;
+        FMD_STEP(0, x1, x0, later)
+        FMD_STEP(1, x0, x1, later || head_keep)
+        FMD_STEP(2, x1, x0, true)
+        FMD_STEP(3, x0, x1, true)
+        src += 512 * S;
+        dst += 128 * S;
+    }
+#undef FMD_STEP
+    /* n_it is not a multiple of the ring depth: up to S-1 more real passes, slots by arithmetic.
+     * After the loop above the newest x is in x1 and position `base` sits in slot 0. */
+    unsigned p = base;
     for (; p < n_it; ++p) {
-        FMD_FETCH(p)
-        if (HALO && p + 1 >= n_ld) nx = make_uint2(FMD_FILL, FMD_FILL);
-        fmd_pass<NTI, NTO, AT, true>(cur, nx, xb, xa, false, dst, keep, lane, nxt_lane, st);
-        keep = true;
-        xb[0] = xa[0]; xb[1] = xa[1]; xb[2] = xa[2]; xb[3] = xa[3];
-        dst += FMD_PASS_OUT;
+        const unsigned u = p - base;
+        if (p + S - 1 < n_ld) fmd_cp_async16(sbase + ((u + S - 1) & (S - 1)) * SLOT, src + 512 * (u + S - 1));
+        fmd_cp_commit();
+        fmd_cp_wait<PENDING>();
+        const uint4 cur = fmd_lds128(sbase + (u & (S - 1)) * SLOT);
+        uint2 nx = fill2;
+        if (HALO && p + 1 < n_ld) nx = fmd_lds64(sbase + ((u + 1) & (S - 1)) * SLOT);
+        fmd_pass<NTI, NTO, AT, true>(cur, nx, x1, x0, false, dst + 128 * ((int) u - 1), p >= 2 || (p == 1 && head_keep),
+                                     lane, nxt_lane, st);
+        x1[0] = x0[0]; x1[1] = x0[1]; x1[2] = x0[2]; x1[3] = x0[3];
     }
-    /* ... then the drain pass (position n_it): only lane 0's first NTO-1 outputs of it are consumed
-     * (by lane 31, through the shuffle), so with a 2-tap output stencil half a pass is enough */
+    /* the drain pass (position n_it): only lane 0's first NTO-1 outputs of it are consumed (by lane
+     * 31, through the shuffle), so with a 2-tap output stencil half a pass is enough */
     {
-        FMD_FETCH(p)
-        if (p >= n_ld) cur = fill;
-        fmd_pass<NTI, NTO, AT, true, (NTO <= 2)>(cur, make_uint2(FMD_FILL, FMD_FILL), xb, xa, end_zero, dst, keep, lane,
-                                             nxt_lane, st);
+        const unsigned u = p - base;
+        fmd_cp_commit();
+        fmd_cp_wait<PENDING>();
+        uint4 cur = fill;
+        if (p < n_ld) cur = fmd_lds128(sbase + (u & (S - 1)) * SLOT);
+        fmd_pass<NTI, NTO, AT, true, (NTO <= 2)>(cur, fill2, x1, x0, end_zero, dst + 128 * ((int) u - 1),
+                                                 p >= 2 || (p == 1 && head_keep), lane, nxt_lane, st);
     }
-#undef FMD_FETCH
+
     fmd_cp_wait<0>();
 }
 
