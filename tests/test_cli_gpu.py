@@ -126,3 +126,16 @@ def test_reference_main_over_this_backend(tmp_path, flags, kw, oracle_best):
     out = np.fromfile(dst, np.float32)
     assert out.size == raw.size // 4
     check_close(out, oracle_best.run(raw, po.Config(**kw)), what=f"seam {flags}")
+
+
+def test_cli_all_gpus_round_robin(tmp_path, oracle_best):
+    """FMD_DEVICES=all: the slots of ONE stream go round-robin over every visible GPU and come
+    back in order (chunk-aligned ranges need no overlap and no hand-off state)."""
+    raw = synth.config_signal("cfg2", 24)
+    src, dst = tmp_path / "in.u8", tmp_path / "out.f32"
+    raw.tofile(src)
+    r = subprocess.run([CLI, "-i", str(src), "-o", str(dst), "-S96000", "-l6500", "-L12500"], capture_output=True,
+                       text=True, env=dict(os.environ, FMD_DEVICES="all", FMD_SLOT_MB="1", FMD_STATS="1"))
+    assert r.returncode == 0, r.stderr
+    out = np.fromfile(dst, np.float32)
+    check_close(out, oracle_best.run(raw, po.Config(fs=96000.0, fc_out=6500.0, fc_in=12500.0)), what="all GPUs")
