@@ -407,9 +407,15 @@ def main() -> None:
     ap.add_argument("--per-channel-launch", action="store_true",
                     help="one call per channel instead of one call for the GPU's whole batch of channels")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: anything a library prints meanwhile (NCCL's version
+    # banner, torchrun chatter) is sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     line = reference_arm(args) if args.impl == "reference" else gpu_arm(args)
+    sys.stdout.flush()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
 if __name__ == "__main__":
