@@ -135,6 +135,32 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------- GPU arm
 
+def bind_to_gpu_numa_node(prop) -> str:
+    """Run this rank (and therefore first-touch its pinned staging buffers) on the CPUs next to its
+    GPU: the end-to-end leg is host-memory / PCIe bound, and a remote socket halves it."""
+    if os.environ.get("FMD_BENCH_NO_AFFINITY"):
+        return "off"
+    try:
+        bdf = f"{getattr(prop, 'pci_domain_id', 0):04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = open(f"{base}/numa_node").read().strip()
+        cpulist = open(f"{base}/local_cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus and int(node) >= 0:
+            os.sched_setaffinity(0, cpus)
+            return f"node {node} ({len(cpus)} cpus)"
+        return f"node {node} (not bound)"
+    except Exception as e:  # topology not exposed (VM): leave the scheduler alone
+        return f"unavailable ({type(e).__name__})"
+
+
 def gpu_arm(args) -> dict | None:
     import torch
     import torch.distributed as dist
@@ -151,6 +177,7 @@ def gpu_arm(args) -> dict | None:
                          "for the CPU baseline)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(torch.cuda.get_device_properties(local))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -276,7 +303,7 @@ def gpu_arm(args) -> dict | None:
             "parallelism": f"channel-parallel x{world}, no collective",
             "launches_per_step_per_gpu": n_ch if args.per_channel_launch else 1,
             "l2": "inputs larger than L2: 2 GiB in + 2 GiB out per GPU per step vs 126 MB L2 (no flush needed)",
-            "e2e_samples_per_step_per_gpu": E2E_SAMPLES, "e2e_steps": e2e_steps,
+            "e2e_samples_per_step_per_gpu": E2E_SAMPLES, "e2e_steps": e2e_steps, "cpu_affinity": numa,
         },
         "roofline": {
             "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
