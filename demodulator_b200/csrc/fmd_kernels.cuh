@@ -1,32 +1,30 @@
 /*
  * fmd_kernels.cuh -- sm_100a device code of the FM demodulation hot path.
  *
- * Two kernels:
+ * One launch per call: fmd_fast_kernel<NTI, NTO, AT> (input taps, output taps, atan terms).
  *
- *  fmd_fast_kernel<NTI,NTO>   the bandwidth kernel.  One 16-byte load per lane per
- *      pass (8 complex u8 samples = 4 discriminator pairs), one 16-byte store per
- *      lane per pass (4 floats); every intermediate lives in registers.  A warp
- *      walks a contiguous segment of a chunk; the stencil neighbours that fall
- *      outside a lane come from the next lane by shuffle, and the ones that fall
- *      outside the warp come from the SAME warp's next pass (the output stage
- *      runs one pass behind the discriminator), so no value is computed twice,
- *      nothing is exchanged through memory and there is no block-level barrier.
+ *  streaming CTAs -- the bandwidth part.  One 16-byte load per lane per pass (8 complex u8
+ *      samples = 4 discriminator pairs), one 16-byte store per lane per pass (4 floats); every
+ *      intermediate lives in registers.  A warp walks a contiguous segment of a chunk; the
+ *      stencil neighbours that fall outside a lane come from the next lane by shuffle, and the
+ *      ones that fall outside the warp come from the SAME warp's next pass (the output stage
+ *      runs one pass behind the discriminator), so no value is computed twice, nothing is
+ *      exchanged through memory and there is no block-level barrier.
  *      Computes, per chunk-local output k:
- *          s[c]  = (int8)(u8 - 127)                       shiftOrigin   matrix.c:82-98
- *          z[c]  = dc + sum_t tin[t]  * s[c+t]   (-L only) applyComplexFilter filter.c:233-259
+ *          s[c]  = (int8)(u8 - 127)                        shiftOrigin        matrix.c:82-98
+ *          z[c]  = dc + sum_t tin[t]  * s[c+t]   (-L only)  applyComplexFilter filter.c:233-259
  *                  (evaluated as z/tin[0]: the common factor cancels in the atan2 below)
- *          x[k]  = atan2(Im, Re)(z[2k] * conj(z[2k+1]))   fmDemod       matrix.c:159-176
- *          y[k]  = dco + sum_t tout[t] * x[k+t]           applyFilter   filter.c:212-231
- *      with zero extension past the chunk end, i.e. the steady-state form of the
- *      reference's section sweep (fmd_fold_taps).
+ *          x[k]  = atan2(Im, Re)(z[2k] * conj(z[2k+1]))    fmDemod            matrix.c:159-176
+ *          y[k]  = dco + sum_t tout[t] * x[k+t]            applyFilter        filter.c:212-231
+ *      with zero extension past the chunk end, i.e. the steady-state form of the reference's
+ *      section sweep (fmd_fold_taps in fmd_design.c).
  *
- *  exact path (leading CTAs of the fast kernel, or fmd_exact_kernel stand-alone)
- *      one thread per output, evaluates the reference's
- *      section recurrence op for op (separately rounded mul/add, literal "+1",
- *      head rules, and the x|y_c|y_o arena aliasing that seeds the first outputs
- *      of every chunk when -L is on).  Used for the first few outputs of every
- *      chunk (where the sweep is not in steady state), for ragged remainders, for
- *      chunk sizes the fast kernel does not take, and for FMD_FLAG_EXACT audits.
+ *  exact CTAs -- the first CTAs of the same launch (or fmd_exact_kernel stand-alone): one thread
+ *      per output evaluates the reference's section recurrence op for op (separately rounded
+ *      mul/add, literal "+1", head rules, and the x|y_c|y_o arena aliasing that seeds the first
+ *      outputs of every chunk when -L is on).  They produce the first few outputs of every
+ *      chunk (where the sweep is not in steady state), ragged remainders, chunk sizes the
+ *      streaming part does not take, and everything under FMD_FLAG_EXACT (audits).
  */
 #ifndef FMD_KERNELS_CUH
 #define FMD_KERNELS_CUH
@@ -40,7 +38,7 @@
 #define FMD_WARPS (FMD_BLOCK / 32)
 #define FMD_PASS_OUT 128u           /* outputs per warp per pass (32 lanes x 4)   */
 
-
+/* folded filters (host: fmd_fold_taps); tin[] is divided by tin[0], and so is dcq */
 struct FmdStencil {
     float tin[FMD_MAX_TAPS];
     float dci, dcq;
@@ -79,13 +77,6 @@ __device__ __forceinline__ float fmd_byte_to_float(uint32_t wb) {
     return __uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7540 | I)) - 8388736.0f;
 }
 
-__device__ __forceinline__ void fmd_unpack_word(uint32_t w, float *f) {
-    const uint32_t wb = fmd_bias_bytes(w);
-    f[0] = fmd_byte_to_float<0>(wb);
-    f[1] = fmd_byte_to_float<1>(wb);
-    f[2] = fmd_byte_to_float<2>(wb);
-    f[3] = fmd_byte_to_float<3>(wb);
-}
 
 /* ---- packed f32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, one issue slot for two lanes) ---- */
 typedef unsigned long long fmd_f2;
@@ -350,10 +341,12 @@ fmd_exact_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const 
  * One pass of one lane: unpack `cur` (8 complex samples), input lowpass, four
  * discriminator outputs into xcur; then the output lowpass over the PREVIOUS
  * pass's xprev (neighbours: next lane's xprev, or lane 0's xcur for lane 31)
- * and one 16-byte store.  `nxt` is the first 8 bytes of the lane's raw input of the
- * following pass: lane 0's copy is what lane 31 needs as its input-filter halo.
+ * and one 16-byte store (predicate `do_store`: the very first pass of a segment has no
+ * previous pass, and the head of a chunk belongs to the exact path).  `nxt` is the first
+ * 8 bytes of the lane's raw input of the following pass: lane 0's copy is what lane 31 needs
+ * as its input-filter halo.  LITE: only outputs 0 and 2 are computed (the drain pass).
  */
-template <int NTI, int NTO, int AT, bool STORE, bool LITE = false>
+template <int NTI, int NTO, int AT, bool LITE = false>
 __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, const float (&xprev)[4],
                                          float (&xcur)[4], const bool zero_x, float *__restrict__ dst,
                                          const bool do_store, const unsigned lane, const unsigned nxt_lane,
@@ -362,41 +355,6 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, con
     constexpr int HW = (HC + 1) / 2;          /* ... as 4-byte words (2 complex each)      */
     constexpr int NB = NTO - 1;               /* discriminator outputs needed from the next lane */
 
-#ifdef FMD_SCALAR
-    float f[16 + 4 * (HW > 0 ? HW : 1)];
-    fmd_unpack_word(cur.x, f + 0);
-    fmd_unpack_word(cur.y, f + 4);
-    fmd_unpack_word(cur.z, f + 8);
-    fmd_unpack_word(cur.w, f + 12);
-    if (HW >= 1) {
-        const uint32_t h = __shfl_sync(0xffffffffu, lane == 0 ? nxt.x : cur.x, nxt_lane);
-        fmd_unpack_word(h, f + 16);
-    }
-    if (HW >= 2) {
-        const uint32_t h = __shfl_sync(0xffffffffu, lane == 0 ? nxt.y : cur.y, nxt_lane);
-        fmd_unpack_word(h, f + 20);
-    }
-
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float a, b, c, d;
-        if (NTI == 0) {
-            a = f[4 * j + 0]; b = f[4 * j + 1]; c = f[4 * j + 2]; d = f[4 * j + 3];
-        } else {
-            a = st.dci; b = st.dcq; c = st.dci; d = st.dcq;
-#pragma unroll
-            for (int t = 0; t < NTI; ++t) {
-                a = fmaf(st.tin[t], f[4 * j + 2 * t + 0], a);
-                b = fmaf(st.tin[t], f[4 * j + 2 * t + 1], b);
-                c = fmaf(st.tin[t], f[4 * j + 2 * t + 2], c);
-                d = fmaf(st.tin[t], f[4 * j + 2 * t + 3], d);
-            }
-        }
-        const float re = fmaf(a, c, b * d);
-        const float im = fmaf(-a, d, b * c);
-        xcur[j] = fmd_atan2(im, re);
-    }
-#else
     /* biased words: own four, then the halo from the next lane (lane 31: lane 0's next pass) */
     uint32_t w[6];
     w[0] = fmd_bias_bytes(cur.x);
@@ -451,7 +409,6 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, con
         const fmd_f2 im = fmd_fma2(fmd_neg2(a), d, fmd_mul2(b, c));
         fmd_atan2_x2<AT>(im, re, xcur[j], xcur[j + 2]);
     }
-#endif
     if (LITE) xcur[1] = xcur[3] = 0.0f; /* drain pass: only lane 0's first output is ever read */
     if (zero_x) { /* past the end of the chunk the discriminator output is exactly 0 */
         xcur[0] = 0.0f; xcur[1] = 0.0f; xcur[2] = 0.0f; xcur[3] = 0.0f;
@@ -462,18 +419,16 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, con
 #pragma unroll
     for (int t = 0; t < NB; ++t)
         xn[4 + t] = __shfl_sync(0xffffffffu, lane == 0 ? xcur[t] : xprev[t], nxt_lane);
-    if (STORE) {
-        float4 y;
-        float *yy = reinterpret_cast<float *>(&y);
+    float4 y;
+    float *yy = reinterpret_cast<float *>(&y);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float acc = st.dco;
+    for (int j = 0; j < 4; ++j) {
+        float acc = st.dco;
 #pragma unroll
-            for (int t = 0; t < NTO; ++t) acc = fmaf(st.tout[t], xn[j + t], acc);
-            yy[j] = acc;
-        }
-        if (do_store) *reinterpret_cast<float4 *>(dst) = y;
+        for (int t = 0; t < NTO; ++t) acc = fmaf(st.tout[t], xn[j + t], acc);
+        yy[j] = acc;
     }
+    if (do_store) *reinterpret_cast<float4 *>(dst) = y;
 }
 
 /* ---- cp.async (LDGSTS) ring: global -> shared without staging registers ---- */
@@ -494,9 +449,6 @@ __device__ __forceinline__ uint2 fmd_lds64(uint32_t a) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
     return v;
-}
-__device__ __forceinline__ void fmd_sts128(uint32_t a, uint4 v) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 #ifndef FMD_MINB
@@ -582,7 +534,7 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
         uint2 nx = fill2;                                                                               \
         if (HALO) nx = fmd_lds64(sbase + (((U) + 1) & (S - 1)) * SLOT);                                 \
         if (HALO && (U) == S - 1 && base + S >= n_ld) nx = fill2;                                       \
-        fmd_pass<NTI, NTO, AT, true>(cur, nx, XPREV, XCUR, false, dst + 128 * ((U) - 1), STP, lane, nxt_lane, st); \
+        fmd_pass<NTI, NTO, AT>(cur, nx, XPREV, XCUR, false, dst + 128 * ((U) - 1), STP, lane, nxt_lane, st); \
     }
 
     unsigned base = 0;
@@ -607,7 +559,7 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
         const uint4 cur = fmd_lds128(sbase + (u & (S - 1)) * SLOT);
         uint2 nx = fill2;
         if (HALO && p + 1 < n_ld) nx = fmd_lds64(sbase + ((u + 1) & (S - 1)) * SLOT);
-        fmd_pass<NTI, NTO, AT, true>(cur, nx, x1, x0, false, dst + 128 * ((int) u - 1), p >= 2 || (p == 1 && head_keep),
+        fmd_pass<NTI, NTO, AT>(cur, nx, x1, x0, false, dst + 128 * ((int) u - 1), p >= 2 || (p == 1 && head_keep),
                                      lane, nxt_lane, st);
         x1[0] = x0[0]; x1[1] = x0[1]; x1[2] = x0[2]; x1[3] = x0[3];
     }
@@ -619,7 +571,7 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
         fmd_cp_wait<PENDING>();
         uint4 cur = fill;
         if (p < n_ld) cur = fmd_lds128(sbase + (u & (S - 1)) * SLOT);
-        fmd_pass<NTI, NTO, AT, true, (NTO <= 2)>(cur, fill2, x1, x0, end_zero, dst + 128 * ((int) u - 1),
+        fmd_pass<NTI, NTO, AT, (NTO <= 2)>(cur, fill2, x1, x0, end_zero, dst + 128 * ((int) u - 1),
                                                  p >= 2 || (p == 1 && head_keep), lane, nxt_lane, st);
     }
 

@@ -189,3 +189,55 @@ def test_atan2_special_values():
     with fm.Demodulator(**demod_kwargs(cfg)) as d:
         out = d.process(pat)
     check_close(out, want, tol=2e-6, what="special values")
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_filter_configurations(seed, oracle_port):
+    """-d/-D/-m/-e/-l/-L/-S/-b drawn at random (both families, orders 1..8, chunk sizes from 4 KiB
+    to 512 KiB, ragged tails): stencil widths 1..5 on either filter, both atan polynomial lengths."""
+    rng = np.random.default_rng(1000 + seed)
+    deg_out = int(rng.integers(1, 9))
+    with_in = bool(rng.integers(0, 2))
+    deg_in = int(rng.integers(0, 9)) if with_in else 0
+    mode = int(rng.integers(0, 4)) if with_in else int(rng.integers(0, 2))
+    fs = float(rng.choice([48000.0, 96000.0, 125000.0, 250000.0]))
+    fc_out = float(rng.uniform(0.04, 0.3) * fs)
+    fc_in = float(rng.uniform(0.05, 0.3) * fs) if with_in else 0.0
+    eps = float(rng.choice([0.3, 0.2, 0.1]))
+    bs = int(rng.choice([4096, 65536, B, 2 * B]))
+    nbytes = int(rng.integers(1, 4)) * bs + int(rng.choice([0, 0, 4 * int(rng.integers(64, bs // 8))]))
+    raw = np.resize(synth.config_signal("cfg2", 2, seed=seed), nbytes)
+    cfg = po.Config(fs=fs, fc_in=fc_in, fc_out=fc_out, eps=eps, deg_in=deg_in, deg_out=deg_out, mode=mode)
+    whole = nbytes // bs * bs
+    want = [oracle_port.run(raw[:whole], cfg, chunk_bytes=bs)]
+    if nbytes > whole:
+        want.append(oracle_port.run(raw[whole:], cfg, chunk_bytes=nbytes - whole))
+    want = np.concatenate(want)
+    with fm.Demodulator(bufSize=bs, **demod_kwargs(cfg)) as d:
+        out = d.process(raw)
+    assert out.size == want.size
+    scale = float(np.abs(want[np.isfinite(want)]).max(initial=1.0))
+    check_close(out, want, tol=1e-4 + 3e-6 * scale, what=f"seed {seed}: {cfg} bs={bs} n={nbytes}")
+
+
+@pytest.mark.parametrize("nbytes,bs,with_in", [(3 * B, B, True), (B + 1000 * 4, B, True), (B + 516, B, False),
+                                               (5 * 4096 + 260, 4096, True), (7 * 512, 512, False),
+                                               (2 * B - 4, B, True), (640, 64, True)])
+def test_no_out_of_bounds_writes(nbytes, bs, with_in):
+    """compute-sanitizer is closed on this pool, so: guard bands around the output (and the input
+    placed flush against the end of its allocation) must come back untouched for ragged sizes,
+    tiny chunks and whole chunks alike."""
+    import torch
+    guard = 4096
+    raw = np.resize(synth.config_signal("cfg1", 1), nbytes)
+    n_out = nbytes // 4
+    d_in = torch.from_numpy(raw).cuda()
+    canvas = torch.full((guard + n_out + guard,), 12345.0, dtype=torch.float32, device="cuda")
+    cfg = po.Config(fs=96000.0, fc_out=6500.0, fc_in=12500.0 if with_in else 0.0)
+    with fm.Demodulator(bufSize=bs, **demod_kwargs(cfg)) as d:
+        s = torch.cuda.current_stream()
+        d.process_device(d_in.data_ptr(), nbytes, canvas.data_ptr() + 4 * guard, n_out and s.cuda_stream)
+        s.synchronize()
+    assert bool((canvas[:guard] == 12345.0).all()) and bool((canvas[guard + n_out:] == 12345.0).all())
+    out = canvas[guard:guard + n_out].cpu().numpy()
+    assert not np.any(out == 12345.0), "an output was never written"
