@@ -392,7 +392,11 @@ static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned
      * enough that the grid still holds a few waves of warps for small inputs */
     const unsigned long long total_iters = (unsigned long long) iters_chunk * nchunks;
     const unsigned long long want_warps = (unsigned long long) c->sm_count * 64ull * 2ull;
-    unsigned ips = 16;
+    /* measured on B200 (profiles/): without the input filter the kernel is HBM-bound and short
+     * segments keep the chip inside a compact window of memory (16 passes: 6.6 TB/s, 64: 6.4);
+     * with it the kernel is pipe-bound and longer segments amortise the drain pass (64: 5.6 TB/s,
+     * 16: 5.4) */
+    unsigned ips = c->nti ? 64u : 16u;
     if (const char *e = getenv("FMD_IPS")) ips = (unsigned) atoi(e); /* tuning experiments only */
     if (ips < 1) ips = 1;
     while (ips > 4 && total_iters / ips < want_warps / 4) ips >>= 1;

@@ -236,7 +236,7 @@ def test_no_out_of_bounds_writes(nbytes, bs, with_in):
     cfg = po.Config(fs=96000.0, fc_out=6500.0, fc_in=12500.0 if with_in else 0.0)
     with fm.Demodulator(bufSize=bs, **demod_kwargs(cfg)) as d:
         s = torch.cuda.current_stream()
-        d.process_device(d_in.data_ptr(), nbytes, canvas.data_ptr() + 4 * guard, n_out and s.cuda_stream)
+        d.process_device(d_in.data_ptr(), nbytes, canvas.data_ptr() + 4 * guard, s.cuda_stream)
         s.synchronize()
     assert bool((canvas[:guard] == 12345.0).all()) and bool((canvas[guard + n_out:] == 12345.0).all())
     out = canvas[guard:guard + n_out].cpu().numpy()
