@@ -241,3 +241,27 @@ def test_no_out_of_bounds_writes(nbytes, bs, with_in):
     assert bool((canvas[:guard] == 12345.0).all()) and bool((canvas[guard + n_out:] == 12345.0).all())
     out = canvas[guard:guard + n_out].cpu().numpy()
     assert not np.any(out == 12345.0), "an output was never written"
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg3"])
+def test_full_size_properties(name, oracle_best):
+    """BASELINE size (1 Gi samples = 2 GiB in, 2 GiB out on the device, far beyond L2) through
+    size-independent properties: the input is a 16-chunk period tiled 512 times, chunks are
+    independent, so the output must be the same 16-chunk period 512 times, bit for bit; and that
+    period must match the reference."""
+    import torch
+    period_chunks, reps = 16, 512
+    base = synth.config_signal(name, period_chunks)
+    cfg = po.Config(**synth.CONFIGS[name]["opts"])
+    d_in = torch.from_numpy(base).cuda().repeat(reps)
+    d_out = torch.empty(d_in.numel() // 4, dtype=torch.float32, device="cuda")
+    with fm.Demodulator(**demod_kwargs(cfg)) as d:
+        s = torch.cuda.current_stream()
+        d.process_device(d_in.data_ptr(), d_in.numel(), d_out.data_ptr(), s.cuda_stream)
+        s.synchronize()
+    o = d_out.view(reps, -1).view(torch.int32)
+    assert bool((o == o[0:1]).all()), "tiles differ: a chunk saw state from outside itself"
+    check_close(d_out[: base.size // 4].cpu().numpy(), oracle_best.run(base, cfg), what=f"{name} first period")
+    # checksum of checksums: per-chunk sums of |y| repeat with the period
+    sums = d_out.view(reps * period_chunks, -1).abs().sum(dim=1).view(reps, period_chunks)
+    assert bool((sums == sums[0:1]).all())
