@@ -61,6 +61,7 @@ struct FmdSections {
     float in[FMD_MAX_SECTIONS][6];
     float out[FMD_MAX_SECTIONS][6];
     int lin, lout;
+    int conditioner; /* consumerArgs.mode bits 2-3 (-q): 0 shiftOrigin, 3 normalizeInput */
 };
 
 /* ------------------------------------------------------------------ helpers */
@@ -244,9 +245,14 @@ struct FmdShiftedLane {
     const uint8_t *cin;
     long long nc;
     int q;
+    int conditioner;
     __device__ float operator()(long long c) const {
         if (c >= nc) return 0.0f;
-        return (float) (int8_t) (cin[2 * c + q] - 127);
+        const uint8_t u = cin[2 * c + q];
+        /* -q3, matrix.c:100-118: (float)((double)((float)u * (float)(2/255)) - 1.0); the double
+         * subtraction of a float and 1 is exact, so one rounded float subtraction is the same */
+        if (conditioner == 3) return __fsub_rn(__fmul_rn((float) u, (float) (2. / 255.)), 1.0f);
+        return (float) (int8_t) (u - 127); /* matrix.c:82-98 */
     }
 };
 
@@ -257,7 +263,7 @@ struct FmdComplexLane {
     const FmdSections *sec;
     int q;
     __device__ float operator()(long long c) const {
-        FmdShiftedLane sl{cin, nc, q};
+        FmdShiftedLane sl{cin, nc, q, sec->conditioner};
         if (sec->lin == 0) return sl(c);
         return fmd_sweep_cone(c, nc, sec->lin, sec->in, q == 0, sl, FmdZeroInit());
     }

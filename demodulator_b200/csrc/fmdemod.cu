@@ -150,9 +150,12 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
     if (cfg.chunk_bytes == 0 || (cfg.chunk_bytes & 3u) || cfg.chunk_bytes > (1ull << 34))
         return fmd_set_error(FMD_EINVAL, "chunk_bytes must be a positive multiple of 4 (got %llu)",
                              (unsigned long long) cfg.chunk_bytes);
-    if ((cfg.mode >> 2) & 3u)
-        return fmd_set_error(FMD_EINVAL, "input conditioner -q%u is outside the accelerated path (only -q0)",
-                             (cfg.mode >> 2) & 3u);
+    const unsigned conditioner = (cfg.mode >> 2) & 3u;
+    if (conditioner == 1u || conditioner == 2u)
+        return fmd_set_error(FMD_EINVAL,
+                             "input conditioner -q%u is outside the accelerated path (-q0 and -q3 only: -q1 is a "
+                             "serial recurrence across chunks, -q2 reads past its buffer in the reference)",
+                             conditioner);
     if (((cfg.mode >> 4) & 3u) == 0)
         return fmd_set_error(FMD_EINVAL, "demodulation off (-c) is unreachable in the reference CLI and unsupported");
 
@@ -180,6 +183,9 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
     memset(&c->st, 0, sizeof c->st);
     c->sec.lin = (int) c->lin;
     c->sec.lout = (int) c->lout;
+    c->sec.conditioner = (int) conditioner;
+    /* -q3 (normalizeInput) is served by the op-for-op path only, for now */
+    if (conditioner == 3u) c->fast_in_ok = false;
 
     int rc = fmd_design_sos(cfg.mode & 1u, cfg.out_degree, cfg.lowpass_out, cfg.sample_rate, cfg.epsilon,
                             &c->sec.out[0][0]);

@@ -151,6 +151,16 @@ void fmo_shift(const uint8_t *in, size_t n, float *out) {
     }
 }
 
+/* src/matrix.c:100-118 (-q3): out = (float)((double)((float)u * (float)(2/255)) - 1.0) */
+void fmo_normalize(const uint8_t *in, size_t n, float *out) {
+    const float denom = 2. / 255.;
+    size_t i;
+    for (i = 0; i < n; ++i) {
+        const float p = (float) in[i] * denom;
+        out[i] = (float) ((double) p - 1.);
+    }
+}
+
 /* src/matrix.c:159-176: s0*conj(s1) over NON-overlapping pairs, atan2f, NaN->0 */
 void fmo_discriminate(const float *iq, size_t n, float *out) {
     size_t p;
@@ -249,9 +259,9 @@ static int one_chunk(const uint8_t *in, size_t B, const fmo_config *cfg,
     float *dem = calloc(ylen, sizeof(float));
     float *y = calloc(ylen, sizeof(float));
     size_t i;
-    (void) cfg;
     if (!xs || !dem || !y) return -1;
-    fmo_shift(in, B, xs);
+    if (((cfg->mode >> 2) & 3u) == 3u) fmo_normalize(in, B, xs);   /* matrix.c:208-222 */
+    else fmo_shift(in, B, xs);
 
     if (Lin) {
         const size_t clen = nc + 2 * Lin;
@@ -303,6 +313,7 @@ size_t fmo_process_chunks(const uint8_t *in, size_t nchunks, size_t B,
     if (cfg->fc_in != 0. && !deg_in) deg_in = cfg->deg_out;          /* matrix.c:190-192 */
     if (cfg->fc_in == 0. && deg_in) return 0;                        /* reference: undefined */
     if (!cfg->deg_out || (B & 3)) return 0;
+    if (((cfg->mode >> 2) & 3u) == 1u || ((cfg->mode >> 2) & 3u) == 2u) return 0; /* -q1/-q2: not restated */
     Lin = fmo_sections(deg_in);
     Lout = fmo_sections(cfg->deg_out);
     /* the aliasing model above assumes the chunk is longer than the head it re-reads */

@@ -33,7 +33,8 @@ typedef struct {
     double eps;       /* -e / 10                       */
     unsigned deg_in;  /* -D  (0 = inherit deg_out when fc_in != 0) */
     unsigned deg_out; /* -d                            */
-    unsigned mode;    /* bit0: output filter Chebyshev, bit1: input filter Chebyshev */
+    unsigned mode;    /* bit0: output filter Chebyshev, bit1: input filter Chebyshev,
+                         bits 2-3: input conditioner (-q): 0 shiftOrigin, 3 normalizeInput */
 } fmo_config;
 
 size_t fmo_sections(unsigned degree);
@@ -43,6 +44,8 @@ void fmo_design_sos(unsigned kind, unsigned degree, double fc, double fs, double
 
 /* u8 -> float, value-127 wrapped to int8 */
 void fmo_shift(const uint8_t *in, size_t n, float *out);
+/* u8 -> float in [-1, 1] (-q3) */
+void fmo_normalize(const uint8_t *in, size_t n, float *out);
 
 /* n floats (n/2 complex, n/4 pairs) -> n/4 phase differences */
 void fmo_discriminate(const float *iq, size_t n, float *out);

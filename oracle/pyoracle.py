@@ -48,7 +48,7 @@ class Config:
     eps: float = 0.3
     deg_in: int = 0
     deg_out: int = 3
-    mode: int = 0  # bit0: output Chebyshev, bit1: input Chebyshev
+    mode: int = 0  # bit0: output Chebyshev, bit1: input Chebyshev, bits 2-3: -q (0 or 3)
 
 
 class _FmoConfig(C.Structure):
@@ -71,6 +71,8 @@ class Port:
         L.fmo_shift.restype = None
         L.fmo_discriminate.argtypes = [_f32p, C.c_size_t, _f32p]
         L.fmo_discriminate.restype = None
+        L.fmo_normalize.argtypes = [_u8p, C.c_size_t, _f32p]
+        L.fmo_normalize.restype = None
         L.fmo_sweep_lane.argtypes = [_f32p, _f32p, C.c_size_t, C.c_size_t, _f32p, C.c_int]
         L.fmo_sweep_lane.restype = None
         L.fmo_process_chunks.argtypes = [_u8p, C.c_size_t, C.c_size_t, C.POINTER(_FmoConfig), _f32p]
@@ -84,6 +86,11 @@ class Port:
     def shift(self, raw: np.ndarray) -> np.ndarray:
         out = np.empty(raw.size, np.float32)
         self.lib.fmo_shift(np.ascontiguousarray(raw, np.uint8), raw.size, out)
+        return out
+
+    def normalize(self, raw: np.ndarray) -> np.ndarray:
+        out = np.empty(raw.size, np.float32)
+        self.lib.fmo_normalize(np.ascontiguousarray(raw, np.uint8), raw.size, out)
         return out
 
     def discriminate(self, iq: np.ndarray) -> np.ndarray:
@@ -143,6 +150,8 @@ class Ref:
         L.ref_shift_origin.restype = None
         L.ref_fm_demod.argtypes = [_f32p, C.c_size_t, _f32p]
         L.ref_fm_demod.restype = None
+        L.ref_normalize_input.argtypes = [_u8p, C.c_size_t, _f32p]
+        L.ref_normalize_input.restype = None
         L.ref_apply_filter.argtypes = [_f32p, _f32p, C.c_size_t, C.c_size_t, _f32p]
         L.ref_apply_filter.restype = None
         L.ref_apply_complex_filter.argtypes = [_f32p, _f32p, C.c_size_t, C.c_size_t, _f32p]
@@ -159,6 +168,11 @@ class Ref:
     def shift(self, raw: np.ndarray) -> np.ndarray:
         out = np.empty(raw.size, np.float32)
         self.lib.ref_shift_origin(np.ascontiguousarray(raw, np.uint8), raw.size, out)
+        return out
+
+    def normalize(self, raw: np.ndarray) -> np.ndarray:
+        out = np.empty(raw.size, np.float32)
+        self.lib.ref_normalize_input(np.ascontiguousarray(raw, np.uint8), raw.size, out)
         return out
 
     def discriminate(self, iq: np.ndarray) -> np.ndarray:

@@ -37,6 +37,10 @@ void ref_shift_origin(const uint8_t *in, size_t len, float *out) {
     shiftOrigin((void *) in, len, out);
 }
 
+void ref_normalize_input(const uint8_t *in, size_t len, float *out) {
+    normalizeInput((void *) in, len, out);
+}
+
 void ref_fm_demod(const float *in, size_t len, float *out) {
     fmDemod(in, len, out);
 }
@@ -65,6 +69,7 @@ size_t ref_run_chunks(const uint8_t *in, size_t nchunks, size_t bufSize, unsigne
     if (fcIn != 0. && !degIn) degIn = degOut;            /* src/matrix.c:190-192 */
     if (fcIn == 0. && degIn) return 0;  /* -D without -L: reference reads an undesigned filter */
     if (!degOut || (bufSize & 3)) return 0;
+    if (((mode >> 2) & 3) == 1 || ((mode >> 2) & 3) == 2) return 0; /* -q1/-q2: stateful / heap overrun */
     const size_t nOut = bufSize >> 2;
     const size_t secOut = sectionsFor(degOut), secIn = sectionsFor(degIn);
     REAL sosOut[secOut ? secOut : 1][6];
@@ -81,7 +86,8 @@ size_t ref_run_chunks(const uint8_t *in, size_t nchunks, size_t bufSize, unsigne
 
     for (c = 0; c < nchunks; ++c) {
         REAL *res;
-        shiftOrigin((void *) (in + c * bufSize), bufSize, arena);
+        if (((mode >> 2) & 3) == 3) normalizeInput((void *) (in + c * bufSize), bufSize, arena);  /* -q3 */
+        else shiftOrigin((void *) (in + c * bufSize), bufSize, arena);
         if (!degIn) {
             res = arena + bufSize;
             fmDemod(arena, bufSize, demod);

@@ -52,6 +52,10 @@ CASES = [
      dict(fs=96000.0, fc_out=12500.0, mode=1, eps=0.5)),
     ("D7_d4_L", "cfg2", 2, ["-S96000", "-l9600", "-d4", "-D7", "-L12500", "-m2"],
      dict(fs=96000.0, fc_out=9600.0, fc_in=12500.0, deg_out=4, deg_in=7, mode=2)),
+    # -q3: normalizeInput instead of shiftOrigin (mode bits 2-3)
+    ("q3", "cfg1", 2, ["-S96000", "-l12500", "-q3"], dict(fs=96000.0, fc_out=12500.0, mode=12)),
+    ("q3_L", "cfg2", 2, ["-S96000", "-l6500", "-L12500", "-q3"],
+     dict(fs=96000.0, fc_out=6500.0, fc_in=12500.0, mode=12)),
 ]
 
 # byte patterns exercising the int8 wrap (255 -> -128), signed zeros and the +-pi cut

@@ -42,6 +42,7 @@ CASES = [
     ("cfg2", ["-S96000", "-l12500", "-d5", "-L12500", "-m3"],
      dict(fs=96000.0, fc_out=12500.0, fc_in=12500.0, deg_out=5, mode=3)),
     ("cfg1", [], dict()),
+    ("cfg2", ["-S96000", "-l6500", "-L12500", "-q3"], dict(fs=96000.0, fc_out=6500.0, fc_in=12500.0, mode=12)),
 ]
 
 

@@ -175,6 +175,8 @@ def test_rejects_what_the_reference_leaves_undefined():
         fm.Demodulator(bufSize=6)
     with pytest.raises(fm.FmdError):
         fm.Demodulator(mode=0x4)  # -q1
+    with pytest.raises(fm.FmdError):
+        fm.Demodulator(mode=0x8)  # -q2
 
 
 def test_atan2_special_values():
