@@ -267,3 +267,34 @@ def test_full_size_properties(name, oracle_best):
     # checksum of checksums: per-chunk sums of |y| repeat with the period
     sums = d_out.view(reps * period_chunks, -1).abs().sum(dim=1).view(reps, period_chunks)
     assert bool((sums == sums[0:1]).all())
+
+
+def test_contexts_are_independent_across_threads(oracle_best):
+    """One context per (GPU, channel), no global state: four host threads, four different filter
+    set-ups, the same GPU, all at once."""
+    import threading
+    setups = [("cfg1", dict(fs=96000.0, fc_out=12500.0)),
+              ("cfg2", dict(fs=96000.0, fc_out=6500.0, fc_in=12500.0)),
+              ("cfg3", dict(fs=48000.0, fc_out=15000.0)),
+              ("cfg2", dict(fs=96000.0, fc_out=12500.0, fc_in=12500.0, deg_out=5, mode=3))]
+    results, errors = {}, []
+
+    def work(i, sig, kw):
+        try:
+            raw = synth.config_signal(sig, 6, seed=50 + i)
+            cfg = po.Config(**kw)
+            with fm.Demodulator(**demod_kwargs(cfg)) as d:
+                for _ in range(3):
+                    out = d.process(raw)
+            results[i] = (raw, cfg, out.copy())
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    ts = [threading.Thread(target=work, args=(i, s, k)) for i, (s, k) in enumerate(setups)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+    for i, (raw, cfg, out) in results.items():
+        check_close(out, oracle_best.run(raw, cfg), what=f"thread {i}")
