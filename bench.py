@@ -7,9 +7,10 @@ Metric (BASELINE.json): input MS/s (complex IQ samples per second), whole job ov
 the fraction of the HBM roofline the dominant kernel reaches (4 algorithmic bytes per input
 sample: 2 B read + 4 B written per 2 samples).
 
-A "step" = one pass of the hot path (fmd_demod_device: fused unpack -> [input lowpass] ->
-discriminator -> output lowpass, + the chunk-head fix-up kernel) over CHANNELS_PER_GPU independent
-channels of synthetic FM IQ that are already resident in HBM.  Default workload = BASELINE.json
+A "step" = one pass of the hot path (fmd_demod_device: ONE launch of the fused unpack -> [input
+lowpass] -> discriminator -> output lowpass kernel, whose leading CTAs also produce the chunk heads
+op for op) over CHANNELS_PER_GPU independent channels of synthetic FM IQ that lie back to back in
+HBM (chunks are independent, so a batch of channels is one call).  Default workload = BASELINE.json
 configs[1] (cfg2: 192 kS/s, -L12500 -l6500 -S96000, both filter stages).  N > 1: one process per
 GPU (torchrun), same per-GPU work (weak scaling), no data-path collective -- channels are
 independent; NCCL is used only for the start barrier and the MAX of the timings.
