@@ -458,7 +458,7 @@ __device__ __forceinline__ uint2 fmd_lds64(uint32_t a) {
 }
 
 #ifndef FMD_MINB
-#define FMD_MINB(NTI) ((NTI) == 0 ? 4 : 5) /* resident CTAs per SM the register budget is cut for */
+#define FMD_MINB(NTI) 4 /* resident CTAs per SM the register budget is cut for */
 #endif
 #ifndef FMD_STAGES
 #define FMD_STAGES 4 /* ring depth per lane: 16 B x FMD_STAGES in flight or landed */
