@@ -461,7 +461,7 @@ __device__ __forceinline__ uint2 fmd_lds64(uint32_t a) {
 #define FMD_MINB(NTI) 4 /* resident CTAs per SM the register budget is cut for */
 #endif
 #ifndef FMD_STAGES
-#define FMD_STAGES 4 /* ring depth per lane: 16 B x FMD_STAGES in flight or landed */
+#define FMD_STAGES 8 /* ring depth per lane (4 or 8): 16 B x FMD_STAGES in flight or landed */
 #endif
 
 /*
@@ -511,7 +511,7 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     const uint4 fill = make_uint4(FMD_FILL, FMD_FILL, FMD_FILL, FMD_FILL);
     const uint32_t sbase = (uint32_t) __cvta_generic_to_shared(&ring[threadIdx.x]);
     constexpr uint32_t SLOT = FMD_BLOCK * 16u;
-    static_assert(S == 4, "the main loop is unrolled by the ring depth");
+    static_assert(S == 4 || S == 8, "the main loop is unrolled by the ring depth");
 
     /* position q of the segment lives in ring slot q % S; positions >= n_ld do not exist in memory */
 #pragma unroll
@@ -550,6 +550,12 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
         FMD_STEP(1, x0, x1, later || head_keep)
         FMD_STEP(2, x1, x0, true)
         FMD_STEP(3, x0, x1, true)
+        if (S == 8) {
+            FMD_STEP(4, x1, x0, true)
+            FMD_STEP(5, x0, x1, true)
+            FMD_STEP(6, x1, x0, true)
+            FMD_STEP(7, x0, x1, true)
+        }
         src += 512 * S;
         dst += 128 * S;
     }
