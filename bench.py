@@ -329,11 +329,33 @@ def gpu_arm(args) -> dict | None:
 
 # --------------------------------------------------------------------------- CPU reference arm
 
-def _ref_binary() -> str:
+def _ref_binary() -> str | None:
+    """The unmodified reference CLI (built where /root/reference exists, travels as a prebuilt
+    file); None when it is absent -- the CPU legs then time the oracle port instead."""
     from oracle import pyoracle as po
-    if not os.path.exists(po.REF_BIN):
-        raise FileNotFoundError(f"{po.REF_BIN} missing (built by `make -C oracle ref` where /root/reference exists)")
-    return po.REF_BIN
+    return po.REF_BIN if os.path.exists(po.REF_BIN) and os.access(po.REF_BIN, os.X_OK) else None
+
+
+def _port_worker(args) -> float:
+    """One process of the fallback CPU leg: the oracle port (fm_oracle.c) on `samples` samples."""
+    cfgname, samples = args
+    from demodulator_b200 import synth
+    from oracle import pyoracle as po
+    sig = synth.CONFIGS[cfgname]
+    base = synth.fm_iq_u8(BASE_CHUNKS * CHUNK // 2, sig["fs_sig"], sig["df"], sig["fm"], 100)
+    raw = np.resize(base, 2 * samples)
+    P = po.port()
+    t0 = time.perf_counter()
+    P.run(raw, po.Config(**sig["opts"]))
+    return time.perf_counter() - t0
+
+
+def _run_port_processes(cfgname: str, samples: int, nproc: int) -> float:
+    import multiprocessing as mp
+    t0 = time.perf_counter()
+    with mp.get_context("spawn").Pool(nproc) as pool:
+        pool.map(_port_worker, [(cfgname, samples)] * nproc)
+    return time.perf_counter() - t0
 
 
 def _scratch_dir() -> str:
@@ -356,6 +378,12 @@ def cpu_baseline(cfgname: str, d_in0=None, samples: int = 384 << 20) -> dict:
     """The reference CLI (1 reader + 1 worker thread) on a bounded sample of the same workload."""
     from demodulator_b200 import synth
     binary = _ref_binary()
+    if binary is None:  # reference binary did not travel: time the plain-C port, one thread
+        samples = 32 << 20
+        sec = min(_port_worker((cfgname, samples)) for _ in range(2))
+        return {"value": round(samples / sec / 1e6, 2), "unit": "MS/s", "cores": 1, "kind": "port",
+                "sample": f"{samples >> 20} Mi samples of the same signal, oracle/fm_oracle.c in-process, best of 2",
+                "host_cores_available": os.cpu_count()}
     path = os.path.join(_scratch_dir(), f"fmd_bench_{os.getpid()}.u8")
     nbytes = 2 * samples
     try:
@@ -386,6 +414,8 @@ def reference_arm(args) -> dict | None:
     cfgname = args.config
     binary = _ref_binary()
     ncpu = os.cpu_count() or 2
+    if binary is None:
+        return _reference_arm_port(args, cfgname, ncpu)
     nproc = max(1, ncpu // 2)                       # each reference process runs 2 threads
     steps_total = args.steps + args.warmup
     # bounded sample: aim at ~120 s for the whole run at ~30 MS/s per process
@@ -419,6 +449,28 @@ def reference_arm(args) -> dict | None:
                    "parallelism": f"{nproc} processes x 2 threads on {ncpu} host cores"},
         "cpu_baseline": {"value": round(value, 2), "unit": "MS/s", "cores": min(2 * nproc, ncpu),
                          "kind": "reference", "sample": sample},
+        "e2e": {"value": round(value, 2), "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def _reference_arm_port(args, cfgname: str, ncpu: int) -> dict:
+    """--impl reference when oracle/_ref/ did not travel: the plain-C port on every host core."""
+    per_proc = max(4 << 20, min(int(120.0 * 15e6 / max(args.steps + args.warmup, 1)), 64 << 20))
+    per_proc = per_proc // (CHUNK // 2) * (CHUNK // 2)
+    for _ in range(args.warmup):
+        _run_port_processes(cfgname, per_proc, ncpu)
+    t = sum(_run_port_processes(cfgname, per_proc, ncpu) for _ in range(args.steps))
+    value = ncpu * per_proc * args.steps / t / 1e6
+    sample = f"{ncpu} processes x {per_proc >> 20} Mi samples per step, oracle/fm_oracle.c (reference binary absent)"
+    return {
+        "impl": "reference", "metric": "input MS/s (complex IQ samples/s), whole job",
+        "value": round(value, 2), "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(t / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD[cfgname], "name": cfgname, "chunk_bytes": CHUNK,
+                   "parallelism": f"{ncpu} processes on {ncpu} host cores"},
+        "cpu_baseline": {"value": round(value, 2), "unit": "MS/s", "cores": ncpu, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 2), "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -440,9 +440,14 @@ extern "C" int fmd_demod_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, 
     const unsigned long long nfull = nbytes / B;
     const unsigned long long rem = (nbytes - nfull * B) & ~3ull;
     if (nfull > 0xffffffffull) return fmd_set_error(FMD_EINVAL, "too many chunks in one call");
+    /* launch on the context's device whatever the calling thread's current device is */
+    int prev = -1;
+    FMD_CUDA(cudaGetDevice(&prev));
+    if (prev != c->device) FMD_CUDA(cudaSetDevice(c->device));
     int rc = launch_chunks(c, d_in, d_out, (unsigned) nfull, (unsigned) (B >> 2), B, s);
     if (!rc && rem)
         rc = launch_chunks(c, d_in + nfull * B, d_out + nfull * (B >> 2), 1u, (unsigned) (rem >> 2), B, s);
+    if (prev != c->device && prev >= 0) cudaSetDevice(prev);
     return rc;
 }
 
