@@ -147,9 +147,14 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
     if (cfg.out_degree == 0 || fmd_sections(cfg.out_degree) > FMD_MAX_SECTIONS ||
         fmd_sections(cfg.in_degree) > FMD_MAX_SECTIONS)
         return fmd_set_error(FMD_EINVAL, "filter degree outside 1..%d", 2 * FMD_MAX_SECTIONS);
-    if (cfg.chunk_bytes == 0 || (cfg.chunk_bytes & 3u) || cfg.chunk_bytes > (1ull << 34))
-        return fmd_set_error(FMD_EINVAL, "chunk_bytes must be a positive multiple of 4 (got %llu)",
+    if (cfg.chunk_bytes == 0 || (cfg.chunk_bytes & 3u) || cfg.chunk_bytes > (1ull << 32))
+        return fmd_set_error(FMD_EINVAL, "chunk_bytes must be a positive multiple of 4, at most 4 GiB (got %llu)",
                              (unsigned long long) cfg.chunk_bytes);
+    if (cfg.in_degree && cfg.chunk_bytes / 2 < 2ull * fmd_sections(cfg.in_degree) + 2ull)
+        return fmd_set_error(FMD_EINVAL,
+                             "chunk of %llu bytes is shorter than the head of a degree-%u input filter: in the "
+                             "reference the result then depends on which overrun it reads first",
+                             (unsigned long long) cfg.chunk_bytes, cfg.in_degree);
     const unsigned conditioner = (cfg.mode >> 2) & 3u;
     if (conditioner == 1u || conditioner == 2u)
         return fmd_set_error(FMD_EINVAL,

@@ -317,7 +317,7 @@ size_t fmo_process_chunks(const uint8_t *in, size_t nchunks, size_t B,
     Lin = fmo_sections(deg_in);
     Lout = fmo_sections(cfg->deg_out);
     /* the aliasing model above assumes the chunk is longer than the head it re-reads */
-    if ((B >> 1) < 2 * Lin + 2 || (B >> 2) < 4 * Lin + 2 * Lout) return 0;
+    if ((B >> 1) < 2 * Lin + 2) return 0;
     sos_out = malloc(Lout * 6 * sizeof(float));
     fmo_design_sos(cfg->mode & 1u, cfg->deg_out, cfg->fc_out, cfg->fs, cfg->eps, sos_out);
     if (Lin) {

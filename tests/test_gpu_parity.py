@@ -298,3 +298,41 @@ def test_contexts_are_independent_across_threads(oracle_best):
     assert not errors, errors
     for i, (raw, cfg, out) in results.items():
         check_close(out, oracle_best.run(raw, cfg), what=f"thread {i}")
+
+
+@pytest.mark.parametrize("bs", [2000, 10000, 1028, 516, 262144 + 512, 36])
+@pytest.mark.parametrize("with_in", [False, True])
+def test_chunk_sizes_that_are_not_powers_of_two(bs, with_in, oracle_port):
+    """The C ABI takes any chunk size that is a multiple of 4 bytes (the CLI only makes powers of
+    two): several chunks whose length is not a multiple of the 128-output pass, so every chunk
+    has a streaming part, a head and a ragged remainder -- or is too small for the streaming part."""
+    raw = np.resize(synth.config_signal("cfg2", 2), 3 * bs + (bs // 2 & ~3))
+    cfg = po.Config(fs=96000.0, fc_out=6500.0, fc_in=12500.0 if with_in else 0.0)
+    with fm.Demodulator(bufSize=bs, **demod_kwargs(cfg)) as d:
+        out = d.process(raw)
+    want = oracle_port.run(raw[:3 * bs], cfg, chunk_bytes=bs)
+    check_close(out[: want.size], want, what=f"bufSize {bs}")
+    assert out.size == raw.size // 4
+
+
+def test_tiny_chunks_every_size(oracle_best):
+    """-b down to 4-byte chunks (one output per chunk): the exact path on chunk sizes 4..128 bytes,
+    against the reference's own code where its prebuilt library is present."""
+    rng = np.random.default_rng(3)
+    for bs in range(4, 132, 4):
+        raw = rng.integers(0, 256, 5 * bs, dtype=np.uint8)
+        for kw in (dict(fs=96000.0, fc_out=12500.0), dict(fs=96000.0, fc_out=6500.0, fc_in=12500.0),
+                   dict(fs=96000.0, fc_out=6500.0, fc_in=12500.0, deg_out=5)):
+            cfg = po.Config(**kw)
+            lin = (max(cfg.deg_in, cfg.deg_out if cfg.fc_in else 0) + 1) // 2
+            if cfg.fc_in and bs // 2 < 2 * lin + 2:
+                with pytest.raises(fm.FmdError):
+                    fm.Demodulator(bufSize=bs, **demod_kwargs(cfg))
+                continue
+            want = oracle_best.run(raw, cfg, chunk_bytes=bs)
+            with fm.Demodulator(bufSize=bs, **demod_kwargs(cfg)) as d:
+                out = d.process(raw)
+            scale = max(1.0, float(np.abs(want).max()))
+            # random bytes: |z| can be tiny after the input filter, where atan2 is ill-conditioned
+            bad = np.abs(out - want) > 2e-5 * scale
+            assert bad.mean() <= 0.02, (bs, kw, int(bad.sum()))
