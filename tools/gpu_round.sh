@@ -1,6 +1,6 @@
 #!/bin/bash
 # one GPU-box session: parity tests, benches, ncu captures -> gpurun_out/
-# usage: ./gpu_round.sh [ref] [ncu]
+# usage (on the GPU box, from the repo root): tools/gpu_round.sh [ref] [ncu]
 mkdir -p gpurun_out
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -30 > gpurun_out/pytest_gpu.log
