@@ -34,7 +34,9 @@
 
 #include "fmdemod.h"
 
+#ifndef FMD_BLOCK
 #define FMD_BLOCK 256               /* threads per CTA: 8 warps, one segment each */
+#endif
 #define FMD_WARPS (FMD_BLOCK / 32)
 #define FMD_PASS_OUT 128u           /* outputs per warp per pass (32 lanes x 4)   */
 
