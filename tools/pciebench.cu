@@ -16,6 +16,19 @@ int main() {
     cudaStreamSynchronize(b); cudaEventRecord(e1, a); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
     if (rep) printf("H2D + D2H both   %.1f GB/s each direction (%.1f total)\n", 4.0 * n / ms / 1e6, 8.0 * n / ms / 1e6);
   }
+  { // write-combined input buffer: does the GPU read it faster?
+    void* hw; cudaHostAlloc(&hw, n, cudaHostAllocPortable | cudaHostAllocWriteCombined);
+    for (int rep = 0; rep < 2; ++rep) {
+      cudaDeviceSynchronize(); cudaEventRecord(e0, a);
+      for (int i = 0; i < 4; ++i) cudaMemcpyAsync(d1, hw, n, cudaMemcpyHostToDevice, a);
+      cudaEventRecord(e1, a); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
+      if (rep) printf("H2D alone, write-combined source  %.1f GB/s\n", 4.0 * n / ms / 1e6);
+      cudaDeviceSynchronize(); cudaEventRecord(e0, a);
+      for (int i = 0; i < 4; ++i) { cudaMemcpyAsync(d1, hw, n, cudaMemcpyHostToDevice, a); cudaMemcpyAsync(h2, d2, n, cudaMemcpyDeviceToHost, b); }
+      cudaStreamSynchronize(b); cudaEventRecord(e1, a); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
+      if (rep) printf("H2D (WC source) + D2H both        %.1f GB/s each direction\n", 4.0 * n / ms / 1e6);
+    }
+  }
   // slice size sensitivity, both directions
   for (size_t s : {4ull << 20, 16ull << 20, 32ull << 20, 64ull << 20, 128ull << 20}) {
     cudaDeviceSynchronize(); cudaEventRecord(e0, a);
