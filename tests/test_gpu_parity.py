@@ -336,3 +336,19 @@ def test_tiny_chunks_every_size(oracle_best):
             # random bytes: |z| can be tiny after the input filter, where atan2 is ill-conditioned
             bad = np.abs(out - want) > 2e-5 * scale
             assert bad.mean() <= 0.02, (bs, kw, int(bad.sum()))
+
+
+@pytest.mark.parametrize("shift", [6, 10])
+def test_large_bufsize(shift, oracle_best):
+    """-b6 / -b10: chunks of 16 MiB and 256 MiB (2^22 and 2^26 outputs per chunk): one head, one
+    zero extension, thousands of segments inside a chunk."""
+    bs = B << shift
+    raw = np.resize(synth.config_signal("cfg2", 32), bs + (bs >> 3))  # one whole chunk + a ragged eighth
+    cfg = po.Config(fs=96000.0, fc_out=6500.0, fc_in=12500.0)
+    with fm.Demodulator(bufSize=bs, **demod_kwargs(cfg)) as d:
+        out = d.process(raw)
+    assert out.size == raw.size // 4
+    want = oracle_best.run(raw[:bs], cfg, chunk_bytes=bs)
+    check_close(out[: bs // 4], want, what=f"bufSize {bs}")
+    tail = oracle_best.run(raw[bs:], cfg, chunk_bytes=raw.size - bs)
+    check_close(out[bs // 4:], tail, what=f"bufSize {bs} tail")
