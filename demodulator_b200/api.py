@@ -19,6 +19,7 @@ DEFAULT_CHUNK_BYTES = 262144
 MAX_SECTIONS = 8
 MAX_TAPS = 6
 FLAG_EXACT = 1
+FLAG_QUALITY = 2
 
 
 class FmdError(RuntimeError):
@@ -28,7 +29,8 @@ class FmdError(RuntimeError):
 class _Config(C.Structure):
     _fields_ = [("sample_rate", C.c_double), ("lowpass_in", C.c_double), ("lowpass_out", C.c_double),
                 ("epsilon", C.c_double), ("in_degree", C.c_uint32), ("out_degree", C.c_uint32),
-                ("mode", C.c_uint32), ("flags", C.c_uint32), ("chunk_bytes", C.c_uint64)]
+                ("mode", C.c_uint32), ("flags", C.c_uint32), ("chunk_bytes", C.c_uint64),
+                ("input_rate", C.c_double)]
 
 
 def lib_path() -> str:
@@ -67,6 +69,9 @@ def load_library() -> C.CDLL:
     L.fmd_host_unregister.argtypes = [vp]
     L.fmd_out_count.argtypes = [vp, C.c_size_t]
     L.fmd_out_count.restype = C.c_size_t
+    L.fmd_max_out_count.argtypes = [vp, C.c_size_t]
+    L.fmd_max_out_count.restype = C.c_size_t
+    L.fmd_reset.argtypes = [vp]
     L.fmd_demod_device.argtypes = [vp, u8p, C.c_size_t, f32p, vp]
     L.fmd_demod_host.argtypes = [vp, u8p, C.c_size_t, f32p, C.POINTER(C.c_size_t)]
     L.fmd_ring_create.argtypes = [vp, C.c_uint, C.c_size_t]
@@ -120,11 +125,15 @@ class Demodulator:
 
     def __init__(self, sampleRate: float = 125000.0, lowpassIn: float = 0.0, lowpassOut: float = 12500.0,
                  epsilon: float = 0.3, inFilterDegree: int = 0, outFilterDegree: int = 3, mode: int = 0,
-                 bufSize: int = DEFAULT_CHUNK_BYTES, device: int = 0, exact: bool = False) -> None:
+                 bufSize: int = DEFAULT_CHUNK_BYTES, device: int = 0, exact: bool = False,
+                 quality: bool = False, inputRate: float = 0.0) -> None:
+        """quality=True selects the opt-in stream pipeline (FMD_FLAG_QUALITY: recursive filters with
+        carried state, adjacent-sample discriminator, decimation by inputRate / sampleRate)."""
         self._L = load_library()
         self._ctx = C.c_void_p()
         cfg = _Config(sampleRate, lowpassIn, lowpassOut, epsilon, inFilterDegree, outFilterDegree,
-                      (mode & 0x3f) | 0x10, FLAG_EXACT if exact else 0, bufSize)
+                      (mode & 0x3f) | 0x10, (FLAG_EXACT if exact else 0) | (FLAG_QUALITY if quality else 0),
+                      bufSize, inputRate)
         _check(self._L.fmd_create(C.byref(cfg), device, C.byref(self._ctx)))
         eff = _Config()
         _check(self._L.fmd_get_config(self._ctx, C.byref(eff)))
@@ -164,6 +173,13 @@ class Demodulator:
 
     def out_count(self, nbytes: int) -> int:
         return int(self._L.fmd_out_count(self._ctx, nbytes))
+
+    def max_out_count(self, nbytes: int) -> int:
+        return int(self._L.fmd_max_out_count(self._ctx, nbytes))
+
+    def reset(self) -> None:
+        """quality mode: start a new stream (forget the carried filter state)."""
+        _check(self._L.fmd_reset(self._ctx))
 
     # -- the hot path -----------------------------------------------------------------------
     def process(self, raw, out: np.ndarray | None = None) -> np.ndarray:

@@ -5,6 +5,9 @@
  *
  *   demodulator -i <file|-> -o <file|-> [-L fcIn] [-l fcOut] [-S fs] [-d degOut] [-D degIn]
  *               [-m bits] [-e eps] [-b shift] [-q n] [-c n] [-r x] [-n x]
+ *               [-Q -r inputRate]      (extension: the opt-in quality pipeline, FMD_FLAG_QUALITY --
+ *                                       recursive filters with carried state, adjacent-sample
+ *                                       discriminator, output decimated to -S; one GPU, one stream)
  *
  * in : raw unsigned 8-bit interleaved I,Q      out: raw native-endian float32,
  *      exactly bufSize/4 floats per bufSize input bytes, in order.
@@ -48,6 +51,7 @@ typedef struct {
     uint8_t *in;   /* pinned */
     float *out;    /* pinned */
     size_t nbytes; /* filled by the reader */
+    size_t nout;   /* floats this slot yields (set at submit time) */
     int last;      /* nothing follows this slot */
     int dev;       /* which context owns it */
     unsigned ring; /* slot index inside that context's ring */
@@ -175,8 +179,9 @@ static void *writer_main(void *arg) {
         }
         if (s->nbytes) {
             if (fmd_wait(h->ctx[s->dev], s->ring)) die("fmd_wait");
-            const size_t nf = s->nbytes >> 2;
-            /* a slot yields as many output bytes as it had input bytes: slot n lands at n*slot_bytes */
+            const size_t nf = s->nout;
+            /* reference-compatible mode: a slot yields as many output bytes as it had input bytes,
+             * so slot n lands at n*slot_bytes (positioned writes are off in quality mode) */
             if (!h->error && write_all(h->out_fd, s->out, nf * sizeof(float), h->out_regular,
                                        (off_t) (n * (unsigned long long) h->slot_bytes))) {
                 perror("demodulator: write");
@@ -225,7 +230,7 @@ int main(int argc, char **argv) {
 
     if (argc < 3) return -1; /* src/main.c:122-123 */
 
-    while ((opt = getopt(argc, argv, "i:o:r:L:l:S:D:d:e:m:b:c:q:n:")) != -1) {
+    while ((opt = getopt(argc, argv, "i:o:r:L:l:S:D:d:e:m:b:c:q:n:Q")) != -1) {
         switch (opt) {
             case 'i': /* any argument containing '-' means stdin (src/main.c:128) */
                 h.in_fd = strstr(optarg, "-") ? STDIN_FILENO : open(optarg, O_RDONLY);
@@ -250,7 +255,13 @@ int main(int argc, char **argv) {
                 break;
             case 'c': cfg.mode |= (uint32_t) strtoul(optarg, NULL, 10) << 4; break;
             case 'q': cfg.mode |= (uint32_t) strtoul(optarg, NULL, 10) << 2; break;
-            default: break; /* -r, -n: accepted and ignored, like the reference */
+            /* -Q (not a reference flag): the opt-in quality pipeline -- recursive filters with state
+             * carried through the stream, adjacent-sample discriminator, decimation from the input
+             * rate -r to the output rate -S.  Without -Q, -r is parsed and ignored like the
+             * reference does (src/main.c:180). */
+            case 'Q': cfg.flags |= FMD_FLAG_QUALITY; break;
+            case 'r': cfg.input_rate = (double) strtold(optarg, NULL); break;
+            default: break; /* -n: accepted and ignored, like the reference */
         }
     }
     cfg.mode &= 0xffu; /* consumerArgs.mode is a uint8_t */
@@ -284,11 +295,19 @@ int main(int argc, char **argv) {
          * (only its last slot is short); a stream may cut slots short, so its output stays sequential */
         h.n_writers = (h.out_regular && h.in_regular) ? want : 1;
         if (!(h.out_regular && h.in_regular)) h.out_regular = 0;
+        if (cfg.flags & FMD_FLAG_QUALITY) { /* one ordered stream: output sizes depend on the position */
+            h.n_writers = 1;
+            h.out_regular = 0;
+        }
         pthread_mutex_init(&h.stat_lock, NULL);
     }
 
     h.ndev = parse_devices(getenv("FMD_DEVICES"), devs);
     if (h.ndev <= 0) die("no CUDA device");
+    if ((cfg.flags & FMD_FLAG_QUALITY) && h.ndev > 1) {
+        fprintf(stderr, "demodulator: -Q carries filter state through the stream: using device %d only\n", devs[0]);
+        h.ndev = 1;
+    }
     for (int d = 0; d < h.ndev; ++d)
         if (fmd_create(&cfg, devs[d], &h.ctx[d])) die("fmd_create");
 
@@ -313,7 +332,9 @@ int main(int argc, char **argv) {
             s->ring = i / (unsigned) h.ndev;
             /* the backend chooses how the reader's buffer is allocated, as in the reference's
              * allocateBuffer seam (src/main.c:65): pinned, so copies are true DMA */
-            if (fmd_host_alloc((void **) &s->in, h.slot_bytes) || fmd_host_alloc((void **) &s->out, h.slot_bytes))
+            size_t out_bytes = fmd_max_out_count(h.ctx[s->dev], h.slot_bytes) * sizeof(float);
+            if (out_bytes < h.slot_bytes) out_bytes = h.slot_bytes;
+            if (fmd_host_alloc((void **) &s->in, h.slot_bytes) || fmd_host_alloc((void **) &s->out, out_bytes))
                 die("fmd_host_alloc");
         }
     }
@@ -341,6 +362,7 @@ int main(int argc, char **argv) {
         sem_wait(&s->filled);
         /* tail policy: a final partial chunk of r bytes is a chunk of r&~3 bytes */
         s->nbytes &= ~(size_t) 3;
+        s->nout = fmd_out_count(h.ctx[s->dev], s->nbytes); /* before the submit moves a -Q stream on */
         if (s->nbytes && fmd_submit(h.ctx[s->dev], s->ring, s->in, s->nbytes, s->out)) die("fmd_submit");
         const int last = s->last;
         sem_post(&s->inflight);

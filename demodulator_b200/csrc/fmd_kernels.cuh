@@ -122,6 +122,17 @@ __device__ __forceinline__ fmd_f2 fmd_bytes_to_f2(uint32_t wa, uint32_t wb) {
                     fmd_bc(-8388736.0f));
 }
 
+/* -q3 (normalizeInput, matrix.c:100-118): bytes `I` of two RAW words -> (float)u * (float)(2/255) - 1,
+ * product and difference rounded separately like the reference's float multiply and its
+ * (exact) double subtraction narrowed back to float */
+template <int I>
+__device__ __forceinline__ fmd_f2 fmd_bytes_to_unit_f2(uint32_t wa, uint32_t wb) {
+    const fmd_f2 u = fmd_add2(fmd_pk(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7540 | I)),
+                                     __uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7540 | I))),
+                              fmd_bc(-8388608.0f));
+    return fmd_add2(fmd_mul2(u, fmd_bc((float) (2. / 255.))), fmd_bc(-1.0f));
+}
+
 __device__ __forceinline__ float fmd_max3(float a, float b, float c) {
     float r;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -354,7 +365,7 @@ fmd_exact_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const 
  * 8 bytes of the lane's raw input of the following pass: lane 0's copy is what lane 31 needs
  * as its input-filter halo.  LITE: only outputs 0 and 2 are computed (the drain pass).
  */
-template <int NTI, int NTO, int AT, bool LITE = false>
+template <int NTI, int NTO, int AT, bool LITE = false, int COND = 0>
 __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, const float (&xprev)[4],
                                          float (&xcur)[4], const bool zero_x, float *__restrict__ dst,
                                          const bool do_store, const unsigned lane, const unsigned nxt_lane,
@@ -364,11 +375,16 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, con
     constexpr int NB = NTO - 1;               /* discriminator outputs needed from the next lane */
 
     /* biased words: own four, then the halo from the next lane (lane 31: lane 0's next pass) */
+    static_assert(COND == 0 || (COND == 3 && NTI == 0), "-q3 streams only without the input filter");
     uint32_t w[6];
-    w[0] = fmd_bias_bytes(cur.x);
-    w[1] = fmd_bias_bytes(cur.y);
-    w[2] = fmd_bias_bytes(cur.z);
-    w[3] = fmd_bias_bytes(cur.w);
+    if (COND == 3) { /* normalizeInput works on the raw bytes */
+        w[0] = cur.x; w[1] = cur.y; w[2] = cur.z; w[3] = cur.w;
+    } else {
+        w[0] = fmd_bias_bytes(cur.x);
+        w[1] = fmd_bias_bytes(cur.y);
+        w[2] = fmd_bias_bytes(cur.z);
+        w[3] = fmd_bias_bytes(cur.w);
+    }
     w[4] = w[5] = 0u;
     if (HW >= 1) w[4] = fmd_bias_bytes(__shfl_sync(0xffffffffu, lane == 0 ? nxt.x : cur.x, nxt_lane));
     if (HW >= 2) w[5] = fmd_bias_bytes(__shfl_sync(0xffffffffu, lane == 0 ? nxt.y : cur.y, nxt_lane));
@@ -379,7 +395,12 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, con
     fmd_f2 vi[NK], vq[NK];
 #pragma unroll
     for (int k = 0; k < NK; ++k) {
-        if (k & 1) {
+        if (COND == 3) {
+            vi[k] = (k & 1) ? fmd_bytes_to_unit_f2<2>(w[k >> 1], w[(k >> 1) + 2])
+                            : fmd_bytes_to_unit_f2<0>(w[k >> 1], w[(k >> 1) + 2]);
+            vq[k] = (k & 1) ? fmd_bytes_to_unit_f2<3>(w[k >> 1], w[(k >> 1) + 2])
+                            : fmd_bytes_to_unit_f2<1>(w[k >> 1], w[(k >> 1) + 2]);
+        } else if (k & 1) {
             vi[k] = fmd_bytes_to_f2<2>(w[k >> 1], w[(k >> 1) + 2]);
             vq[k] = fmd_bytes_to_f2<3>(w[k >> 1], w[(k >> 1) + 2]);
         } else {
@@ -477,7 +498,7 @@ __device__ __forceinline__ uint2 fmd_lds64(uint32_t a) {
  * reads them back with one LDS.128, so the loads in flight per SM do not depend on the
  * register budget or on occupancy, and no lane ever reads another lane's slot (no barrier).
  */
-template <int NTI, int NTO, int AT>
+template <int NTI, int NTO, int AT, int COND = 0>
 __global__ void __launch_bounds__(FMD_BLOCK, FMD_MINB(NTI))
 fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const FmdGeom g, const FmdStencil st,
                 const FmdSections *__restrict__ sec) {
@@ -542,7 +563,7 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
         uint2 nx = fill2;                                                                               \
         if (HALO) nx = fmd_lds64(sbase + (((U) + 1) & (S - 1)) * SLOT);                                 \
         if (HALO && (U) == S - 1 && base + S >= n_ld) nx = fill2;                                       \
-        fmd_pass<NTI, NTO, AT>(cur, nx, XPREV, XCUR, false, dst + 128 * ((U) - 1), STP, lane, nxt_lane, st); \
+        fmd_pass<NTI, NTO, AT, false, COND>(cur, nx, XPREV, XCUR, false, dst + 128 * ((U) - 1), STP, lane, nxt_lane, st); \
     }
 
     unsigned base = 0;
@@ -573,7 +594,7 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
         const uint4 cur = fmd_lds128(sbase + (u & (S - 1)) * SLOT);
         uint2 nx = fill2;
         if (HALO && p + 1 < n_ld) nx = fmd_lds64(sbase + ((u + 1) & (S - 1)) * SLOT);
-        fmd_pass<NTI, NTO, AT>(cur, nx, x1, x0, false, dst + 128 * ((int) u - 1), p >= 2 || (p == 1 && head_keep),
+        fmd_pass<NTI, NTO, AT, false, COND>(cur, nx, x1, x0, false, dst + 128 * ((int) u - 1), p >= 2 || (p == 1 && head_keep),
                                      lane, nxt_lane, st);
         x1[0] = x0[0]; x1[1] = x0[1]; x1[2] = x0[2]; x1[3] = x0[3];
     }
@@ -585,7 +606,7 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
         fmd_cp_wait<PENDING>();
         uint4 cur = fill;
         if (p < n_ld) cur = fmd_lds128(sbase + (u & (S - 1)) * SLOT);
-        fmd_pass<NTI, NTO, AT, (NTO <= 2)>(cur, fill2, x1, x0, end_zero, dst + 128 * ((int) u - 1),
+        fmd_pass<NTI, NTO, AT, (NTO <= 2), COND>(cur, fill2, x1, x0, end_zero, dst + 128 * ((int) u - 1),
                                                  p >= 2 || (p == 1 && head_keep), lane, nxt_lane, st);
     }
 

@@ -1,0 +1,700 @@
+/*
+ * fmd_quality.cuh -- sm_100a kernels of the opt-in quality pipeline (FMD_FLAG_QUALITY).
+ *
+ *   s[n] = (I - 127.5, Q - 127.5)
+ *   z[n] = input lowpass cascade (recursive, per lane; only with -L)
+ *   x[n] = atan2(Im, Re)(z[n] * conj(z[n-1]))
+ *   v[n] = output lowpass cascade (recursive)
+ *   y[m] = v[m * M]                     only these floats are written to HBM
+ *
+ * The recursions run as a three-level scan with an explicit state carry (fmd_quality.h):
+ *
+ *   thread  FMQ_T = 32 consecutive samples, serially, from a ZERO state
+ *   CTA     affine scan over its 256 threads (warp shuffles with the matrices A^(32*2^j), then a
+ *           short serial pass over the 8 warp totals): state at the start of every thread's span
+ *   launch  fmq_scan_tiles_kernel scans the per-tile end states of all CTAs (and takes the carry
+ *           of the previous call in, leaves the carry for the next call behind)
+ *
+ * Input lowpass (a scan whose result feeds a non-linearity, so it has to be resolved first):
+ *   fmq_in_aggregate_kernel  per-tile end state from a zero state       reads the input once
+ *   fmq_scan_tiles_kernel    state at the start of every tile
+ *   fmq_main_kernel          re-runs the cascade from the right state and goes on to x and v
+ * Output lowpass (linear in x, so the carry can be added afterwards, to the kept samples only):
+ *   fmq_main_kernel          v from a zero state at the tile start (thread-level carry applied
+ *                            in shared memory), decimated; per-tile end state
+ *   fmq_scan_tiles_kernel    state at the start of every tile
+ *   fmq_zir_kernel           y[m] += C A^k q_tile        (the tile's zero-input response)
+ *
+ * The input cascade's spans are shifted by one sample (thread t owns samples F-1 .. F+T-2 of it,
+ * F = first sample of its x span): re-running it from the state at F-1 yields z[F-1], the
+ * neighbour the discriminator needs for x[F], with no exchange between threads.
+ *
+ * No spin-waits, no inter-CTA dependencies inside a kernel: the carries travel between launches.
+ */
+#ifndef FMD_QUALITY_CUH
+#define FMD_QUALITY_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fmd_kernels.cuh"
+#include "fmd_quality.h"
+
+/* the carry between calls (one per context, device memory) */
+struct FmqState {
+    float in_q[2][FMQ_MAXD]; /* input cascade, lanes I and Q: state BEFORE the sample s_prev   */
+    float out_q[FMQ_MAXD];   /* output cascade: state before the next x                        */
+    float s_prev[2];         /* the centred sample that precedes the next call (0,0 at start)  */
+};
+
+struct FmqGeom {
+    unsigned n;      /* samples in this launch (< 2^31)                                        */
+    unsigned ntiles;
+    unsigned r0;     /* launch-relative index of the first kept sample (may be >= n)           */
+    unsigned decim;  /* M                                                                      */
+    unsigned n_out;  /* outputs of this launch                                                 */
+};
+
+struct FmqMat {
+    float m[FMQ_MAXD * FMQ_MAXD];
+};
+
+/* byte B of a raw word -> exact float u - 127.5:  0x4700uu00 = 32768 + u */
+template <int B>
+__device__ __forceinline__ float fmq_centre(uint32_t w) {
+    return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7504 | (B << 4))) - 32895.5f;
+}
+
+__device__ __forceinline__ void fmq_load_sample(const uint8_t *__restrict__ in, unsigned idx, float &si, float &sq) {
+    const unsigned short h = *reinterpret_cast<const unsigned short *>(in + 2ull * idx);
+    si = (float) (h & 0xffu) - 127.5f;
+    sq = (float) (h >> 8) - 127.5f;
+}
+
+/* one sample through L sections, direct form II transposed; q = (s1_0, s2_0, s1_1, ...) */
+template <int L>
+__device__ __forceinline__ float fmq_step(const fmq_consts &c, float (&q)[2 * L], float u) {
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+        const float w = fmaf(c.sos[i][0], u, q[2 * i]);
+        q[2 * i] = fmaf(-c.sos[i][3], w, fmaf(c.sos[i][1], u, q[2 * i + 1]));
+        q[2 * i + 1] = fmaf(-c.sos[i][4], w, c.sos[i][2] * u);
+        u = w;
+    }
+    return u;
+}
+
+/* number of kept samples (launch-relative index >= r0, (index - r0) % M == 0) below `pos` */
+__device__ __forceinline__ unsigned fmq_kept_below(unsigned pos, unsigned r0, unsigned M) {
+    return pos <= r0 ? 0u : (pos - r0 + M - 1u) / M;
+}
+
+/*
+ * Exclusive affine scan over the threads of a CTA: in  v[nv] = end state of the thread's span run
+ * from a zero state; out v[nv] = state at the START of the thread's span, given `carry` = state at
+ * the start of the tile.  Every thread of the CTA must call it (one __syncthreads inside).
+ */
+template <int D, int NV>
+__device__ __forceinline__ void fmq_block_scan(float (&v)[NV][D], const fmq_consts &c,
+                                               const float *__restrict__ lane_tab, const float (&carry)[NV][D],
+                                               float *tot /* shared, FMQ_WARPS * NV * D */) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        float up[NV][D];
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+            for (int i = 0; i < D; ++i) up[a][i] = __shfl_up_sync(0xffffffffu, v[a][i], 1u << j);
+        if (lane >= (1u << j)) {
+#pragma unroll
+            for (int a = 0; a < NV; ++a)
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    float acc = v[a][i];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) acc = fmaf(c.lvl[j][i * D + k], up[a][k], acc);
+                    v[a][i] = acc;
+                }
+        }
+    }
+    if (lane == 31u) {
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+            for (int i = 0; i < D; ++i) tot[(warp * NV + a) * D + i] = v[a][i];
+    }
+    __syncthreads();
+    float wp[NV][D];
+#pragma unroll
+    for (int a = 0; a < NV; ++a)
+#pragma unroll
+        for (int i = 0; i < D; ++i) wp[a][i] = carry[a][i];
+    for (unsigned w = 0; w < warp; ++w) {
+        float nw[NV][D];
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                float acc = tot[(w * NV + a) * D + i];
+#pragma unroll
+                for (int k = 0; k < D; ++k) acc = fmaf(c.warp[i * D + k], wp[a][k], acc);
+                nw[a][i] = acc;
+            }
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+            for (int i = 0; i < D; ++i) wp[a][i] = nw[a][i];
+    }
+    float ex[NV][D];
+#pragma unroll
+    for (int a = 0; a < NV; ++a)
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const float t = __shfl_up_sync(0xffffffffu, v[a][i], 1u);
+            ex[a][i] = lane ? t : 0.0f;
+        }
+    const float *__restrict__ lt = lane_tab + lane * (D * D);
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const float m = __ldg(lt + i * D + k);
+#pragma unroll
+            for (int a = 0; a < NV; ++a) ex[a][i] = fmaf(m, wp[a][k], ex[a][i]);
+        }
+#pragma unroll
+    for (int a = 0; a < NV; ++a)
+#pragma unroll
+        for (int i = 0; i < D; ++i) v[a][i] = ex[a][i];
+}
+
+/* end state of a span of `cnt` samples: A^cnt q0 + e  (apow = table of A^k, k = 0..T) */
+template <int D>
+__device__ __forceinline__ void fmq_span_end(const float *__restrict__ apow, unsigned cnt, const float (&q0)[D],
+                                             const float (&e)[D], float *__restrict__ dst) {
+    const float *__restrict__ m = apow + cnt * (D * D);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        float acc = e[i];
+#pragma unroll
+        for (int k = 0; k < D; ++k) acc = fmaf(__ldg(m + i * D + k), q0[k], acc);
+        dst[i] = acc;
+    }
+}
+
+/* the thread's 64 input bytes (full spans only) */
+__device__ __forceinline__ void fmq_load_span(const uint8_t *__restrict__ in, unsigned F, uint32_t (&w)[FMQ_T / 2]) {
+    const uint4 *__restrict__ p = reinterpret_cast<const uint4 *>(in + 2ull * F);
+#pragma unroll
+    for (int i = 0; i < FMQ_T / 8; ++i) {
+        const uint4 v = __ldg(p + i);
+        w[4 * i] = v.x;
+        w[4 * i + 1] = v.y;
+        w[4 * i + 2] = v.z;
+        w[4 * i + 3] = v.w;
+    }
+}
+
+#define FMQ_SI(w, i) (((i) & 1) ? fmq_centre<2>((w)[(i) >> 1]) : fmq_centre<0>((w)[(i) >> 1]))
+#define FMQ_SQ(w, i) (((i) & 1) ? fmq_centre<3>((w)[(i) >> 1]) : fmq_centre<1>((w)[(i) >> 1]))
+
+/*
+ * Input cascade from a zero state over the thread's SHIFTED span: the halo sample (F-1), then
+ * samples F .. F+cnt-2.  cnt = number of samples of the x span (0 for a thread past the end).
+ */
+template <int LIN>
+__device__ __forceinline__ void fmq_in_zero_state(const fmq_consts &cin, const uint8_t *__restrict__ in, unsigned F,
+                                                  unsigned cnt, const uint32_t (&w)[FMQ_T / 2], float hi, float hq,
+                                                  float (&e)[2][2 * LIN]) {
+#pragma unroll
+    for (int i = 0; i < 2 * LIN; ++i) e[0][i] = e[1][i] = 0.0f;
+    if (cnt == FMQ_T) {
+        fmq_step<LIN>(cin, e[0], hi);
+        fmq_step<LIN>(cin, e[1], hq);
+#pragma unroll
+        for (int i = 0; i < FMQ_T - 1; ++i) {
+            fmq_step<LIN>(cin, e[0], FMQ_SI(w, i));
+            fmq_step<LIN>(cin, e[1], FMQ_SQ(w, i));
+        }
+    } else if (cnt) {
+        fmq_step<LIN>(cin, e[0], hi);
+        fmq_step<LIN>(cin, e[1], hq);
+#pragma unroll 1
+        for (unsigned i = 0; i + 1 < cnt; ++i) {
+            float si, sq;
+            fmq_load_sample(in, F + i, si, sq);
+            fmq_step<LIN>(cin, e[0], si);
+            fmq_step<LIN>(cin, e[1], sq);
+        }
+    }
+}
+
+/* per-thread geometry shared by the kernels */
+struct FmqSpan {
+    unsigned S, F, cnt; /* tile start, thread start (launch-relative samples), samples in the span */
+    bool last;          /* this thread's span reaches the end of the tile's valid samples          */
+};
+
+__device__ __forceinline__ FmqSpan fmq_span(const FmqGeom &g) {
+    FmqSpan s;
+    s.S = blockIdx.x * (unsigned) FMQ_TILE;
+    s.F = s.S + threadIdx.x * (unsigned) FMQ_T;
+    s.cnt = s.F >= g.n ? 0u : min((unsigned) FMQ_T, g.n - s.F);
+    s.last = s.cnt != 0u && (threadIdx.x == FMQ_THREADS - 1 || s.F + FMQ_T >= g.n);
+    return s;
+}
+
+__device__ __forceinline__ void fmq_halo(const uint8_t *__restrict__ in, const FmqState *__restrict__ st, unsigned F,
+                                         unsigned cnt, float &hi, float &hq) {
+    hi = hq = 0.0f;
+    if (cnt == 0u) return;
+    if (F == 0u) {
+        hi = st->s_prev[0];
+        hq = st->s_prev[1];
+    } else {
+        fmq_load_sample(in, F - 1u, hi, hq);
+    }
+}
+
+/* ------------------------------------------------ input cascade: per-tile end state (zero state in) */
+
+template <int LIN>
+__global__ void __launch_bounds__(FMQ_THREADS)
+fmq_in_aggregate_kernel(const uint8_t *__restrict__ in, const FmqGeom g, const fmq_consts cin,
+                        const float *__restrict__ lane_tab, const float *__restrict__ apow,
+                        const FmqState *__restrict__ st, float *__restrict__ e_tile /* [ntiles][2][D] */) {
+    constexpr int D = 2 * LIN;
+    __shared__ float tot[FMQ_WARPS * 2 * D];
+    const FmqSpan sp = fmq_span(g);
+    uint32_t w[FMQ_T / 2];
+    if (sp.cnt == FMQ_T) fmq_load_span(in, sp.F, w);
+    float hi, hq;
+    fmq_halo(in, st, sp.F, sp.cnt, hi, hq);
+    float e[2][D], q[2][D];
+    fmq_in_zero_state<LIN>(cin, in, sp.F, sp.cnt, w, hi, hq, e);
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int i = 0; i < D; ++i) q[a][i] = e[a][i];
+    float zero[2][D];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int i = 0; i < D; ++i) zero[a][i] = 0.0f;
+    fmq_block_scan<D, 2>(q, cin, lane_tab, zero, tot);
+    if (sp.last) {
+        float *dst = e_tile + (size_t) blockIdx.x * 2 * D;
+        fmq_span_end<D>(apow, sp.cnt, q[0], e[0], dst);
+        fmq_span_end<D>(apow, sp.cnt, q[1], e[1], dst + D);
+    }
+}
+
+/* ------------------------------------------------------------------------------- the main kernel */
+
+/* discriminator for two consecutive samples: x0 from (z0, zp), x1 from (z1, z0) */
+__device__ __forceinline__ void fmq_discriminate2(float pr, float pi, float z0r, float z0i, float z1r, float z1i,
+                                                  float &x0, float &x1) {
+    const float re0 = fmaf(z0r, pr, z0i * pi), im0 = fmaf(z0i, pr, -(z0r * pi));
+    const float re1 = fmaf(z1r, z0r, z1i * z0i), im1 = fmaf(z1i, z0r, -(z1r * z0i));
+    fmd_atan2_x2<8>(fmd_pk(im0, im1), fmd_pk(re0, re1), x0, x1);
+}
+
+template <int LIN, int LOUT>
+__global__ void __launch_bounds__(FMQ_THREADS, 2)
+fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const FmqGeom g, const fmq_consts cin,
+                const fmq_consts cout, const float *__restrict__ lane_in, const float *__restrict__ lane_out,
+                const float *__restrict__ apow_out, const float *__restrict__ ck_out,
+                const float *__restrict__ qin_tile /* [ntiles][2][DIN], state at F-1 of thread 0 */,
+                float *__restrict__ eout_tile /* [ntiles][DOUT] */, const FmqState *__restrict__ st) {
+    constexpr int DI = LIN > 0 ? 2 * LIN : 2;
+    constexpr int DO = 2 * LOUT;
+    extern __shared__ float ybuf[];                    /* kept v of this tile, zero state at the tile start */
+    __shared__ float qs[FMQ_THREADS * DO];             /* output-cascade state at the start of every thread */
+    __shared__ float ck[FMQ_T * DO];
+    __shared__ float tot_in[FMQ_WARPS * 2 * DI];
+    __shared__ float tot_out[FMQ_WARPS * DO];
+
+    const FmqSpan sp = fmq_span(g);
+    for (unsigned i = threadIdx.x; i < FMQ_T * DO; i += FMQ_THREADS) ck[i] = __ldg(ck_out + i);
+
+    uint32_t w[FMQ_T / 2];
+    const bool full = sp.cnt == FMQ_T;
+    if (full) fmq_load_span(in, sp.F, w);
+    float hi, hq;
+    fmq_halo(in, st, sp.F, sp.cnt, hi, hq);
+
+    /* input cascade: state at F-1 */
+    float qi[2][DI];
+    if (LIN > 0) {
+        float e[2][DI];
+        fmq_in_zero_state<(LIN > 0 ? LIN : 1)>(cin, in, sp.F, sp.cnt, w, hi, hq, e);
+        float carry[2][DI];
+        const float *__restrict__ src = qin_tile + (size_t) blockIdx.x * 2 * DI;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int i = 0; i < DI; ++i) {
+                qi[a][i] = e[a][i];
+                carry[a][i] = __ldg(src + a * DI + i);
+            }
+        fmq_block_scan<DI, 2>(qi, cin, lane_in, carry, tot_in);
+    }
+
+    /* kept samples of this thread: offset of the first one in its span, and its slot in ybuf */
+    const unsigned o_tile = fmq_kept_below(sp.S, g.r0, g.decim);
+    unsigned next, slot;
+    {
+        const unsigned o_first = fmq_kept_below(sp.F, g.r0, g.decim);
+        const unsigned long long kfirst = (unsigned long long) g.r0 + (unsigned long long) o_first * g.decim;
+        next = kfirst - sp.F >= (unsigned long long) FMQ_T ? 0xffffffffu : (unsigned) (kfirst - sp.F);
+        slot = o_first - o_tile;
+    }
+
+    /* second pass: z (from the right state), x, v from a zero state; v kept every M-th sample */
+    float pr, pi; /* z[F-1] */
+    if (LIN > 0) {
+        pr = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[0], hi);
+        pi = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[1], hq);
+    } else {
+        pr = hi;
+        pi = hq;
+    }
+    float eo[DO];
+#pragma unroll
+    for (int i = 0; i < DO; ++i) eo[i] = 0.0f;
+
+    if (full) {
+#pragma unroll
+        for (int i = 0; i < FMQ_T; i += 2) {
+            float z0r = FMQ_SI(w, i), z0i = FMQ_SQ(w, i), z1r = FMQ_SI(w, i + 1), z1i = FMQ_SQ(w, i + 1);
+            if (LIN > 0) {
+                z0r = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[0], z0r);
+                z0i = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[1], z0i);
+                z1r = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[0], z1r);
+                z1i = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[1], z1i);
+            }
+            float x0, x1;
+            fmq_discriminate2(pr, pi, z0r, z0i, z1r, z1i, x0, x1);
+            pr = z1r;
+            pi = z1i;
+            const float v0 = fmq_step<LOUT>(cout, eo, x0);
+            if ((unsigned) i == next) {
+                ybuf[slot++] = v0;
+                next += g.decim;
+            }
+            const float v1 = fmq_step<LOUT>(cout, eo, x1);
+            if ((unsigned) (i + 1) == next) {
+                ybuf[slot++] = v1;
+                next += g.decim;
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (unsigned i = 0; i < sp.cnt; ++i) {
+            float zr, zi;
+            fmq_load_sample(in, sp.F + i, zr, zi);
+            if (LIN > 0) {
+                zr = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[0], zr);
+                zi = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[1], zi);
+            }
+            const float re = fmaf(zr, pr, zi * pi), im = fmaf(zi, pr, -(zr * pi));
+            pr = zr;
+            pi = zi;
+            const float v = fmq_step<LOUT>(cout, eo, fmd_atan2(im, re));
+            if (i == next) {
+                ybuf[slot++] = v;
+                next += g.decim;
+            }
+        }
+    }
+
+    /* output cascade: state at the start of every thread's span (zero at the tile start) */
+    float qo[1][DO], zero[1][DO];
+#pragma unroll
+    for (int i = 0; i < DO; ++i) {
+        qo[0][i] = eo[i];
+        zero[0][i] = 0.0f;
+    }
+    fmq_block_scan<DO, 1>(qo, cout, lane_out, zero, tot_out);
+#pragma unroll
+    for (int i = 0; i < DO; ++i) qs[threadIdx.x * DO + i] = qo[0][i];
+    if (sp.last) fmq_span_end<DO>(apow_out, sp.cnt, qo[0], eo, eout_tile + (size_t) blockIdx.x * DO);
+    __syncthreads();
+
+    /* kept samples: add the thread-level zero-input response, store coalesced */
+    const unsigned tile_end = min(sp.S + (unsigned) FMQ_TILE, g.n);
+    const unsigned count = fmq_kept_below(tile_end, g.r0, g.decim) - o_tile;
+    for (unsigned o = threadIdx.x; o < count; o += FMQ_THREADS) {
+        const unsigned ks = (unsigned) ((unsigned long long) g.r0 + (unsigned long long) (o_tile + o) * g.decim - sp.S);
+        const unsigned owner = ks / FMQ_T, k = ks % FMQ_T;
+        float y = ybuf[o];
+#pragma unroll
+        for (int i = 0; i < DO; ++i) y = fmaf(ck[k * DO + i], qs[owner * DO + i], y);
+        out[o_tile + o] = y;
+    }
+}
+
+/* ------------------------------------------- tile-level zero-input response on the kept samples */
+
+template <int DO>
+__global__ void __launch_bounds__(256)
+fmq_zir_kernel(float *__restrict__ out, const FmqGeom g, const float *__restrict__ ckn /* [TILE][DO] */,
+               const float *__restrict__ q_tile /* [ntiles][DO] */) {
+    const unsigned o = blockIdx.x * 256u + threadIdx.x;
+    if (o >= g.n_out) return;
+    const unsigned long long ks = (unsigned long long) g.r0 + (unsigned long long) o * g.decim;
+    const unsigned tile = (unsigned) (ks / FMQ_TILE), k = (unsigned) (ks % FMQ_TILE);
+    const float *__restrict__ c = ckn + (size_t) k * DO;
+    const float *__restrict__ q = q_tile + (size_t) tile * DO;
+    float y = out[o];
+#pragma unroll
+    for (int i = 0; i < DO; ++i) y = fmaf(__ldg(c + i), __ldg(q + i), y);
+    out[o] = y;
+}
+
+/* --------------------------------------------------------- scan of the per-tile end states */
+
+#define FMQ_SCAN_BLOCK 512
+
+template <int D>
+__device__ __forceinline__ void fmq_mm(const float (&x)[D * D], const float (&y)[D * D], float (&o)[D * D]) {
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) acc = fmaf(x[i * D + k], y[k * D + j], acc);
+            o[i * D + j] = acc;
+        }
+}
+
+/* (M, v) <- (M, v) after (Mu, vu):  v = M vu + v,  M = M Mu   ("u" is the EARLIER map) */
+template <int D, int NV>
+__device__ __forceinline__ void fmq_compose(float (&M)[D * D], float (&v)[NV][D], const float (&Mu)[D * D],
+                                            const float (&vu)[NV][D]) {
+#pragma unroll
+    for (int a = 0; a < NV; ++a)
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            float acc = v[a][i];
+#pragma unroll
+            for (int k = 0; k < D; ++k) acc = fmaf(M[i * D + k], vu[a][k], acc);
+            v[a][i] = acc;
+        }
+    float t[D * D];
+    fmq_mm<D>(M, Mu, t);
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) M[i] = t[i];
+}
+
+template <int D, int NV>
+__device__ __forceinline__ void fmq_warp_scan_maps(float (&M)[D * D], float (&v)[NV][D], unsigned lane) {
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        float Mu[D * D], vu[NV][D];
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) Mu[i] = __shfl_up_sync(0xffffffffu, M[i], 1u << j);
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+            for (int i = 0; i < D; ++i) vu[a][i] = __shfl_up_sync(0xffffffffu, v[a][i], 1u << j);
+        if (lane >= (1u << j)) fmq_compose<D, NV>(M, v, Mu, vu);
+    }
+}
+
+/*
+ * q[j+1] = P_j q[j] + E[j],  P_j = pn (a full tile) or plast (the ragged last tile);  q[0] = *carry.
+ * Writes q[j] (the state at the START of tile j) for every tile and leaves q[ntiles] in *carry.
+ * One CTA: a thread takes a run of consecutive tiles, the runs are combined as affine maps.
+ * When `last_sample` is given, also records the centred last input sample for the next call.
+ */
+template <int D, int NV>
+__global__ void __launch_bounds__(FMQ_SCAN_BLOCK)
+fmq_scan_tiles_kernel(const float *__restrict__ E, float *__restrict__ Q, float *__restrict__ carry, const FmqMat pn,
+                      const FmqMat plast, const unsigned ntiles, const uint8_t *__restrict__ last_sample,
+                      float *__restrict__ s_prev) {
+    __shared__ float wM[16][D * D];
+    __shared__ float wv[16][NV * D];
+    const unsigned t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    const unsigned R = (ntiles + FMQ_SCAN_BLOCK - 1) / FMQ_SCAN_BLOCK;
+    const unsigned j0 = min(t * R, ntiles), j1 = min(j0 + R, ntiles);
+
+    float c0[NV][D];
+#pragma unroll
+    for (int a = 0; a < NV; ++a)
+#pragma unroll
+        for (int i = 0; i < D; ++i) c0[a][i] = carry[a * D + i];
+    float PN[D * D], PL[D * D];
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) {
+        PN[i] = pn.m[i];
+        PL[i] = plast.m[i];
+    }
+
+    /* this thread's run as one affine map (M, v) */
+    float v[NV][D];
+#pragma unroll
+    for (int a = 0; a < NV; ++a)
+#pragma unroll
+        for (int i = 0; i < D; ++i) v[a][i] = 0.0f;
+    for (unsigned j = j0; j < j1; ++j) {
+        const bool is_last = j + 1u == ntiles;
+        float nv[NV][D];
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                float acc = E[((size_t) j * NV + a) * D + i];
+#pragma unroll
+                for (int k = 0; k < D; ++k) acc = fmaf(is_last ? PL[i * D + k] : PN[i * D + k], v[a][k], acc);
+                nv[a][i] = acc;
+            }
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+            for (int i = 0; i < D; ++i) v[a][i] = nv[a][i];
+    }
+    float M[D * D];
+    {
+        /* M = [plast] * pn^(full tiles of the run), by binary powering */
+        const bool has_last = j1 == ntiles && j1 > j0;
+        unsigned e = (j1 - j0) - (has_last ? 1u : 0u);
+        float base[D * D], tmp[D * D];
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) {
+            M[i] = (i / D == i % D) ? 1.0f : 0.0f;
+            base[i] = PN[i];
+        }
+        while (e) {
+            if (e & 1u) {
+                fmq_mm<D>(base, M, tmp);
+#pragma unroll
+                for (int i = 0; i < D * D; ++i) M[i] = tmp[i];
+            }
+            fmq_mm<D>(base, base, tmp);
+#pragma unroll
+            for (int i = 0; i < D * D; ++i) base[i] = tmp[i];
+            e >>= 1;
+        }
+        if (has_last) {
+            fmq_mm<D>(PL, M, tmp);
+#pragma unroll
+            for (int i = 0; i < D * D; ++i) M[i] = tmp[i];
+        }
+    }
+
+    /* exclusive scan of the maps over the CTA */
+    fmq_warp_scan_maps<D, NV>(M, v, lane);
+    if (lane == 31u) {
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) wM[warp][i] = M[i];
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+            for (int i = 0; i < D; ++i) wv[warp][a * D + i] = v[a][i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float tM[D * D], tv[NV][D];
+        const bool have = lane < FMQ_SCAN_BLOCK / 32;
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) tM[i] = have ? wM[lane & 15u][i] : ((i / D == i % D) ? 1.0f : 0.0f);
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+            for (int i = 0; i < D; ++i) tv[a][i] = have ? wv[lane & 15u][a * D + i] : 0.0f;
+        fmq_warp_scan_maps<D, NV>(tM, tv, lane);
+        /* exclusive: the map of all warps BEFORE warp `lane` */
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) {
+            const float u = __shfl_up_sync(0xffffffffu, tM[i], 1u);
+            tM[i] = lane ? u : ((i / D == i % D) ? 1.0f : 0.0f);
+        }
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                const float u = __shfl_up_sync(0xffffffffu, tv[a][i], 1u);
+                tv[a][i] = lane ? u : 0.0f;
+            }
+        __syncwarp();
+        if (have) {
+#pragma unroll
+            for (int i = 0; i < D * D; ++i) wM[lane][i] = tM[i];
+#pragma unroll
+            for (int a = 0; a < NV; ++a)
+#pragma unroll
+                for (int i = 0; i < D; ++i) wv[lane][a * D + i] = tv[a][i];
+        }
+    }
+    __syncthreads();
+    /* the map of everything before this thread = (lanes before it in its warp) after (warps before) */
+    float eM[D * D], ev[NV][D];
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) {
+        const float u = __shfl_up_sync(0xffffffffu, M[i], 1u);
+        eM[i] = lane ? u : ((i / D == i % D) ? 1.0f : 0.0f);
+    }
+#pragma unroll
+    for (int a = 0; a < NV; ++a)
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const float u = __shfl_up_sync(0xffffffffu, v[a][i], 1u);
+            ev[a][i] = lane ? u : 0.0f;
+        }
+    {
+        float bM[D * D], bv[NV][D];
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) bM[i] = wM[warp][i];
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+            for (int i = 0; i < D; ++i) bv[a][i] = wv[warp][a * D + i];
+        fmq_compose<D, NV>(eM, ev, bM, bv);
+    }
+    /* state at the start of this thread's run, then walk the run */
+    float q[NV][D];
+#pragma unroll
+    for (int a = 0; a < NV; ++a)
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            float acc = ev[a][i];
+#pragma unroll
+            for (int k = 0; k < D; ++k) acc = fmaf(eM[i * D + k], c0[a][k], acc);
+            q[a][i] = acc;
+        }
+    for (unsigned j = j0; j < j1; ++j) {
+        const bool is_last = j + 1u == ntiles;
+        float nq[NV][D];
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                Q[((size_t) j * NV + a) * D + i] = q[a][i];
+                float acc = E[((size_t) j * NV + a) * D + i];
+#pragma unroll
+                for (int k = 0; k < D; ++k) acc = fmaf(is_last ? PL[i * D + k] : PN[i * D + k], q[a][k], acc);
+                nq[a][i] = acc;
+            }
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+            for (int i = 0; i < D; ++i) q[a][i] = nq[a][i];
+    }
+    if (j1 == ntiles && j1 > j0) {
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+            for (int i = 0; i < D; ++i) carry[a * D + i] = q[a][i];
+        if (last_sample) {
+            float si, sq;
+            fmq_load_sample(last_sample, 0u, si, sq);
+            s_prev[0] = si;
+            s_prev[1] = sq;
+        }
+    }
+}
+
+#endif /* FMD_QUALITY_CUH */

@@ -20,6 +20,7 @@
 
 #include "fmd_internal.h"
 #include "fmd_kernels.cuh"
+#include "fmd_quality.cuh"
 
 /* ------------------------------------------------------------------ errors */
 
@@ -45,6 +46,11 @@ extern "C" const char *fmd_last_error(void) { return g_err; }
 
 /* ----------------------------------------------------------------- context */
 
+struct fmd_ctx;
+static int quality_setup(fmd_ctx *c, unsigned decim);
+static void quality_free(fmd_ctx *c);
+static size_t quality_out_count(unsigned long long pos, size_t nsamp, unsigned M);
+
 struct fmd_slot {
     uint8_t *d_in = nullptr;
     float *d_out = nullptr;
@@ -54,8 +60,32 @@ struct fmd_slot {
     bool busy = false;
 };
 
+/* one cascade of the quality pipeline: host design + constants + device tables */
+struct fmq_filter {
+    fmq_design des;
+    fmq_consts c;
+    fmq_table_sizes sz;
+    float *d_tab = nullptr; /* lane | apow | ck | ckn */
+    const float *lane() const { return d_tab; }
+    const float *apow() const { return d_tab + sz.lane; }
+    const float *ck() const { return d_tab + sz.lane + sz.apow; }
+    const float *ckn() const { return d_tab + sz.lane + sz.apow + sz.ck; }
+};
+
+/* FMD_FLAG_QUALITY state of a context (fmd_quality.cuh) */
+struct fmq_ctx {
+    unsigned decim = 1;
+    unsigned lin = 0, lout = 0; /* sections */
+    fmq_filter fin, fout;
+    FmqState *d_state = nullptr;
+    float *d_ein = nullptr, *d_qin = nullptr, *d_eout = nullptr, *d_qout = nullptr; /* per-tile scratch */
+    unsigned tile_cap = 0;
+    unsigned long long pos = 0; /* stream position: global index of the next input sample */
+};
+
 struct fmd_ctx {
     fmd_config cfg;
+    fmq_ctx *q = nullptr;
     int device = 0;
     unsigned lin = 0, lout = 0;
     FmdSections sec;
@@ -156,6 +186,27 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
                              "reference the result then depends on which overrun it reads first",
                              (unsigned long long) cfg.chunk_bytes, cfg.in_degree);
     const unsigned conditioner = (cfg.mode >> 2) & 3u;
+    const bool quality = (cfg.flags & FMD_FLAG_QUALITY) != 0;
+    unsigned q_decim = 1;
+    if (quality) {
+        if (cfg.flags & FMD_FLAG_EXACT)
+            return fmd_set_error(FMD_EINVAL, "FMD_FLAG_EXACT audits the reference-compatible path; not with FMD_FLAG_QUALITY");
+        if (conditioner != 0u) return fmd_set_error(FMD_EINVAL, "quality mode centres the samples itself: -q0 only");
+        if (!(cfg.input_rate > 0.0) || !(cfg.sample_rate > 0.0))
+            return fmd_set_error(FMD_EINVAL, "quality mode needs the input rate (-r) and the output rate (-S)");
+        const double ratio = cfg.input_rate / cfg.sample_rate, m = floor(ratio + 0.5);
+        if (m < 1.0 || m > 65536.0 || fabs(ratio - m) > 1e-9 * ratio)
+            return fmd_set_error(FMD_EINVAL, "input rate / output rate = %.9g is not an integer in 1..65536", ratio);
+        q_decim = (unsigned) m;
+        if (fmd_sections(cfg.out_degree) > FMQ_MAXL || fmd_sections(cfg.in_degree) > FMQ_MAXL)
+            return fmd_set_error(FMD_EINVAL, "quality mode takes filter degrees up to %d", 2 * FMQ_MAXL);
+        const double lo = cfg.input_rate / 1000.0, hi = cfg.input_rate / 2.0;
+        if (!(cfg.lowpass_out >= lo && cfg.lowpass_out < hi) ||
+            (cfg.lowpass_in != 0.0 && !(cfg.lowpass_in >= lo && cfg.lowpass_in < hi)))
+            return fmd_set_error(FMD_EINVAL,
+                                 "quality mode keeps the filter state in float32: cut-offs must lie in "
+                                 "[input_rate/1000, input_rate/2)");
+    }
     if (conditioner == 1u || conditioner == 2u)
         return fmd_set_error(FMD_EINVAL,
                              "input conditioner -q%u is outside the accelerated path (-q0 and -q3 only: -q1 is a "
@@ -189,17 +240,20 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
     c->sec.lin = (int) c->lin;
     c->sec.lout = (int) c->lout;
     c->sec.conditioner = (int) conditioner;
-    /* -q3 (normalizeInput) is served by the op-for-op path only, for now */
-    if (conditioner == 3u) c->fast_in_ok = false;
+    /* -q3 (normalizeInput) streams without the input filter; with it the zero extension past a
+     * chunk is not a byte value (no u8 normalises to 0.0), so that combination stays op-for-op */
+    if (conditioner == 3u && c->lin) c->fast_in_ok = false;
 
-    int rc = fmd_design_sos(cfg.mode & 1u, cfg.out_degree, cfg.lowpass_out, cfg.sample_rate, cfg.epsilon,
+    /* quality mode runs both filters at the input rate (the output one BEFORE the decimation) */
+    const double design_rate = quality ? cfg.input_rate : cfg.sample_rate;
+    int rc = fmd_design_sos(cfg.mode & 1u, cfg.out_degree, cfg.lowpass_out, design_rate, cfg.epsilon,
                             &c->sec.out[0][0]);
     if (!rc) rc = fmd_fold_taps(&c->sec.out[0][0], c->lout, 1, c->st.tout, &c->st.dco, &c->nto);
     if (!rc && c->lin) {
         float dci = 0.f;
         unsigned nti_q = 0;
         float taps_q[FMD_MAX_TAPS];
-        rc = fmd_design_sos((cfg.mode >> 1) & 1u, cfg.in_degree, cfg.lowpass_in, cfg.sample_rate, cfg.epsilon,
+        rc = fmd_design_sos((cfg.mode >> 1) & 1u, cfg.in_degree, cfg.lowpass_in, design_rate, cfg.epsilon,
                             &c->sec.in[0][0]);
         if (!rc) rc = fmd_fold_taps(&c->sec.in[0][0], c->lin, 1, c->st.tin, &dci, &c->nti);
         /* the Q lane lacks the "+1" (filter.c:255): same taps, different constant */
@@ -242,6 +296,13 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
         fmd_destroy(c);
         return fmd_set_error(FMD_ECUDA, "coefficient upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
+    if (quality) {
+        rc = quality_setup(c, q_decim);
+        if (rc) {
+            fmd_destroy(c);
+            return rc;
+        }
+    }
     *out = c;
     return FMD_OK;
 }
@@ -272,6 +333,7 @@ extern "C" void fmd_destroy(fmd_ctx *c) {
         delete[] c->pev;
     }
     if (c->d_sec) cudaFree(c->d_sec);
+    quality_free(c);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_k) cudaStreamDestroy(c->s_k);
     if (c->s_out) cudaStreamDestroy(c->s_out);
@@ -320,8 +382,13 @@ extern "C" int fmd_host_unregister(void *ptr) {
 /* ---------------------------------------------------------------- launching */
 
 extern "C" size_t fmd_out_count(const fmd_ctx *c, size_t nbytes) {
-    (void) c;
+    if (c && c->q) return quality_out_count(c->q->pos, nbytes / 2, c->q->decim);
     return nbytes >> 2; /* whole chunks give B/4 each; the ragged tail gives r/4 */
+}
+
+extern "C" size_t fmd_max_out_count(const fmd_ctx *c, size_t nbytes) {
+    if (c && c->q) return quality_out_count(0, nbytes / 2, c->q->decim);
+    return nbytes >> 2;
 }
 
 typedef void (*fast_fn)(const uint8_t *, float *, const FmdGeom, const FmdStencil, const FmdSections *);
@@ -351,8 +418,22 @@ static fast_fn pick_in(unsigned nti, unsigned nto) {
     }
 }
 
+/* -q3 (normalizeInput) streams when there is no input filter */
+template <int AT>
+static fast_fn pick_q3(unsigned nto) {
+    switch (nto) {
+        case 1: return fmd_fast_kernel<0, 1, AT, 3>;
+        case 2: return fmd_fast_kernel<0, 2, AT, 3>;
+        case 3: return fmd_fast_kernel<0, 3, AT, 3>;
+        case 4: return fmd_fast_kernel<0, 4, AT, 3>;
+        case 5: return fmd_fast_kernel<0, 5, AT, 3>;
+        default: return nullptr;
+    }
+}
+
 /* `at` = terms of the atan polynomial: 6 (1.75e-6) unless the output stencil amplifies too much */
-static fast_fn pick_fast(unsigned nti, unsigned nto, unsigned at) {
+static fast_fn pick_fast(unsigned nti, unsigned nto, unsigned at, unsigned conditioner) {
+    if (conditioner == 3u) return nti ? nullptr : (at <= 6 ? pick_q3<6>(nto) : pick_q3<8>(nto));
     return at <= 6 ? pick_in<6>(nti, nto) : pick_in<8>(nti, nto);
 }
 
@@ -385,7 +466,7 @@ static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned
     g.head = 0;
     g.exact_blocks = 0;
 
-    fast_fn fn = pick_fast(c->nti, c->nto, c->atan_terms);
+    fast_fn fn = pick_fast(c->nti, c->nto, c->atan_terms, (unsigned) c->sec.conditioner);
     const bool aligned = ((uintptr_t) d_in % 16 == 0) && ((uintptr_t) d_out % 16 == 0) && (stride % 16 == 0) &&
                          (nchunks == 1 || chunk_out % 4 == 0);
     /* the fast kernel covers whole 128-output passes; if the chunk is not a multiple of 128
@@ -438,6 +519,213 @@ static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned
     return FMD_OK;
 }
 
+
+/* ------------------------------------------------------------ quality pipeline (opt-in) */
+
+static int quality_upload_filter(fmq_filter &f, const float *sos6, unsigned sections) {
+    int rc = fmq_design_from_sos(sos6, sections, &f.des);
+    if (rc) return rc;
+    fmq_build_consts(&f.des, &f.c);
+    fmq_table_layout(&f.des, &f.sz);
+    const size_t n = (size_t) f.sz.lane + f.sz.apow + f.sz.ck + f.sz.ckn;
+    float *h = (float *) malloc(n * sizeof(float));
+    if (!h) return fmd_set_error(FMD_ENOMEM, "out of host memory");
+    fmq_build_tables(&f.des, h, h + f.sz.lane, h + f.sz.lane + f.sz.apow, h + f.sz.lane + f.sz.apow + f.sz.ck);
+    cudaError_t e = cudaMalloc(&f.d_tab, n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(f.d_tab, h, n * sizeof(float), cudaMemcpyHostToDevice);
+    free(h);
+    if (e != cudaSuccess) return fmd_set_error(FMD_ECUDA, "quality table upload failed: %s", cudaGetErrorString(e));
+    return FMD_OK;
+}
+
+static int quality_setup(fmd_ctx *c, unsigned decim) {
+    fmq_ctx *q = new (std::nothrow) fmq_ctx();
+    if (!q) return fmd_set_error(FMD_ENOMEM, "out of host memory");
+    c->q = q;
+    q->decim = decim;
+    q->lout = c->lout;
+    q->lin = c->lin;
+    int rc = quality_upload_filter(q->fout, &c->sec.out[0][0], q->lout);
+    if (!rc && q->lin) rc = quality_upload_filter(q->fin, &c->sec.in[0][0], q->lin);
+    if (rc) return rc;
+    FMD_CUDA(cudaMalloc(&q->d_state, sizeof(FmqState)));
+    FMD_CUDA(cudaMemset(q->d_state, 0, sizeof(FmqState)));
+    return FMD_OK;
+}
+
+static void quality_free(fmd_ctx *c) {
+    fmq_ctx *q = c->q;
+    if (!q) return;
+    if (q->fin.d_tab) cudaFree(q->fin.d_tab);
+    if (q->fout.d_tab) cudaFree(q->fout.d_tab);
+    if (q->d_state) cudaFree(q->d_state);
+    if (q->d_ein) cudaFree(q->d_ein);
+    if (q->d_qin) cudaFree(q->d_qin);
+    if (q->d_eout) cudaFree(q->d_eout);
+    if (q->d_qout) cudaFree(q->d_qout);
+    delete q;
+    c->q = nullptr;
+}
+
+static int quality_reserve_tiles(fmq_ctx *q, unsigned ntiles) {
+    if (ntiles <= q->tile_cap) return FMD_OK;
+    /* cudaFree waits for the kernels that may still read the old scratch */
+    if (q->d_ein) cudaFree(q->d_ein);
+    if (q->d_qin) cudaFree(q->d_qin);
+    if (q->d_eout) cudaFree(q->d_eout);
+    if (q->d_qout) cudaFree(q->d_qout);
+    q->d_ein = q->d_qin = q->d_eout = q->d_qout = nullptr;
+    q->tile_cap = 0;
+    const unsigned cap = ntiles < 4096u ? 4096u : ntiles;
+    const size_t per_in = (size_t) cap * 2 * FMQ_MAXD * sizeof(float), per_out = (size_t) cap * FMQ_MAXD * sizeof(float);
+    FMD_CUDA(cudaMalloc(&q->d_ein, per_in));
+    FMD_CUDA(cudaMalloc(&q->d_qin, per_in));
+    FMD_CUDA(cudaMalloc(&q->d_eout, per_out));
+    FMD_CUDA(cudaMalloc(&q->d_qout, per_out));
+    q->tile_cap = cap;
+    return FMD_OK;
+}
+
+/* outputs of the next `nsamp` samples when the stream stands at `pos` */
+static size_t quality_out_count(unsigned long long pos, size_t nsamp, unsigned M) {
+    const unsigned long long r0 = (M - pos % M) % M;
+    return nsamp > r0 ? (size_t) ((nsamp - r0 + M - 1) / M) : 0;
+}
+
+typedef void (*fmq_main_fn)(const uint8_t *, float *, const FmqGeom, const fmq_consts, const fmq_consts, const float *,
+                            const float *, const float *, const float *, const float *, float *, const FmqState *);
+
+template <int LIN>
+static fmq_main_fn quality_pick_out(unsigned lout) {
+    switch (lout) {
+        case 1: return fmq_main_kernel<LIN, 1>;
+        case 2: return fmq_main_kernel<LIN, 2>;
+        case 3: return fmq_main_kernel<LIN, 3>;
+        default: return nullptr;
+    }
+}
+
+static fmq_main_fn quality_pick_main(unsigned lin, unsigned lout) {
+    switch (lin) {
+        case 0: return quality_pick_out<0>(lout);
+        case 1: return quality_pick_out<1>(lout);
+        case 2: return quality_pick_out<2>(lout);
+        case 3: return quality_pick_out<3>(lout);
+        default: return nullptr;
+    }
+}
+
+/* one launch group: `n` samples (< 2^31) that continue the stream; *nout = floats written */
+static int quality_launch(fmd_ctx *c, const uint8_t *d_in, unsigned n, float *d_out, cudaStream_t s, size_t *nout) {
+    fmq_ctx *q = c->q;
+    FmqGeom g;
+    g.n = n;
+    g.ntiles = (n + FMQ_TILE - 1) / FMQ_TILE;
+    g.decim = q->decim;
+    g.r0 = (unsigned) ((q->decim - q->pos % q->decim) % q->decim);
+    g.n_out = (unsigned) quality_out_count(q->pos, n, q->decim);
+    *nout = g.n_out;
+    int rc = quality_reserve_tiles(q, g.ntiles);
+    if (rc) return rc;
+    const unsigned len_last = n - (g.ntiles - 1u) * FMQ_TILE;
+    FmqMat pn, pl;
+
+    if (q->lin) {
+        memset(&pn, 0, sizeof pn);
+        memset(&pl, 0, sizeof pl);
+        memcpy(pn.m, q->fin.c.tile, sizeof pn.m);
+        fmq_matpow_f(&q->fin.des, len_last, pl.m);
+        switch (q->lin) {
+            case 1:
+                fmq_in_aggregate_kernel<1><<<g.ntiles, FMQ_THREADS, 0, s>>>(d_in, g, q->fin.c, q->fin.lane(), q->fin.apow(), q->d_state, q->d_ein);
+                fmq_scan_tiles_kernel<2, 2><<<1, FMQ_SCAN_BLOCK, 0, s>>>(q->d_ein, q->d_qin, &q->d_state->in_q[0][0], pn, pl, g.ntiles, nullptr, nullptr);
+                break;
+            case 2:
+                fmq_in_aggregate_kernel<2><<<g.ntiles, FMQ_THREADS, 0, s>>>(d_in, g, q->fin.c, q->fin.lane(), q->fin.apow(), q->d_state, q->d_ein);
+                fmq_scan_tiles_kernel<4, 2><<<1, FMQ_SCAN_BLOCK, 0, s>>>(q->d_ein, q->d_qin, &q->d_state->in_q[0][0], pn, pl, g.ntiles, nullptr, nullptr);
+                break;
+            default:
+                fmq_in_aggregate_kernel<3><<<g.ntiles, FMQ_THREADS, 0, s>>>(d_in, g, q->fin.c, q->fin.lane(), q->fin.apow(), q->d_state, q->d_ein);
+                fmq_scan_tiles_kernel<6, 2><<<1, FMQ_SCAN_BLOCK, 0, s>>>(q->d_ein, q->d_qin, &q->d_state->in_q[0][0], pn, pl, g.ntiles, nullptr, nullptr);
+                break;
+        }
+        FMD_CUDA(cudaGetLastError());
+        c->launches += 2;
+    }
+
+    fmq_main_fn fn = quality_pick_main(q->lin, q->lout);
+    if (!fn) return fmd_set_error(FMD_EINVAL, "no quality kernel for %u/%u sections", q->lin, q->lout);
+    /* shared memory for the kept samples of one tile */
+    const unsigned keep_cap = FMQ_TILE / q->decim + 2u;
+    const size_t smem = (size_t) (keep_cap < FMQ_TILE ? keep_cap : FMQ_TILE) * sizeof(float);
+    cudaEvent_t *pe = nullptr;
+    if (c->profile) {
+        if (c->pev_used == c->pev_cap) {
+            rc = prof_flush(c);
+            if (rc) return rc;
+        }
+        pe = &c->pev[2 * c->pev_used++];
+        FMD_CUDA(cudaEventRecord(pe[0], s));
+    }
+    fn<<<g.ntiles, FMQ_THREADS, smem, s>>>(d_in, d_out, g, q->lin ? q->fin.c : q->fout.c, q->fout.c,
+                                           q->lin ? q->fin.lane() : nullptr, q->fout.lane(), q->fout.apow(),
+                                           q->fout.ck(), q->d_qin, q->d_eout, q->d_state);
+    FMD_CUDA(cudaGetLastError());
+    if (pe) FMD_CUDA(cudaEventRecord(pe[1], s));
+
+    memset(&pn, 0, sizeof pn);
+    memset(&pl, 0, sizeof pl);
+    memcpy(pn.m, q->fout.c.tile, sizeof pn.m);
+    fmq_matpow_f(&q->fout.des, len_last, pl.m);
+    const uint8_t *last = d_in + 2ull * (n - 1u);
+    switch (q->lout) {
+        case 1:
+            fmq_scan_tiles_kernel<2, 1><<<1, FMQ_SCAN_BLOCK, 0, s>>>(q->d_eout, q->d_qout, q->d_state->out_q, pn, pl, g.ntiles, last, q->d_state->s_prev);
+            if (g.n_out) fmq_zir_kernel<2><<<(g.n_out + 255u) / 256u, 256, 0, s>>>(d_out, g, q->fout.ckn(), q->d_qout);
+            break;
+        case 2:
+            fmq_scan_tiles_kernel<4, 1><<<1, FMQ_SCAN_BLOCK, 0, s>>>(q->d_eout, q->d_qout, q->d_state->out_q, pn, pl, g.ntiles, last, q->d_state->s_prev);
+            if (g.n_out) fmq_zir_kernel<4><<<(g.n_out + 255u) / 256u, 256, 0, s>>>(d_out, g, q->fout.ckn(), q->d_qout);
+            break;
+        default:
+            fmq_scan_tiles_kernel<6, 1><<<1, FMQ_SCAN_BLOCK, 0, s>>>(q->d_eout, q->d_qout, q->d_state->out_q, pn, pl, g.ntiles, last, q->d_state->s_prev);
+            if (g.n_out) fmq_zir_kernel<6><<<(g.n_out + 255u) / 256u, 256, 0, s>>>(d_out, g, q->fout.ckn(), q->d_qout);
+            break;
+    }
+    FMD_CUDA(cudaGetLastError());
+    c->launches += g.n_out ? 3 : 2;
+    q->pos += n;
+    return FMD_OK;
+}
+
+static int quality_demod_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, float *d_out, cudaStream_t s) {
+    if (nbytes & 1u) return fmd_set_error(FMD_EINVAL, "quality mode takes whole IQ samples (an even number of bytes)");
+    if (((uintptr_t) d_in % 16) || ((uintptr_t) d_out % 4))
+        return fmd_set_error(FMD_EINVAL, "quality mode needs a 16-byte aligned input and a 4-byte aligned output");
+    size_t left = nbytes / 2;
+    const size_t step = (size_t) 1 << 30; /* a multiple of the tile: later groups stay 16-byte aligned */
+    while (left) {
+        const unsigned n = (unsigned) (left < step ? left : step);
+        size_t nout = 0;
+        int rc = quality_launch(c, d_in, n, d_out, s, &nout);
+        if (rc) return rc;
+        d_in += 2ull * n;
+        d_out += nout;
+        left -= n;
+    }
+    return FMD_OK;
+}
+
+extern "C" int fmd_reset(fmd_ctx *c) {
+    if (!c) return fmd_set_error(FMD_EINVAL, "null argument");
+    if (!c->q) return FMD_OK;
+    FMD_CUDA(cudaSetDevice(c->device));
+    FMD_CUDA(cudaDeviceSynchronize());
+    FMD_CUDA(cudaMemset(c->q->d_state, 0, sizeof(FmqState)));
+    c->q->pos = 0;
+    return FMD_OK;
+}
+
 extern "C" int fmd_demod_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, float *d_out, void *stream) {
     if (!c || (!d_in && nbytes) || (!d_out && nbytes)) return fmd_set_error(FMD_EINVAL, "null argument");
     cudaStream_t s = (cudaStream_t) stream; /* NULL is CUDA's default stream, as everywhere in CUDA */
@@ -449,9 +737,14 @@ extern "C" int fmd_demod_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, 
     int prev = -1;
     FMD_CUDA(cudaGetDevice(&prev));
     if (prev != c->device) FMD_CUDA(cudaSetDevice(c->device));
-    int rc = launch_chunks(c, d_in, d_out, (unsigned) nfull, (unsigned) (B >> 2), B, s);
-    if (!rc && rem)
-        rc = launch_chunks(c, d_in + nfull * B, d_out + nfull * (B >> 2), 1u, (unsigned) (rem >> 2), B, s);
+    int rc;
+    if (c->q) {
+        rc = quality_demod_device(c, d_in, nbytes, d_out, s);
+    } else {
+        rc = launch_chunks(c, d_in, d_out, (unsigned) nfull, (unsigned) (B >> 2), B, s);
+        if (!rc && rem)
+            rc = launch_chunks(c, d_in + nfull * B, d_out + nfull * (B >> 2), 1u, (unsigned) (rem >> 2), B, s);
+    }
     if (prev != c->device && prev >= 0) cudaSetDevice(prev);
     return rc;
 }
@@ -488,9 +781,11 @@ extern "C" int fmd_ring_create(fmd_ctx *c, unsigned slots, size_t slot_bytes) {
     if (!c->slots) return fmd_set_error(FMD_ENOMEM, "out of host memory");
     c->nslots = slots;
     c->slot_bytes = slot_bytes;
+    const size_t out_bytes = fmd_max_out_count(c, slot_bytes) * sizeof(float);
     for (unsigned i = 0; i < slots; ++i) {
         fmd_slot &s = c->slots[i];
-        if (cudaMalloc(&s.d_in, slot_bytes) != cudaSuccess || cudaMalloc(&s.d_out, slot_bytes) != cudaSuccess ||
+        if (cudaMalloc(&s.d_in, slot_bytes) != cudaSuccess ||
+            cudaMalloc(&s.d_out, out_bytes ? out_bytes : sizeof(float)) != cudaSuccess ||
             cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming) != cudaSuccess) {
@@ -551,21 +846,23 @@ extern "C" int fmd_demod_host(fmd_ctx *c, const uint8_t *in, size_t nbytes, floa
         if (rc) return rc;
     }
     const unsigned ns = c->nslots;
-    size_t off = 0;
+    size_t off = 0, out_off = 0;
     unsigned n = 0;
     while (off < nbytes) {
         const unsigned slot = n % ns;
         const size_t len = nbytes - off < c->slot_bytes ? nbytes - off : c->slot_bytes;
         int rc = fmd_wait(c, slot);
-        if (!rc) rc = fmd_submit(c, slot, in + off, len, out + (off >> 2));
+        const size_t produced = fmd_out_count(c, len); /* before the submit moves the stream on */
+        if (!rc) rc = fmd_submit(c, slot, in + off, len, out + out_off);
         if (rc) return rc;
         off += len;
+        out_off += produced;
         ++n;
     }
     for (unsigned i = 0; i < ns; ++i) {
         int rc = fmd_wait(c, i);
         if (rc) return rc;
     }
-    if (nout) *nout = fmd_out_count(c, nbytes);
+    if (nout) *nout = out_off;
     return FMD_OK;
 }

@@ -46,7 +46,19 @@ enum { FMD_BUTTER_LP = 0, FMD_CHEBY1_LP = 1, FMD_BUTTER_HP = 2, FMD_CHEBY1_HP = 
 
 /* fmd_config.flags */
 enum {
-    FMD_FLAG_EXACT = 1u /* run every output through the op-for-op kernel (slow; for audits) */
+    FMD_FLAG_EXACT = 1u,  /* run every output through the op-for-op kernel (slow; for audits) */
+    /*
+     * Opt-in "quality" pipeline -- NOT what the reference computes, never the
+     * default.  The same designed sections (src/matrix.c:25-80, designed at `input_rate`) run as
+     * true recursive filters whose state is carried through the whole stream, the discriminator
+     * works on ADJACENT samples (x[n] = arg z[n] conj z[n-1]), and the output is decimated by
+     * M = input_rate / sample_rate inside the output filter's kernel: float m of the stream is
+     * the filtered discriminator at input sample m*M.  Samples are centred by -127.5.  The
+     * context is a STREAM: successive fmd_demod_* / fmd_submit calls continue it (issue them in
+     * order on one stream), fmd_reset starts a new one.  Needs input_rate / sample_rate to be an
+     * integer >= 1, degrees <= 6, -q0, and cut-offs of at least input_rate / 1000 (float32 state).
+     */
+    FMD_FLAG_QUALITY = 2u
 };
 
 /*
@@ -67,6 +79,8 @@ typedef struct fmd_config {
                              are rejected), bits4-5 demod (-c) */
     uint32_t flags;       /* FMD_FLAG_*                                                           */
     uint64_t chunk_bytes; /* consumerArgs.bufSize (default 262144); multiple of 4                 */
+    double input_rate;    /* -r  rate of the IQ input; read only under FMD_FLAG_QUALITY (the
+                             reference parses and ignores -r, src/main.c:180)                     */
 } fmd_config;
 
 typedef struct fmd_ctx fmd_ctx;
@@ -112,8 +126,14 @@ int fmd_host_free(void *ptr);
 int fmd_host_register(void *ptr, size_t bytes);
 int fmd_host_unregister(void *ptr);
 
-/* floats produced for `nbytes` of input under the tail policy below */
+/* floats produced for `nbytes` of input under the tail policy below.  Under FMD_FLAG_QUALITY:
+ * for the NEXT `nbytes` of the stream (depends on the stream position modulo M). */
 size_t fmd_out_count(const fmd_ctx *ctx, size_t nbytes);
+/* upper bound of fmd_out_count over every stream position (sizes output buffers) */
+size_t fmd_max_out_count(const fmd_ctx *ctx, size_t nbytes);
+/* FMD_FLAG_QUALITY: forget the carried filter state and stream position (waits for the device).
+ * No effect otherwise: the reference keeps no state between chunks (src/matrix.c:272). */
+int fmd_reset(fmd_ctx *ctx);
 
 /*
  * ---- the hot path: replaces one or many iterations of the worker loop

@@ -64,6 +64,20 @@ void fmo_sweep_lane(const float *x, float *y, size_t n, size_t L, const float *s
 size_t fmo_process_chunks(const uint8_t *in, size_t nchunks, size_t chunk_bytes,
                           const fmo_config *cfg, float *out);
 
+/*
+ * ---- opt-in "quality" pipeline (fm_quality_oracle.c): recursive filters with state carried
+ * through the stream, adjacent-sample discriminator, decimation by M = input_rate / cfg->fs.
+ * Not a restatement of the reference (which computes none of this): pinned against
+ * scipy.signal.sosfilt instead, see the header of fm_quality_oracle.c. ----
+ */
+size_t fmo_quality_state_size(void);
+/* returns M, or 0 if input_rate / cfg->fs is not an integer >= 1 or a degree is out of range */
+unsigned fmo_quality_init(void *state, const fmo_config *cfg, double input_rate);
+/* the next nsamples complex samples of the stream -> floats written (global index % M == 0) */
+size_t fmo_quality_run(void *state, const uint8_t *in, size_t nsamples, float *out);
+/* undecimated intermediate signals: z[2n], z[2n+1], x[n], v[n] */
+void fmo_quality_stages(void *state, const uint8_t *in, size_t nsamples, double *z, double *x, double *v);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,18 @@ class Port:
         L.fmo_sweep_lane.restype = None
         L.fmo_process_chunks.argtypes = [_u8p, C.c_size_t, C.c_size_t, C.POINTER(_FmoConfig), _f32p]
         L.fmo_process_chunks.restype = C.c_size_t
+        L.fmo_quality_state_size.restype = C.c_size_t
+        L.fmo_quality_init.argtypes = [C.c_void_p, C.POINTER(_FmoConfig), C.c_double]
+        L.fmo_quality_init.restype = C.c_uint
+        L.fmo_quality_run.argtypes = [C.c_void_p, _u8p, C.c_size_t, _f32p]
+        L.fmo_quality_run.restype = C.c_size_t
+        _f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+        L.fmo_quality_stages.argtypes = [C.c_void_p, _u8p, C.c_size_t, _f64p, _f64p, _f64p]
+        L.fmo_quality_stages.restype = None
+
+    def quality(self, cfg: "Config", input_rate: float) -> "QualityStream":
+        """Streaming state of the opt-in quality pipeline (fm_quality_oracle.c)."""
+        return QualityStream(self.lib, cfg, input_rate)
 
     def design(self, kind: int, degree: int, fc: float, fs: float, eps: float = 0.3) -> np.ndarray:
         sos = np.zeros((sections(degree), 6), np.float32)
@@ -133,6 +145,33 @@ class Port:
         if n != out.size:
             raise ValueError("oracle port rejected the configuration")
         return out
+
+
+class QualityStream:
+    """fm_quality_oracle.c: causal IIR cascades with carried state, adjacent-sample discriminator,
+    decimation by M = input_rate / cfg.fs.  Double precision, serial."""
+
+    def __init__(self, lib, cfg: Config, input_rate: float) -> None:
+        self.lib = lib
+        self._st = C.create_string_buffer(lib.fmo_quality_state_size())
+        c = _FmoConfig(cfg.fs, cfg.fc_in, cfg.fc_out, cfg.eps, cfg.deg_in, cfg.deg_out, cfg.mode)
+        self.decim = int(lib.fmo_quality_init(self._st, C.byref(c), input_rate))
+        if self.decim == 0:
+            raise ValueError("quality oracle rejected the configuration")
+
+    def run(self, raw: np.ndarray) -> np.ndarray:
+        raw = np.ascontiguousarray(raw, np.uint8)
+        n = raw.size // 2
+        out = np.empty(n // self.decim + 2, np.float32)
+        got = self.lib.fmo_quality_run(self._st, raw, n, out)
+        return out[:got].copy()
+
+    def stages(self, raw: np.ndarray):
+        raw = np.ascontiguousarray(raw, np.uint8)
+        n = raw.size // 2
+        z, x, v = np.empty(2 * n), np.empty(n), np.empty(n)
+        self.lib.fmo_quality_stages(self._st, raw, n, z, x, v)
+        return z, x, v
 
 
 class Ref:

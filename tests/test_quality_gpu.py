@@ -1,0 +1,136 @@
+"""GPU: the opt-in quality pipeline (FMD_FLAG_QUALITY) through the C ABI against its oracle
+(oracle/fm_quality_oracle.c, pinned to scipy fixtures by tests/test_quality_oracle.py).
+
+Bar: the same as the reference-compatible path -- decimation indices identical (output m is input
+sample m*M of the stream, whatever the call boundaries), floats within max-abs 1e-4."""
+from __future__ import annotations
+
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import demodulator_b200 as fm
+from demodulator_b200 import synth
+from oracle import pyoracle as po
+from helpers import TOL
+from test_quality_oracle import QUALITY_CASES, check_against_fixture, load_quality
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "demodulator_b200", "bin", "demodulator")
+
+
+def quality_kwargs(cfg: po.Config, rate: float) -> dict:
+    return dict(sampleRate=cfg.fs, lowpassIn=cfg.fc_in, lowpassOut=cfg.fc_out, epsilon=cfg.eps,
+                inFilterDegree=cfg.deg_in, outFilterDegree=cfg.deg_out, mode=cfg.mode, quality=True, inputRate=rate)
+
+
+def max_err(got: np.ndarray, want: np.ndarray) -> float:
+    assert got.shape == want.shape, (got.shape, want.shape)
+    return float(np.abs(got.astype(np.float64) - want.astype(np.float64)).max()) if want.size else 0.0
+
+
+@pytest.mark.parametrize("name", QUALITY_CASES)
+def test_quality_fixture_and_oracle(name, oracle_port):
+    g, cfg, raw, rate = load_quality(name)
+    with fm.Demodulator(**quality_kwargs(cfg, rate)) as d:
+        out = d.process(raw)
+        launches = d.launches
+    check_against_fixture(out, g, TOL, name)
+    err = max_err(out, oracle_port.quality(cfg, rate).run(raw))
+    print(f"{name}: {out.size} floats, {launches} launches, max-abs vs oracle {err:.2e}")
+    assert err <= TOL and launches >= 3
+
+
+@pytest.mark.parametrize("name,sizes", [
+    ("quality_cfg2", (2, 4, 30, 64, 8192, 8190, 20000, 131072 + 6, 100000)),
+    ("quality_cfg3", (50, 49, 1, 8191, 8193, 300000)),
+    ("quality_d5_M1", (1, 1, 2, 33, 16384, 50000)),
+])
+def test_quality_stream_continues_across_calls(name, sizes, oracle_port):
+    """filter state, the discriminator's neighbour and the decimation phase are carried from call
+    to call: any split gives the unsplit result; reset() starts over"""
+    g, cfg, raw, rate = load_quality(name)
+    with fm.Demodulator(**quality_kwargs(cfg, rate)) as d:
+        for rep in range(2):
+            off = 0
+            worst = 0.0
+            q = oracle_port.quality(cfg, rate)
+            for n in sizes:
+                seg = raw[2 * off:2 * (off + n)]
+                want = q.run(seg)
+                assert d.out_count(seg.size) == want.size  # depends on the stream position
+                got = d.process(seg)
+                worst = max(worst, max_err(got, want))
+                off += n
+            assert worst <= TOL, (name, rep, worst)
+            d.reset()
+
+
+def test_quality_device_resident_many_tiles(oracle_port):
+    """16 Mi samples resident in HBM, one call: 2048 tiles through the tile-level scan"""
+    import torch
+    cfg, rate = po.Config(fs=48000.0, fc_out=15000.0), 2.4e6
+    n = 16 << 20
+    c = synth.CONFIGS["cfg3"]
+    raw = synth.fm_iq_u8(n, c["fs_sig"], c["df"], c["fm"], 11)
+    want = oracle_port.quality(cfg, rate).run(raw)
+    d_in = torch.from_numpy(raw).cuda()
+    with fm.Demodulator(**quality_kwargs(cfg, rate)) as d:
+        d_out = torch.full((d.max_out_count(raw.size) + 8,), 7.0, dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        d.process_device(d_in.data_ptr(), raw.size, d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+    out = d_out.cpu().numpy()
+    assert (out[want.size:] == 7.0).all()  # nothing written past the last output
+    err = max_err(out[:want.size], want)
+    print(f"device-resident 16 Mi samples: max-abs {err:.2e}")
+    assert err <= TOL
+
+
+def test_quality_with_input_filter_many_tiles(oracle_port):
+    """both cascades over 4 Mi samples (512 tiles), in two unequal calls"""
+    cfg, rate = po.Config(fs=96000.0, fc_out=6500.0, fc_in=12500.0), 192e3
+    n = 4 << 20
+    c = synth.CONFIGS["cfg2"]
+    raw = synth.fm_iq_u8(n, c["fs_sig"], c["df"], c["fm"], 12)
+    want = oracle_port.quality(cfg, rate).run(raw)
+    cut = 2 * (3 * 8192 * 100 + 4097)
+    with fm.Demodulator(**quality_kwargs(cfg, rate)) as d:
+        out = np.concatenate([d.process(raw[:cut]), d.process(raw[cut:])])
+    err = max_err(out, want)
+    print(f"-L quality 4 Mi samples: max-abs {err:.2e}")
+    assert err <= TOL
+
+
+def test_quality_constant_tone_property():
+    """a pure tone at f has phase step 2*pi*f/rate per sample: once the filters have settled every
+    output equals it (DC gain of the Butterworth cascade is 1), at any size"""
+    rate, f, n = 2.4e6, 60e3, 8 << 20
+    t = np.arange(n, dtype=np.float64)
+    iq = np.empty(2 * n, np.float64)
+    iq[0::2] = 127.5 + 100.0 * np.cos(2 * np.pi * f * t / rate)
+    iq[1::2] = 127.5 + 100.0 * np.sin(2 * np.pi * f * t / rate)
+    raw = np.clip(np.rint(iq), 0, 255).astype(np.uint8)
+    with fm.Demodulator(sampleRate=48000.0, lowpassOut=15000.0, quality=True, inputRate=rate) as d:
+        out = d.process(raw)
+    assert out.size == n // 50
+    settled = out[1000:]
+    assert abs(float(settled.mean()) - 2 * np.pi * f / rate) < 2e-4
+    assert float(settled.std()) < 2e-3  # 8-bit quantisation noise through a 15 kHz lowpass
+
+
+def test_quality_cli(tmp_path_nodash, oracle_port):
+    g, cfg, raw, rate = load_quality("quality_cfg3")
+    src, dst = tmp_path_nodash / "in.u8", tmp_path_nodash / "out.f32"
+    raw.tofile(src)
+    r = subprocess.run([CLI, "-i", str(src), "-o", str(dst), "-Q", "-r2400000", "-S48000", "-l15000"],
+                       capture_output=True, text=True, env=dict(os.environ, FMD_SLOT_MB="1"))
+    assert r.returncode == 0, r.stderr
+    out = np.fromfile(dst, np.float32)
+    # the CLI drops a ragged tail below 4 bytes (2 samples), like the reference-compatible mode
+    want = oracle_port.quality(cfg, rate).run(raw[: raw.size & ~3])
+    assert max_err(out, want) <= TOL
