@@ -104,13 +104,13 @@ void fmq_matpow_f(const fmq_design *d, unsigned long long k, float *out) {
     to_float(m, d->D * d->D, out);
 }
 
-void fmq_build_consts(const fmq_design *d, fmq_consts *c) {
+void fmq_build_consts(const fmq_design *d, unsigned unit, fmq_consts *c) {
     memset(c, 0, sizeof *c);
     c->L = d->L;
     c->D = d->D;
     memcpy(c->sos, d->sos, sizeof c->sos);
-    for (int j = 0; j < 5; ++j) fmq_matpow_f(d, (unsigned long long) FMQ_T << j, c->lvl[j]);
-    fmq_matpow_f(d, 32ull * FMQ_T, c->warp);
+    for (int j = 0; j < 5; ++j) fmq_matpow_f(d, (unsigned long long) unit << j, c->lvl[j]);
+    fmq_matpow_f(d, 32ull * unit, c->warp);
     fmq_matpow_f(d, (unsigned long long) FMQ_TILE, c->tile);
 }
 
@@ -120,16 +120,25 @@ void fmq_table_layout(const fmq_design *d, fmq_table_sizes *sz) {
     sz->apow = (FMQ_T + 1u) * D * D;
     sz->ck = FMQ_T * D;
     sz->ckn = FMQ_TILE * D;
+    sz->lane_tile = 32u * D * D;
 }
 
-void fmq_build_tables(const fmq_design *d, float *lane, float *apow, float *ck, float *ckn) {
+unsigned fmq_build_tables(const fmq_design *d, float *lane, float *apow, float *ck, float *ckn, float *lane_tile) {
     const int D = d->D;
     ld a[FMQ_MAXD * FMQ_MAXD], pt[FMQ_MAXD * FMQ_MAXD], cur[FMQ_MAXD * FMQ_MAXD], tmp[FMQ_MAXD * FMQ_MAXD];
+    unsigned zir_len = 1;
     mat_pack(d, a);
     fmq_matpow(d, FMQ_T, pt);
     mat_identity(D, cur);
     for (int l = 0; l < 32; ++l) { /* (A^T)^l */
         to_float(cur, D * D, lane + l * D * D);
+        mat_mul(D, pt, cur, tmp);
+        memcpy(cur, tmp, sizeof tmp);
+    }
+    fmq_matpow(d, FMQ_TILE, pt);
+    mat_identity(D, cur);
+    for (int l = 0; l < 32; ++l) { /* (A^TILE)^l */
+        to_float(cur, D * D, lane_tile + l * D * D);
         mat_mul(D, pt, cur, tmp);
         memcpy(cur, tmp, sizeof tmp);
     }
@@ -146,6 +155,7 @@ void fmq_build_tables(const fmq_design *d, float *lane, float *apow, float *ck, 
         for (int j = 0; j < D; ++j) {
             ckn[k * D + j] = (float) row[j];
             if (k < FMQ_T) ck[k * D + j] = (float) row[j];
+            if (row[j] >= FMQ_ZIR_EPS || row[j] <= -FMQ_ZIR_EPS || row[j] != row[j]) zir_len = (unsigned) k + 1u;
         }
         for (int j = 0; j < D; ++j) {
             ld acc = 0.0L;
@@ -154,12 +164,13 @@ void fmq_build_tables(const fmq_design *d, float *lane, float *apow, float *ck, 
         }
         memcpy(row, nxt, sizeof row);
     }
+    return zir_len;
 }
 
 /* ---- flat exports for the CPU-side test of the scan algebra (tests/test_quality_tables.py);
  *      not part of include/fmdemod.h ---- */
 
-int fmq_test_sizes(unsigned sections, unsigned *consts_bytes, unsigned sizes[4]) {
+int fmq_test_sizes(unsigned sections, unsigned *consts_bytes, unsigned sizes[5]) {
     fmq_design d;
     memset(&d, 0, sizeof d);
     d.L = (int) sections;
@@ -171,16 +182,18 @@ int fmq_test_sizes(unsigned sections, unsigned *consts_bytes, unsigned sizes[4])
     sizes[1] = sz.apow;
     sizes[2] = sz.ck;
     sizes[3] = sz.ckn;
+    sizes[4] = sz.lane_tile;
     return FMD_OK;
 }
 
-int fmq_test_build(const float *sos6, unsigned sections, fmq_consts *c, float *lane, float *apow, float *ck,
-                   float *ckn, double *abcd /* D*D + D + D + 1 */) {
+int fmq_test_build(const float *sos6, unsigned sections, fmq_consts *c, fmq_consts *c_tile, float *lane, float *apow,
+                   float *ck, float *ckn, float *lane_tile, double *abcd /* D*D + D + D + 1 */, unsigned *zir_len) {
     fmq_design d;
     int rc = fmq_design_from_sos(sos6, sections, &d);
     if (rc) return rc;
-    fmq_build_consts(&d, c);
-    fmq_build_tables(&d, lane, apow, ck, ckn);
+    fmq_build_consts(&d, FMQ_T, c);
+    fmq_build_consts(&d, FMQ_TILE, c_tile);
+    *zir_len = fmq_build_tables(&d, lane, apow, ck, ckn, lane_tile);
     int p = 0;
     for (int i = 0; i < d.D; ++i)
         for (int j = 0; j < d.D; ++j) abcd[p++] = (double) d.A[i][j];

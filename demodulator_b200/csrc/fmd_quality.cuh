@@ -89,16 +89,10 @@ __device__ __forceinline__ unsigned fmq_kept_below(unsigned pos, unsigned r0, un
     return pos <= r0 ? 0u : (pos - r0 + M - 1u) / M;
 }
 
-/*
- * Exclusive affine scan over the threads of a CTA: in  v[nv] = end state of the thread's span run
- * from a zero state; out v[nv] = state at the START of the thread's span, given `carry` = state at
- * the start of the tile.  Every thread of the CTA must call it (one __syncthreads inside).
- */
+/* inclusive affine scan over the lanes of a warp: v_l <- sum_{i<=l} P^(l-i) v_i, with the
+ * matrices c.lvl[j] = P^(2^j) */
 template <int D, int NV>
-__device__ __forceinline__ void fmq_block_scan(float (&v)[NV][D], const fmq_consts &c,
-                                               const float *__restrict__ lane_tab, const float (&carry)[NV][D],
-                                               float *tot /* shared, FMQ_WARPS * NV * D */) {
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void fmq_warp_scan(float (&v)[NV][D], const fmq_consts &c, const unsigned lane) {
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         float up[NV][D];
@@ -118,6 +112,19 @@ __device__ __forceinline__ void fmq_block_scan(float (&v)[NV][D], const fmq_cons
                 }
         }
     }
+}
+
+/*
+ * Exclusive affine scan over the threads of a CTA: in  v[nv] = end state of the thread's span run
+ * from a zero state; out v[nv] = state at the START of the thread's span, given `carry` = state at
+ * the start of the tile.  Every thread of the CTA must call it (one __syncthreads inside).
+ */
+template <int D, int NV>
+__device__ __forceinline__ void fmq_block_scan(float (&v)[NV][D], const fmq_consts &c,
+                                               const float *__restrict__ lane_tab, const float (&carry)[NV][D],
+                                               float *tot /* shared, FMQ_WARPS * NV * D */) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    fmq_warp_scan<D, NV>(v, c, lane);
     if (lane == 31u) {
 #pragma unroll
         for (int a = 0; a < NV; ++a)
@@ -300,8 +307,12 @@ __device__ __forceinline__ void fmq_discriminate2(float pr, float pi, float z0r,
     fmd_atan2_x2<8>(fmd_pk(im0, im1), fmd_pk(re0, re1), x0, x1);
 }
 
+#ifndef FMQ_MINB
+#define FMQ_MINB 2 /* resident CTAs per SM the register budget of the main kernel is cut for */
+#endif
+
 template <int LIN, int LOUT>
-__global__ void __launch_bounds__(FMQ_THREADS, 2)
+__global__ void __launch_bounds__(FMQ_THREADS, FMQ_MINB)
 fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const FmqGeom g, const fmq_consts cin,
                 const fmq_consts cout, const float *__restrict__ lane_in, const float *__restrict__ lane_out,
                 const float *__restrict__ apow_out, const float *__restrict__ ck_out,
@@ -437,14 +448,21 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
 
 /* ------------------------------------------- tile-level zero-input response on the kept samples */
 
+/*
+ * y[o] += C A^k q_tile for the kept samples at tile offsets k < zir_len (beyond that the rows of
+ * C A^k are below FMQ_ZIR_EPS and the host does not even launch threads for them).
+ * Grid: x = tile, y = group of 256 kept samples inside the tile.
+ */
 template <int DO>
 __global__ void __launch_bounds__(256)
-fmq_zir_kernel(float *__restrict__ out, const FmqGeom g, const float *__restrict__ ckn /* [TILE][DO] */,
-               const float *__restrict__ q_tile /* [ntiles][DO] */) {
-    const unsigned o = blockIdx.x * 256u + threadIdx.x;
+fmq_zir_kernel(float *__restrict__ out, const FmqGeom g, const unsigned zir_len,
+               const float *__restrict__ ckn /* [TILE][DO] */, const float *__restrict__ q_tile /* [ntiles][DO] */) {
+    const unsigned tile = blockIdx.x, S = tile * (unsigned) FMQ_TILE;
+    const unsigned o = fmq_kept_below(S, g.r0, g.decim) + blockIdx.y * 256u + threadIdx.x;
     if (o >= g.n_out) return;
     const unsigned long long ks = (unsigned long long) g.r0 + (unsigned long long) o * g.decim;
-    const unsigned tile = (unsigned) (ks / FMQ_TILE), k = (unsigned) (ks % FMQ_TILE);
+    if (ks >= (unsigned long long) S + zir_len || ks >= (unsigned long long) S + FMQ_TILE) return;
+    const unsigned k = (unsigned) (ks - S);
     const float *__restrict__ c = ckn + (size_t) k * DO;
     const float *__restrict__ q = q_tile + (size_t) tile * DO;
     float y = out[o];
@@ -455,245 +473,147 @@ fmq_zir_kernel(float *__restrict__ out, const FmqGeom g, const float *__restrict
 
 /* --------------------------------------------------------- scan of the per-tile end states */
 
-#define FMQ_SCAN_BLOCK 512
-
-template <int D>
-__device__ __forceinline__ void fmq_mm(const float (&x)[D * D], const float (&y)[D * D], float (&o)[D * D]) {
-#pragma unroll
-    for (int i = 0; i < D; ++i)
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-            float acc = 0.0f;
-#pragma unroll
-            for (int k = 0; k < D; ++k) acc = fmaf(x[i * D + k], y[k * D + j], acc);
-            o[i * D + j] = acc;
-        }
-}
-
-/* (M, v) <- (M, v) after (Mu, vu):  v = M vu + v,  M = M Mu   ("u" is the EARLIER map) */
-template <int D, int NV>
-__device__ __forceinline__ void fmq_compose(float (&M)[D * D], float (&v)[NV][D], const float (&Mu)[D * D],
-                                            const float (&vu)[NV][D]) {
-#pragma unroll
-    for (int a = 0; a < NV; ++a)
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-            float acc = v[a][i];
-#pragma unroll
-            for (int k = 0; k < D; ++k) acc = fmaf(M[i * D + k], vu[a][k], acc);
-            v[a][i] = acc;
-        }
-    float t[D * D];
-    fmq_mm<D>(M, Mu, t);
-#pragma unroll
-    for (int i = 0; i < D * D; ++i) M[i] = t[i];
-}
-
-template <int D, int NV>
-__device__ __forceinline__ void fmq_warp_scan_maps(float (&M)[D * D], float (&v)[NV][D], unsigned lane) {
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        float Mu[D * D], vu[NV][D];
-#pragma unroll
-        for (int i = 0; i < D * D; ++i) Mu[i] = __shfl_up_sync(0xffffffffu, M[i], 1u << j);
-#pragma unroll
-        for (int a = 0; a < NV; ++a)
-#pragma unroll
-            for (int i = 0; i < D; ++i) vu[a][i] = __shfl_up_sync(0xffffffffu, v[a][i], 1u << j);
-        if (lane >= (1u << j)) fmq_compose<D, NV>(M, v, Mu, vu);
-    }
-}
-
 /*
- * q[j+1] = P_j q[j] + E[j],  P_j = pn (a full tile) or plast (the ragged last tile);  q[0] = *carry.
- * Writes q[j] (the state at the START of tile j) for every tile and leaves q[ntiles] in *carry.
- * One CTA: a thread takes a run of consecutive tiles, the runs are combined as affine maps.
+ * q[j+1] = P q[j] + E[j] over the tiles of a launch, q[0] = *carry, P = A^TILE.  Writes q[j] (the
+ * state at the START of tile j) for every tile and leaves the state after the last tile in
+ * *carry (its transition is `plast` = A^(samples in the last, possibly ragged, tile)).
+ *
+ * One CTA of 32 warps.  A warp owns a run of `runlen` consecutive tiles (a multiple of 32) and
+ * walks it 32 tiles at a time with the same shuffle scan the CTAs of the main kernel use over
+ * their threads (`ct` and `lane_tile` are the tables for the unit TILE instead of T): once from a
+ * zero state to get the run's end state, then -- after the 32 run states have been chained with
+ * `prun` = P^runlen -- again from the right state, storing.
  * When `last_sample` is given, also records the centred last input sample for the next call.
  */
 template <int D, int NV>
-__global__ void __launch_bounds__(FMQ_SCAN_BLOCK)
-fmq_scan_tiles_kernel(const float *__restrict__ E, float *__restrict__ Q, float *__restrict__ carry, const FmqMat pn,
-                      const FmqMat plast, const unsigned ntiles, const uint8_t *__restrict__ last_sample,
+__global__ void __launch_bounds__(FMQ_SCAN_THREADS)
+fmq_scan_tiles_kernel(const float *__restrict__ E, float *__restrict__ Q, float *__restrict__ carry,
+                      const fmq_consts ct, const float *__restrict__ lane_tile, const FmqMat prun, const FmqMat plast,
+                      const unsigned ntiles, const unsigned runlen, const uint8_t *__restrict__ last_sample,
                       float *__restrict__ s_prev) {
-    __shared__ float wM[16][D * D];
-    __shared__ float wv[16][NV * D];
-    const unsigned t = threadIdx.x, lane = t & 31u, warp = t >> 5;
-    const unsigned R = (ntiles + FMQ_SCAN_BLOCK - 1) / FMQ_SCAN_BLOCK;
-    const unsigned j0 = min(t * R, ntiles), j1 = min(j0 + R, ntiles);
+    __shared__ float run_e[FMQ_SCAN_THREADS / 32][NV * D];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned j0 = min(warp * runlen, ntiles), j1 = min(j0 + runlen, ntiles);
 
-    float c0[NV][D];
+    float c[NV][D]; /* read before any thread may overwrite *carry */
 #pragma unroll
     for (int a = 0; a < NV; ++a)
 #pragma unroll
-        for (int i = 0; i < D; ++i) c0[a][i] = carry[a * D + i];
-    float PN[D * D], PL[D * D];
-#pragma unroll
-    for (int i = 0; i < D * D; ++i) {
-        PN[i] = pn.m[i];
-        PL[i] = plast.m[i];
-    }
+        for (int i = 0; i < D; ++i) c[a][i] = carry[a * D + i];
 
-    /* this thread's run as one affine map (M, v) */
-    float v[NV][D];
+    /* pass 1: end state of the run from a zero state */
+    float cw[NV][D];
 #pragma unroll
     for (int a = 0; a < NV; ++a)
 #pragma unroll
-        for (int i = 0; i < D; ++i) v[a][i] = 0.0f;
-    for (unsigned j = j0; j < j1; ++j) {
-        const bool is_last = j + 1u == ntiles;
-        float nv[NV][D];
+        for (int i = 0; i < D; ++i) cw[a][i] = 0.0f;
+    for (unsigned base = j0; base < j1; base += 32u) {
+        const unsigned j = base + lane;
+        float v[NV][D];
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+            for (int i = 0; i < D; ++i) v[a][i] = j < j1 ? E[((size_t) j * NV + a) * D + i] : 0.0f;
+        fmq_warp_scan<D, NV>(v, ct, lane);
+        float nw[NV][D];
 #pragma unroll
         for (int a = 0; a < NV; ++a)
 #pragma unroll
             for (int i = 0; i < D; ++i) {
-                float acc = E[((size_t) j * NV + a) * D + i];
+                float acc = __shfl_sync(0xffffffffu, v[a][i], 31);
 #pragma unroll
-                for (int k = 0; k < D; ++k) acc = fmaf(is_last ? PL[i * D + k] : PN[i * D + k], v[a][k], acc);
-                nv[a][i] = acc;
+                for (int k = 0; k < D; ++k) acc = fmaf(ct.warp[i * D + k], cw[a][k], acc);
+                nw[a][i] = acc;
             }
 #pragma unroll
         for (int a = 0; a < NV; ++a)
 #pragma unroll
-            for (int i = 0; i < D; ++i) v[a][i] = nv[a][i];
+            for (int i = 0; i < D; ++i) cw[a][i] = nw[a][i];
     }
-    float M[D * D];
-    {
-        /* M = [plast] * pn^(full tiles of the run), by binary powering */
-        const bool has_last = j1 == ntiles && j1 > j0;
-        unsigned e = (j1 - j0) - (has_last ? 1u : 0u);
-        float base[D * D], tmp[D * D];
-#pragma unroll
-        for (int i = 0; i < D * D; ++i) {
-            M[i] = (i / D == i % D) ? 1.0f : 0.0f;
-            base[i] = PN[i];
-        }
-        while (e) {
-            if (e & 1u) {
-                fmq_mm<D>(base, M, tmp);
-#pragma unroll
-                for (int i = 0; i < D * D; ++i) M[i] = tmp[i];
-            }
-            fmq_mm<D>(base, base, tmp);
-#pragma unroll
-            for (int i = 0; i < D * D; ++i) base[i] = tmp[i];
-            e >>= 1;
-        }
-        if (has_last) {
-            fmq_mm<D>(PL, M, tmp);
-#pragma unroll
-            for (int i = 0; i < D * D; ++i) M[i] = tmp[i];
-        }
-    }
-
-    /* exclusive scan of the maps over the CTA */
-    fmq_warp_scan_maps<D, NV>(M, v, lane);
-    if (lane == 31u) {
-#pragma unroll
-        for (int i = 0; i < D * D; ++i) wM[warp][i] = M[i];
+    if (lane == 0u) {
 #pragma unroll
         for (int a = 0; a < NV; ++a)
 #pragma unroll
-            for (int i = 0; i < D; ++i) wv[warp][a * D + i] = v[a][i];
+            for (int i = 0; i < D; ++i) run_e[warp][a * D + i] = cw[a][i];
     }
     __syncthreads();
-    if (warp == 0) {
-        float tM[D * D], tv[NV][D];
-        const bool have = lane < FMQ_SCAN_BLOCK / 32;
-#pragma unroll
-        for (int i = 0; i < D * D; ++i) tM[i] = have ? wM[lane & 15u][i] : ((i / D == i % D) ? 1.0f : 0.0f);
-#pragma unroll
-        for (int a = 0; a < NV; ++a)
-#pragma unroll
-            for (int i = 0; i < D; ++i) tv[a][i] = have ? wv[lane & 15u][a * D + i] : 0.0f;
-        fmq_warp_scan_maps<D, NV>(tM, tv, lane);
-        /* exclusive: the map of all warps BEFORE warp `lane` */
-#pragma unroll
-        for (int i = 0; i < D * D; ++i) {
-            const float u = __shfl_up_sync(0xffffffffu, tM[i], 1u);
-            tM[i] = lane ? u : ((i / D == i % D) ? 1.0f : 0.0f);
-        }
+    /* state at the start of this warp's run (runs before it are full: runlen tiles each) */
+    for (unsigned w = 0; w < warp; ++w) {
+        float nw[NV][D];
 #pragma unroll
         for (int a = 0; a < NV; ++a)
 #pragma unroll
             for (int i = 0; i < D; ++i) {
-                const float u = __shfl_up_sync(0xffffffffu, tv[a][i], 1u);
-                tv[a][i] = lane ? u : 0.0f;
-            }
-        __syncwarp();
-        if (have) {
+                float acc = run_e[w][a * D + i];
 #pragma unroll
-            for (int i = 0; i < D * D; ++i) wM[lane][i] = tM[i];
+                for (int k = 0; k < D; ++k) acc = fmaf(prun.m[i * D + k], c[a][k], acc);
+                nw[a][i] = acc;
+            }
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+            for (int i = 0; i < D; ++i) c[a][i] = nw[a][i];
+    }
+    /* pass 2: the same walk from the right state, storing the state at the start of every tile */
+    float lp[D * D];
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) lp[i] = __ldg(lane_tile + lane * (D * D) + i);
+    for (unsigned base = j0; base < j1; base += 32u) {
+        const unsigned j = base + lane;
+        float e[NV][D], v[NV][D];
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+            for (int i = 0; i < D; ++i) v[a][i] = e[a][i] = j < j1 ? E[((size_t) j * NV + a) * D + i] : 0.0f;
+        fmq_warp_scan<D, NV>(v, ct, lane);
+        float q[NV][D];
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                const float t = __shfl_up_sync(0xffffffffu, v[a][i], 1u);
+                float acc = lane ? t : 0.0f;
+#pragma unroll
+                for (int k = 0; k < D; ++k) acc = fmaf(lp[i * D + k], c[a][k], acc);
+                q[a][i] = acc;
+            }
+        if (j < j1) {
 #pragma unroll
             for (int a = 0; a < NV; ++a)
 #pragma unroll
-                for (int i = 0; i < D; ++i) wv[lane][a * D + i] = tv[a][i];
+                for (int i = 0; i < D; ++i) Q[((size_t) j * NV + a) * D + i] = q[a][i];
+            if (j + 1u == ntiles) { /* the state after the last tile: the carry for the next call */
+#pragma unroll
+                for (int a = 0; a < NV; ++a)
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+                        float acc = e[a][i];
+#pragma unroll
+                        for (int k = 0; k < D; ++k) acc = fmaf(plast.m[i * D + k], q[a][k], acc);
+                        carry[a * D + i] = acc;
+                    }
+                if (last_sample) {
+                    float si, sq;
+                    fmq_load_sample(last_sample, 0u, si, sq);
+                    s_prev[0] = si;
+                    s_prev[1] = sq;
+                }
+            }
         }
-    }
-    __syncthreads();
-    /* the map of everything before this thread = (lanes before it in its warp) after (warps before) */
-    float eM[D * D], ev[NV][D];
-#pragma unroll
-    for (int i = 0; i < D * D; ++i) {
-        const float u = __shfl_up_sync(0xffffffffu, M[i], 1u);
-        eM[i] = lane ? u : ((i / D == i % D) ? 1.0f : 0.0f);
-    }
-#pragma unroll
-    for (int a = 0; a < NV; ++a)
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-            const float u = __shfl_up_sync(0xffffffffu, v[a][i], 1u);
-            ev[a][i] = lane ? u : 0.0f;
-        }
-    {
-        float bM[D * D], bv[NV][D];
-#pragma unroll
-        for (int i = 0; i < D * D; ++i) bM[i] = wM[warp][i];
-#pragma unroll
-        for (int a = 0; a < NV; ++a)
-#pragma unroll
-            for (int i = 0; i < D; ++i) bv[a][i] = wv[warp][a * D + i];
-        fmq_compose<D, NV>(eM, ev, bM, bv);
-    }
-    /* state at the start of this thread's run, then walk the run */
-    float q[NV][D];
-#pragma unroll
-    for (int a = 0; a < NV; ++a)
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-            float acc = ev[a][i];
-#pragma unroll
-            for (int k = 0; k < D; ++k) acc = fmaf(eM[i * D + k], c0[a][k], acc);
-            q[a][i] = acc;
-        }
-    for (unsigned j = j0; j < j1; ++j) {
-        const bool is_last = j + 1u == ntiles;
-        float nq[NV][D];
+        float nw[NV][D];
 #pragma unroll
         for (int a = 0; a < NV; ++a)
 #pragma unroll
             for (int i = 0; i < D; ++i) {
-                Q[((size_t) j * NV + a) * D + i] = q[a][i];
-                float acc = E[((size_t) j * NV + a) * D + i];
+                float acc = __shfl_sync(0xffffffffu, v[a][i], 31);
 #pragma unroll
-                for (int k = 0; k < D; ++k) acc = fmaf(is_last ? PL[i * D + k] : PN[i * D + k], q[a][k], acc);
-                nq[a][i] = acc;
+                for (int k = 0; k < D; ++k) acc = fmaf(ct.warp[i * D + k], c[a][k], acc);
+                nw[a][i] = acc;
             }
 #pragma unroll
         for (int a = 0; a < NV; ++a)
 #pragma unroll
-            for (int i = 0; i < D; ++i) q[a][i] = nq[a][i];
-    }
-    if (j1 == ntiles && j1 > j0) {
-#pragma unroll
-        for (int a = 0; a < NV; ++a)
-#pragma unroll
-            for (int i = 0; i < D; ++i) carry[a * D + i] = q[a][i];
-        if (last_sample) {
-            float si, sq;
-            fmq_load_sample(last_sample, 0u, si, sq);
-            s_prev[0] = si;
-            s_prev[1] = sq;
-        }
+            for (int i = 0; i < D; ++i) c[a][i] = nw[a][i];
     }
 }
 

@@ -31,6 +31,7 @@ extern "C" {
 #define FMQ_MAXL 3                        /* sections per cascade: degree <= 6                */
 #define FMQ_MAXD (2 * FMQ_MAXL)
 #define FMQ_SCAN_THREADS 1024             /* the tile-carry scan is one CTA of this size      */
+#define FMQ_ZIR_EPS 1.0e-15L              /* rows of C A^k below this are not applied at all   */
 
 /* per-filter constants that travel as kernel parameters (constant bank); matrices are packed
  * row-major D x D for the filter's own D */
@@ -41,6 +42,8 @@ typedef struct fmq_consts {
     float warp[FMQ_MAXD * FMQ_MAXD];        /* A^(32 T): from one warp to the next            */
     float tile[FMQ_MAXD * FMQ_MAXD];        /* A^TILE: from one tile to the next              */
 } fmq_consts;
+/* The same struct describes the scan over TILES (fmq_scan_tiles_kernel): built with unit = TILE,
+ * lvl[j] = A^(TILE 2^j), warp = A^(32 TILE), tile = A^TILE. */
 
 /* per-filter tables in device global memory (floats), one allocation laid out in this order */
 typedef struct fmq_table_sizes {
@@ -48,6 +51,7 @@ typedef struct fmq_table_sizes {
     unsigned apow;   /* [T+1][D*D]     A^k, k = 0..T                                         */
     unsigned ck;     /* [T][D]         C A^k: zero-input response seen at offset k of a thread */
     unsigned ckn;    /* [TILE][D]      C A^k: the same for a whole tile                       */
+    unsigned lane_tile; /* [32][D*D]   (A^TILE)^l: the lane table of the scan over tiles      */
 } fmq_table_sizes;
 
 typedef struct fmq_design {
@@ -60,10 +64,13 @@ typedef struct fmq_design {
 int fmq_design_from_sos(const float *sos6, unsigned sections, fmq_design *d);
 /* out = A^k, packed row-major D x D */
 void fmq_matpow(const fmq_design *d, unsigned long long k, long double *out);
-void fmq_build_consts(const fmq_design *d, fmq_consts *c);
+/* unit = FMQ_T for the scan over threads, FMQ_TILE for the scan over tiles */
+void fmq_build_consts(const fmq_design *d, unsigned unit, fmq_consts *c);
 void fmq_table_layout(const fmq_design *d, fmq_table_sizes *sz);
-/* fills the four tables (sizes from fmq_table_layout) */
-void fmq_build_tables(const fmq_design *d, float *lane, float *apow, float *ck, float *ckn);
+/* fills the tables (sizes from fmq_table_layout); returns the number of leading rows of ckn that
+ * are not negligible (|C A^k| >= FMQ_ZIR_EPS somewhere in the row): the tile-level zero-input
+ * response is applied to those offsets only */
+unsigned fmq_build_tables(const fmq_design *d, float *lane, float *apow, float *ck, float *ckn, float *lane_tile);
 /* float copy of A^k for the launch-dependent transition of a ragged last tile */
 void fmq_matpow_f(const fmq_design *d, unsigned long long k, float *out);
 

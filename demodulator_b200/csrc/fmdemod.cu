@@ -63,13 +63,16 @@ struct fmd_slot {
 /* one cascade of the quality pipeline: host design + constants + device tables */
 struct fmq_filter {
     fmq_design des;
-    fmq_consts c;
+    fmq_consts c;      /* scan over the threads of a CTA (unit T)   */
+    fmq_consts c_tile; /* scan over the tiles of a launch (unit TILE) */
     fmq_table_sizes sz;
-    float *d_tab = nullptr; /* lane | apow | ck | ckn */
+    unsigned zir_len = FMQ_TILE; /* tile offsets whose zero-input response is not negligible */
+    float *d_tab = nullptr; /* lane | apow | ck | ckn | lane_tile */
     const float *lane() const { return d_tab; }
     const float *apow() const { return d_tab + sz.lane; }
     const float *ck() const { return d_tab + sz.lane + sz.apow; }
     const float *ckn() const { return d_tab + sz.lane + sz.apow + sz.ck; }
+    const float *lane_tile() const { return d_tab + sz.lane + sz.apow + sz.ck + sz.ckn; }
 };
 
 /* FMD_FLAG_QUALITY state of a context (fmd_quality.cuh) */
@@ -525,12 +528,14 @@ static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned
 static int quality_upload_filter(fmq_filter &f, const float *sos6, unsigned sections) {
     int rc = fmq_design_from_sos(sos6, sections, &f.des);
     if (rc) return rc;
-    fmq_build_consts(&f.des, &f.c);
+    fmq_build_consts(&f.des, FMQ_T, &f.c);
+    fmq_build_consts(&f.des, FMQ_TILE, &f.c_tile);
     fmq_table_layout(&f.des, &f.sz);
-    const size_t n = (size_t) f.sz.lane + f.sz.apow + f.sz.ck + f.sz.ckn;
+    const size_t n = (size_t) f.sz.lane + f.sz.apow + f.sz.ck + f.sz.ckn + f.sz.lane_tile;
     float *h = (float *) malloc(n * sizeof(float));
     if (!h) return fmd_set_error(FMD_ENOMEM, "out of host memory");
-    fmq_build_tables(&f.des, h, h + f.sz.lane, h + f.sz.lane + f.sz.apow, h + f.sz.lane + f.sz.apow + f.sz.ck);
+    f.zir_len = fmq_build_tables(&f.des, h, h + f.sz.lane, h + f.sz.lane + f.sz.apow, h + f.sz.lane + f.sz.apow + f.sz.ck,
+                                 h + f.sz.lane + f.sz.apow + f.sz.ck + f.sz.ckn);
     cudaError_t e = cudaMalloc(&f.d_tab, n * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(f.d_tab, h, n * sizeof(float), cudaMemcpyHostToDevice);
     free(h);
@@ -628,25 +633,29 @@ static int quality_launch(fmd_ctx *c, const uint8_t *d_in, unsigned n, float *d_
     int rc = quality_reserve_tiles(q, g.ntiles);
     if (rc) return rc;
     const unsigned len_last = n - (g.ntiles - 1u) * FMQ_TILE;
-    FmqMat pn, pl;
+    /* the scan over tiles: 32 warps, each a run of `runlen` tiles (a multiple of 32) */
+    const unsigned nwarps = FMQ_SCAN_THREADS / 32;
+    const unsigned runlen = ((g.ntiles + nwarps - 1u) / nwarps + 31u) & ~31u;
+    FmqMat prun, pl;
 
     if (q->lin) {
-        memset(&pn, 0, sizeof pn);
+        memset(&prun, 0, sizeof prun);
         memset(&pl, 0, sizeof pl);
-        memcpy(pn.m, q->fin.c.tile, sizeof pn.m);
+        fmq_matpow_f(&q->fin.des, (unsigned long long) FMQ_TILE * runlen, prun.m);
         fmq_matpow_f(&q->fin.des, len_last, pl.m);
+        float *cin = &q->d_state->in_q[0][0];
         switch (q->lin) {
             case 1:
                 fmq_in_aggregate_kernel<1><<<g.ntiles, FMQ_THREADS, 0, s>>>(d_in, g, q->fin.c, q->fin.lane(), q->fin.apow(), q->d_state, q->d_ein);
-                fmq_scan_tiles_kernel<2, 2><<<1, FMQ_SCAN_BLOCK, 0, s>>>(q->d_ein, q->d_qin, &q->d_state->in_q[0][0], pn, pl, g.ntiles, nullptr, nullptr);
+                fmq_scan_tiles_kernel<2, 2><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_ein, q->d_qin, cin, q->fin.c_tile, q->fin.lane_tile(), prun, pl, g.ntiles, runlen, nullptr, nullptr);
                 break;
             case 2:
                 fmq_in_aggregate_kernel<2><<<g.ntiles, FMQ_THREADS, 0, s>>>(d_in, g, q->fin.c, q->fin.lane(), q->fin.apow(), q->d_state, q->d_ein);
-                fmq_scan_tiles_kernel<4, 2><<<1, FMQ_SCAN_BLOCK, 0, s>>>(q->d_ein, q->d_qin, &q->d_state->in_q[0][0], pn, pl, g.ntiles, nullptr, nullptr);
+                fmq_scan_tiles_kernel<4, 2><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_ein, q->d_qin, cin, q->fin.c_tile, q->fin.lane_tile(), prun, pl, g.ntiles, runlen, nullptr, nullptr);
                 break;
             default:
                 fmq_in_aggregate_kernel<3><<<g.ntiles, FMQ_THREADS, 0, s>>>(d_in, g, q->fin.c, q->fin.lane(), q->fin.apow(), q->d_state, q->d_ein);
-                fmq_scan_tiles_kernel<6, 2><<<1, FMQ_SCAN_BLOCK, 0, s>>>(q->d_ein, q->d_qin, &q->d_state->in_q[0][0], pn, pl, g.ntiles, nullptr, nullptr);
+                fmq_scan_tiles_kernel<6, 2><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_ein, q->d_qin, cin, q->fin.c_tile, q->fin.lane_tile(), prun, pl, g.ntiles, runlen, nullptr, nullptr);
                 break;
         }
         FMD_CUDA(cudaGetLastError());
@@ -673,23 +682,26 @@ static int quality_launch(fmd_ctx *c, const uint8_t *d_in, unsigned n, float *d_
     FMD_CUDA(cudaGetLastError());
     if (pe) FMD_CUDA(cudaEventRecord(pe[1], s));
 
-    memset(&pn, 0, sizeof pn);
+    memset(&prun, 0, sizeof prun);
     memset(&pl, 0, sizeof pl);
-    memcpy(pn.m, q->fout.c.tile, sizeof pn.m);
+    fmq_matpow_f(&q->fout.des, (unsigned long long) FMQ_TILE * runlen, prun.m);
     fmq_matpow_f(&q->fout.des, len_last, pl.m);
     const uint8_t *last = d_in + 2ull * (n - 1u);
+    /* zero-input response of the tile carry: only the leading zir_len offsets of every tile */
+    const unsigned zl = q->fout.zir_len < FMQ_TILE ? q->fout.zir_len : FMQ_TILE;
+    const dim3 zgrid(g.ntiles, (zl / q->decim + 1u + 255u) / 256u);
     switch (q->lout) {
         case 1:
-            fmq_scan_tiles_kernel<2, 1><<<1, FMQ_SCAN_BLOCK, 0, s>>>(q->d_eout, q->d_qout, q->d_state->out_q, pn, pl, g.ntiles, last, q->d_state->s_prev);
-            if (g.n_out) fmq_zir_kernel<2><<<(g.n_out + 255u) / 256u, 256, 0, s>>>(d_out, g, q->fout.ckn(), q->d_qout);
+            fmq_scan_tiles_kernel<2, 1><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_eout, q->d_qout, q->d_state->out_q, q->fout.c_tile, q->fout.lane_tile(), prun, pl, g.ntiles, runlen, last, q->d_state->s_prev);
+            if (g.n_out) fmq_zir_kernel<2><<<zgrid, 256, 0, s>>>(d_out, g, zl, q->fout.ckn(), q->d_qout);
             break;
         case 2:
-            fmq_scan_tiles_kernel<4, 1><<<1, FMQ_SCAN_BLOCK, 0, s>>>(q->d_eout, q->d_qout, q->d_state->out_q, pn, pl, g.ntiles, last, q->d_state->s_prev);
-            if (g.n_out) fmq_zir_kernel<4><<<(g.n_out + 255u) / 256u, 256, 0, s>>>(d_out, g, q->fout.ckn(), q->d_qout);
+            fmq_scan_tiles_kernel<4, 1><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_eout, q->d_qout, q->d_state->out_q, q->fout.c_tile, q->fout.lane_tile(), prun, pl, g.ntiles, runlen, last, q->d_state->s_prev);
+            if (g.n_out) fmq_zir_kernel<4><<<zgrid, 256, 0, s>>>(d_out, g, zl, q->fout.ckn(), q->d_qout);
             break;
         default:
-            fmq_scan_tiles_kernel<6, 1><<<1, FMQ_SCAN_BLOCK, 0, s>>>(q->d_eout, q->d_qout, q->d_state->out_q, pn, pl, g.ntiles, last, q->d_state->s_prev);
-            if (g.n_out) fmq_zir_kernel<6><<<(g.n_out + 255u) / 256u, 256, 0, s>>>(d_out, g, q->fout.ckn(), q->d_qout);
+            fmq_scan_tiles_kernel<6, 1><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_eout, q->d_qout, q->d_state->out_q, q->fout.c_tile, q->fout.lane_tile(), prun, pl, g.ntiles, runlen, last, q->d_state->s_prev);
+            if (g.n_out) fmq_zir_kernel<6><<<zgrid, 256, 0, s>>>(d_out, g, zl, q->fout.ckn(), q->d_qout);
             break;
     }
     FMD_CUDA(cudaGetLastError());

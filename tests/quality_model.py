@@ -26,21 +26,29 @@ class Filter:
         L = sos.shape[0]
         D = 2 * L
         nbytes = C.c_uint(0)
-        sizes = (C.c_uint * 4)()
+        sizes = (C.c_uint * 5)()
         lib.fmq_test_sizes.argtypes = [C.c_uint, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
-        lib.fmq_test_build.argtypes = [C.c_void_p, C.c_uint, C.POINTER(_Consts)] + [C.c_void_p] * 5
+        lib.fmq_test_build.argtypes = ([C.c_void_p, C.c_uint, C.POINTER(_Consts), C.POINTER(_Consts)] +
+                                       [C.c_void_p] * 6 + [C.POINTER(C.c_uint)])
         lib.fmq_test_sizes(L, C.byref(nbytes), sizes)
         assert nbytes.value == C.sizeof(_Consts), (nbytes.value, C.sizeof(_Consts))
-        self.c = _Consts()
+        self.c, self.ct = _Consts(), _Consts()
         lane = np.zeros(sizes[0], np.float32)
         apow = np.zeros(sizes[1], np.float32)
         ck = np.zeros(sizes[2], np.float32)
         ckn = np.zeros(sizes[3], np.float32)
+        lane_tile = np.zeros(sizes[4], np.float32)
         abcd = np.zeros(D * D + 2 * D + 1, np.float64)
-        rc = lib.fmq_test_build(sos.ctypes.data, L, C.byref(self.c), lane.ctypes.data, apow.ctypes.data,
-                                ck.ctypes.data, ckn.ctypes.data, abcd.ctypes.data)
+        zl = C.c_uint(0)
+        rc = lib.fmq_test_build(sos.ctypes.data, L, C.byref(self.c), C.byref(self.ct), lane.ctypes.data,
+                                apow.ctypes.data, ck.ctypes.data, ckn.ctypes.data, lane_tile.ctypes.data,
+                                abcd.ctypes.data, C.byref(zl))
         assert rc == 0
+        self.zir_len = int(zl.value)
         self.L, self.D = L, D
+        self.lvl_tile = [np.array(self.ct.lvl[j], np.float64)[:D * D].reshape(D, D) for j in range(5)]
+        self.warp_tile = np.array(self.ct.warp, np.float64)[:D * D].reshape(D, D)
+        self.lane_tile = lane_tile.astype(np.float64).reshape(32, D, D)
         self.sos = np.array(self.c.sos, np.float64)[:L]  # b0 b1 b2 a1 a2
         self.lvl = [np.array(self.c.lvl[j], np.float64)[:D * D].reshape(D, D) for j in range(5)]
         self.warp = np.array(self.c.warp, np.float64)[:D * D].reshape(D, D)
@@ -88,15 +96,56 @@ def block_scan(f: Filter, e: np.ndarray, carry: np.ndarray) -> np.ndarray:
     return ex.reshape(nt, THREADS, f.D)
 
 
-def scan_tiles(E: np.ndarray, carry: np.ndarray, pn: np.ndarray, plast: np.ndarray):
-    """serial statement of fmq_scan_tiles_kernel: returns (state at the start of every tile, carry out)"""
-    nt = E.shape[0]
+def warp_scan(lvl, v: np.ndarray) -> np.ndarray:
+    """fmq_warp_scan over axis 0 (32 lanes) of v[32, D]"""
+    v = v.copy()
+    for j in range(5):
+        off = 1 << j
+        up = np.zeros_like(v)
+        up[off:] = v[:-off]
+        add = up @ lvl[j].T
+        add[:off] = 0.0
+        v = v + add
+    return v
+
+
+def scan_tiles(f: "Filter", E: np.ndarray, carry: np.ndarray, len_last: int):
+    """fmq_scan_tiles_kernel: 32 warps, each a run of `runlen` tiles walked 32 tiles at a time with
+    the tile-level tables; returns (state at the start of every tile, carry out)"""
+    nt, D = E.shape
+    nwarps = 32
+    runlen = ((nt + nwarps - 1) // nwarps + 31) & ~31
+    prun = f.matpow(TILE * runlen)
+    plast = f.matpow(len_last)
+    runs = [(min(w * runlen, nt), min(min(w * runlen, nt) + runlen, nt)) for w in range(nwarps)]
+    run_e = np.zeros((nwarps, D))
+    for w, (j0, j1) in enumerate(runs):
+        cw = np.zeros(D)
+        for base in range(j0, j1, 32):
+            v = np.zeros((32, D))
+            m = min(32, j1 - base)
+            v[:m] = E[base:base + m]
+            cw = f.warp_tile @ cw + warp_scan(f.lvl_tile, v)[31]
+        run_e[w] = cw
     Q = np.zeros_like(E)
-    q = carry.copy()
-    for j in range(nt):
-        Q[j] = q
-        q = (plast if j == nt - 1 else pn) @ q + E[j]
-    return Q, q
+    out = carry.copy()
+    for w, (j0, j1) in enumerate(runs):
+        c = carry.copy()
+        for w2 in range(w):
+            c = prun @ c + run_e[w2]
+        for base in range(j0, j1, 32):
+            v = np.zeros((32, D))
+            m = min(32, j1 - base)
+            v[:m] = E[base:base + m]
+            inc = warp_scan(f.lvl_tile, v)
+            ex = np.zeros((32, D))
+            ex[1:] = inc[:-1]
+            q = ex + np.einsum("lik,k->li", f.lane_tile, c)
+            Q[base:base + m] = q[:m]
+            if base + m == nt:
+                out = plast @ q[m - 1] + E[nt - 1]
+            c = f.warp_tile @ c + inc[31]
+    return Q, out
 
 
 def kept_below(pos, r0, M):
@@ -151,10 +200,9 @@ class Stream:
                 idx = np.nonzero(last)[0]
                 for t in idx:
                     Ein[t // THREADS, lanei] = f.apow[cnt[t]] @ ex[t] + e[lanei][t]
-            plast = f.matpow(len_last)
             Qin = np.zeros_like(Ein)
             for lanei in range(2):
-                Qin[:, lanei], self.in_q[lanei] = scan_tiles(Ein[:, lanei], self.in_q[lanei], f.tile, plast)
+                Qin[:, lanei], self.in_q[lanei] = scan_tiles(f, Ein[:, lanei], self.in_q[lanei], len_last)
             # main kernel, input part: state at F-1 of every thread
             qi = np.zeros((2, nthr, f.D))
             for lanei in range(2):
@@ -195,8 +243,9 @@ class Stream:
         thr, k = ks // T, ks % T
         out = vz[thr, k] + np.einsum("oi,oi->o", fo.ck[k], qo[thr])
         # tile scan + tile-level correction
-        Qout, self.out_q = scan_tiles(Eout, self.out_q, fo.tile, fo.matpow(len_last))
-        out = out + np.einsum("oi,oi->o", fo.ckn[ks % TILE], Qout[ks // TILE])
+        Qout, self.out_q = scan_tiles(fo, Eout, self.out_q, len_last)
+        zir = np.einsum("oi,oi->o", fo.ckn[ks % TILE], Qout[ks // TILE])
+        out = out + np.where(ks % TILE < fo.zir_len, zir, 0.0)  # fmq_zir_kernel stops at zir_len
         self.s_prev = s[n - 1].copy()
         self.pos += n
         return out.astype(np.float32)
