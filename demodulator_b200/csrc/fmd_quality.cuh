@@ -190,21 +190,19 @@ __device__ __forceinline__ void fmq_span_end(const float *__restrict__ apow, uns
     }
 }
 
-/* the thread's 64 input bytes (full spans only) */
-__device__ __forceinline__ void fmq_load_span(const uint8_t *__restrict__ in, unsigned F, uint32_t (&w)[FMQ_T / 2]) {
-    const uint4 *__restrict__ p = reinterpret_cast<const uint4 *>(in + 2ull * F);
-#pragma unroll
-    for (int i = 0; i < FMQ_T / 8; ++i) {
-        const uint4 v = __ldg(p + i);
-        w[4 * i] = v.x;
-        w[4 * i + 1] = v.y;
-        w[4 * i + 2] = v.z;
-        w[4 * i + 3] = v.w;
-    }
+/* Full spans are walked in FMQ_T / 8 groups of 8 samples (one 16-byte load each); only the body of
+ * a group is unrolled, so the instruction footprint stays a quarter of the fully unrolled span
+ * (the fully unrolled <2,2> kernel stalled mostly on instruction fetch: ncu `no_instruction`). */
+#define FMQ_GROUPS (FMQ_T / 8)
+
+__device__ __forceinline__ uint4 fmq_load_group(const uint8_t *__restrict__ in, unsigned F, int grp) {
+    return __ldg(reinterpret_cast<const uint4 *>(in + 2ull * F) + grp);
 }
 
-#define FMQ_SI(w, i) (((i) & 1) ? fmq_centre<2>((w)[(i) >> 1]) : fmq_centre<0>((w)[(i) >> 1]))
-#define FMQ_SQ(w, i) (((i) & 1) ? fmq_centre<3>((w)[(i) >> 1]) : fmq_centre<1>((w)[(i) >> 1]))
+/* sample i (0..7) of a group: compile-time i */
+#define FMQ_GW(v, i) ((i) < 2 ? (v).x : (i) < 4 ? (v).y : (i) < 6 ? (v).z : (v).w)
+#define FMQ_SI(v, i) (((i) & 1) ? fmq_centre<2>(FMQ_GW(v, i)) : fmq_centre<0>(FMQ_GW(v, i)))
+#define FMQ_SQ(v, i) (((i) & 1) ? fmq_centre<3>(FMQ_GW(v, i)) : fmq_centre<1>(FMQ_GW(v, i)))
 
 /*
  * Input cascade from a zero state over the thread's SHIFTED span: the halo sample (F-1), then
@@ -212,17 +210,26 @@ __device__ __forceinline__ void fmq_load_span(const uint8_t *__restrict__ in, un
  */
 template <int LIN>
 __device__ __forceinline__ void fmq_in_zero_state(const fmq_consts &cin, const uint8_t *__restrict__ in, unsigned F,
-                                                  unsigned cnt, const uint32_t (&w)[FMQ_T / 2], float hi, float hq,
-                                                  float (&e)[2][2 * LIN]) {
+                                                  unsigned cnt, float hi, float hq, float (&e)[2][2 * LIN]) {
 #pragma unroll
     for (int i = 0; i < 2 * LIN; ++i) e[0][i] = e[1][i] = 0.0f;
     if (cnt == FMQ_T) {
         fmq_step<LIN>(cin, e[0], hi);
         fmq_step<LIN>(cin, e[1], hq);
+        uint4 nx = fmq_load_group(in, F, 0);
+#pragma unroll 1
+        for (int grp = 0; grp < FMQ_GROUPS; ++grp) {
+            const uint4 v = nx;
+            if (grp + 1 < FMQ_GROUPS) nx = fmq_load_group(in, F, grp + 1);
 #pragma unroll
-        for (int i = 0; i < FMQ_T - 1; ++i) {
-            fmq_step<LIN>(cin, e[0], FMQ_SI(w, i));
-            fmq_step<LIN>(cin, e[1], FMQ_SQ(w, i));
+            for (int i = 0; i < 7; ++i) {
+                fmq_step<LIN>(cin, e[0], FMQ_SI(v, i));
+                fmq_step<LIN>(cin, e[1], FMQ_SQ(v, i));
+            }
+            if (grp + 1 < FMQ_GROUPS) { /* the span's very last sample belongs to the next thread's span */
+                fmq_step<LIN>(cin, e[0], FMQ_SI(v, 7));
+                fmq_step<LIN>(cin, e[1], FMQ_SQ(v, 7));
+            }
         }
     } else if (cnt) {
         fmq_step<LIN>(cin, e[0], hi);
@@ -274,12 +281,10 @@ fmq_in_aggregate_kernel(const uint8_t *__restrict__ in, const FmqGeom g, const f
     constexpr int D = 2 * LIN;
     __shared__ float tot[FMQ_WARPS * 2 * D];
     const FmqSpan sp = fmq_span(g);
-    uint32_t w[FMQ_T / 2];
-    if (sp.cnt == FMQ_T) fmq_load_span(in, sp.F, w);
     float hi, hq;
     fmq_halo(in, st, sp.F, sp.cnt, hi, hq);
     float e[2][D], q[2][D];
-    fmq_in_zero_state<LIN>(cin, in, sp.F, sp.cnt, w, hi, hq, e);
+    fmq_in_zero_state<LIN>(cin, in, sp.F, sp.cnt, hi, hq, e);
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -308,7 +313,7 @@ __device__ __forceinline__ void fmq_discriminate2(float pr, float pi, float z0r,
 }
 
 #ifndef FMQ_MINB
-#define FMQ_MINB 2 /* resident CTAs per SM the register budget of the main kernel is cut for */
+#define FMQ_MINB 4 /* resident CTAs per SM the register budget of the main kernel is cut for */
 #endif
 
 template <int LIN, int LOUT>
@@ -329,9 +334,7 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     const FmqSpan sp = fmq_span(g);
     for (unsigned i = threadIdx.x; i < FMQ_T * DO; i += FMQ_THREADS) ck[i] = __ldg(ck_out + i);
 
-    uint32_t w[FMQ_T / 2];
     const bool full = sp.cnt == FMQ_T;
-    if (full) fmq_load_span(in, sp.F, w);
     float hi, hq;
     fmq_halo(in, st, sp.F, sp.cnt, hi, hq);
 
@@ -339,7 +342,7 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     float qi[2][DI];
     if (LIN > 0) {
         float e[2][DI];
-        fmq_in_zero_state<(LIN > 0 ? LIN : 1)>(cin, in, sp.F, sp.cnt, w, hi, hq, e);
+        fmq_in_zero_state<(LIN > 0 ? LIN : 1)>(cin, in, sp.F, sp.cnt, hi, hq, e);
         float carry[2][DI];
         const float *__restrict__ src = qin_tile + (size_t) blockIdx.x * 2 * DI;
 #pragma unroll
@@ -376,28 +379,38 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     for (int i = 0; i < DO; ++i) eo[i] = 0.0f;
 
     if (full) {
+        /* measured on B200: without the input cascade the fully unrolled span is 8 % faster (more
+         * freedom for the scheduler); with it the rolled form is 4 % faster (instruction fetch) */
+        constexpr int UNR = LIN > 0 ? 1 : FMQ_GROUPS;
+        uint4 nx = fmq_load_group(in, sp.F, 0);
+#pragma unroll(UNR)
+        for (int grp = 0; grp < FMQ_GROUPS; ++grp) {
+            const uint4 v = nx;
+            if (grp + 1 < FMQ_GROUPS) nx = fmq_load_group(in, sp.F, grp + 1);
+            const unsigned i0 = 8u * (unsigned) grp;
 #pragma unroll
-        for (int i = 0; i < FMQ_T; i += 2) {
-            float z0r = FMQ_SI(w, i), z0i = FMQ_SQ(w, i), z1r = FMQ_SI(w, i + 1), z1i = FMQ_SQ(w, i + 1);
-            if (LIN > 0) {
-                z0r = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[0], z0r);
-                z0i = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[1], z0i);
-                z1r = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[0], z1r);
-                z1i = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[1], z1i);
-            }
-            float x0, x1;
-            fmq_discriminate2(pr, pi, z0r, z0i, z1r, z1i, x0, x1);
-            pr = z1r;
-            pi = z1i;
-            const float v0 = fmq_step<LOUT>(cout, eo, x0);
-            if ((unsigned) i == next) {
-                ybuf[slot++] = v0;
-                next += g.decim;
-            }
-            const float v1 = fmq_step<LOUT>(cout, eo, x1);
-            if ((unsigned) (i + 1) == next) {
-                ybuf[slot++] = v1;
-                next += g.decim;
+            for (int i = 0; i < 8; i += 2) {
+                float z0r = FMQ_SI(v, i), z0i = FMQ_SQ(v, i), z1r = FMQ_SI(v, i + 1), z1i = FMQ_SQ(v, i + 1);
+                if (LIN > 0) {
+                    z0r = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[0], z0r);
+                    z0i = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[1], z0i);
+                    z1r = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[0], z1r);
+                    z1i = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[1], z1i);
+                }
+                float x0, x1;
+                fmq_discriminate2(pr, pi, z0r, z0i, z1r, z1i, x0, x1);
+                pr = z1r;
+                pi = z1i;
+                const float v0 = fmq_step<LOUT>(cout, eo, x0);
+                if (i0 + (unsigned) i == next) {
+                    ybuf[slot++] = v0;
+                    next += g.decim;
+                }
+                const float v1 = fmq_step<LOUT>(cout, eo, x1);
+                if (i0 + (unsigned) (i + 1) == next) {
+                    ybuf[slot++] = v1;
+                    next += g.decim;
+                }
             }
         }
     } else {

@@ -24,7 +24,9 @@
 extern "C" {
 #endif
 
+#ifndef FMQ_T
 #define FMQ_T 32                          /* samples per thread (64 input bytes)              */
+#endif
 #define FMQ_THREADS 256                   /* threads per CTA                                  */
 #define FMQ_WARPS (FMQ_THREADS / 32)
 #define FMQ_TILE (FMQ_T * FMQ_THREADS)    /* samples per CTA: 8192 (16 KiB of input)          */
