@@ -9,8 +9,8 @@
  *
  * The recursions run as a three-level scan with an explicit state carry (fmd_quality.h):
  *
- *   thread  FMQ_T = 32 consecutive samples, serially, from a ZERO state
- *   CTA     affine scan over its 256 threads (warp shuffles with the matrices A^(32*2^j), then a
+ *   thread  FMQ_T = 64 consecutive samples, serially, from a ZERO state
+ *   CTA     affine scan over its 256 threads (warp shuffles with the matrices A^(T*2^j), then a
  *           short serial pass over the 8 warp totals): state at the start of every thread's span
  *   launch  fmq_scan_tiles_kernel scans the per-tile end states of all CTAs (and takes the carry
  *           of the previous call in, leaves the carry for the next call behind)
@@ -194,6 +194,9 @@ __device__ __forceinline__ void fmq_span_end(const float *__restrict__ apow, uns
  * a group is unrolled, so the instruction footprint stays a quarter of the fully unrolled span
  * (the fully unrolled <2,2> kernel stalled mostly on instruction fetch: ncu `no_instruction`). */
 #define FMQ_GROUPS (FMQ_T / 8)
+#ifndef FMQ_UNR0
+#define FMQ_UNR0 FMQ_GROUPS /* groups unrolled in the main loop when there is no input cascade */
+#endif
 
 __device__ __forceinline__ uint4 fmq_load_group(const uint8_t *__restrict__ in, unsigned F, int grp) {
     return __ldg(reinterpret_cast<const uint4 *>(in + 2ull * F) + grp);
@@ -312,8 +315,12 @@ __device__ __forceinline__ void fmq_discriminate2(float pr, float pi, float z0r,
     fmd_atan2_x2<8>(fmd_pk(im0, im1), fmd_pk(re0, re1), x0, x1);
 }
 
+/* kept samples of thread t start at slot t*T/M: one word of padding per 32 keeps those starts on
+ * different shared-memory banks (M = 2 had 80 M bank conflicts per launch without it) */
+#define FMQ_PAD(o) ((o) + ((o) >> 5))
+
 #ifndef FMQ_MINB
-#define FMQ_MINB 4 /* resident CTAs per SM the register budget of the main kernel is cut for */
+#define FMQ_MINB (1024 / FMQ_THREADS) /* resident CTAs per SM the register budget of the main kernel is cut for: 32 warps */
 #endif
 
 template <int LIN, int LOUT>
@@ -381,7 +388,7 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     if (full) {
         /* measured on B200: without the input cascade the fully unrolled span is 8 % faster (more
          * freedom for the scheduler); with it the rolled form is 4 % faster (instruction fetch) */
-        constexpr int UNR = LIN > 0 ? 1 : FMQ_GROUPS;
+        constexpr int UNR = LIN > 0 ? 1 : FMQ_UNR0;
         uint4 nx = fmq_load_group(in, sp.F, 0);
 #pragma unroll(UNR)
         for (int grp = 0; grp < FMQ_GROUPS; ++grp) {
@@ -403,12 +410,14 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
                 pi = z1i;
                 const float v0 = fmq_step<LOUT>(cout, eo, x0);
                 if (i0 + (unsigned) i == next) {
-                    ybuf[slot++] = v0;
+                    ybuf[FMQ_PAD(slot)] = v0;
+                    ++slot;
                     next += g.decim;
                 }
                 const float v1 = fmq_step<LOUT>(cout, eo, x1);
                 if (i0 + (unsigned) (i + 1) == next) {
-                    ybuf[slot++] = v1;
+                    ybuf[FMQ_PAD(slot)] = v1;
+                    ++slot;
                     next += g.decim;
                 }
             }
@@ -427,7 +436,8 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
             pi = zi;
             const float v = fmq_step<LOUT>(cout, eo, fmd_atan2(im, re));
             if (i == next) {
-                ybuf[slot++] = v;
+                ybuf[FMQ_PAD(slot)] = v;
+                ++slot;
                 next += g.decim;
             }
         }
@@ -452,7 +462,7 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     for (unsigned o = threadIdx.x; o < count; o += FMQ_THREADS) {
         const unsigned ks = (unsigned) ((unsigned long long) g.r0 + (unsigned long long) (o_tile + o) * g.decim - sp.S);
         const unsigned owner = ks / FMQ_T, k = ks % FMQ_T;
-        float y = ybuf[o];
+        float y = ybuf[FMQ_PAD(o)];
 #pragma unroll
         for (int i = 0; i < DO; ++i) y = fmaf(ck[k * DO + i], qs[owner * DO + i], y);
         out[o_tile + o] = y;

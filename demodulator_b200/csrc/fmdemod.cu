@@ -83,6 +83,7 @@ struct fmq_ctx {
     FmqState *d_state = nullptr;
     float *d_ein = nullptr, *d_qin = nullptr, *d_eout = nullptr, *d_qout = nullptr; /* per-tile scratch */
     unsigned tile_cap = 0;
+    bool smem_opted_in = false;
     unsigned long long pos = 0; /* stream position: global index of the next input sample */
 };
 
@@ -666,7 +667,8 @@ static int quality_launch(fmd_ctx *c, const uint8_t *d_in, unsigned n, float *d_
     if (!fn) return fmd_set_error(FMD_EINVAL, "no quality kernel for %u/%u sections", q->lin, q->lout);
     /* shared memory for the kept samples of one tile */
     const unsigned keep_cap = FMQ_TILE / q->decim + 2u;
-    const size_t smem = (size_t) (keep_cap < FMQ_TILE ? keep_cap : FMQ_TILE) * sizeof(float);
+    const unsigned keep = keep_cap < FMQ_TILE ? keep_cap : FMQ_TILE;
+    const size_t smem = (size_t) (keep + (keep >> 5) + 1u) * sizeof(float); /* FMQ_PAD */
     cudaEvent_t *pe = nullptr;
     if (c->profile) {
         if (c->pev_used == c->pev_cap) {
@@ -675,6 +677,10 @@ static int quality_launch(fmd_ctx *c, const uint8_t *d_in, unsigned n, float *d_
         }
         pe = &c->pev[2 * c->pev_used++];
         FMD_CUDA(cudaEventRecord(pe[0], s));
+    }
+    if (smem > 48u * 1024u && !q->smem_opted_in) { /* M = 1 keeps a whole tile: 64 KiB */
+        FMD_CUDA(cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        q->smem_opted_in = true;
     }
     fn<<<g.ntiles, FMQ_THREADS, smem, s>>>(d_in, d_out, g, q->lin ? q->fin.c : q->fout.c, q->fout.c,
                                            q->lin ? q->fin.lane() : nullptr, q->fout.lane(), q->fout.apow(),

@@ -12,7 +12,8 @@ import ctypes as C
 
 import numpy as np
 
-T, THREADS, TILE, MAXD = 32, 256, 8192, 6
+THREADS, MAXD = 256, 6
+T, TILE = 64, 64 * THREADS  # FMQ_T, FMQ_TILE of the library (checked against its table sizes below)
 
 
 class _Consts(C.Structure):
@@ -32,6 +33,7 @@ class Filter:
                                        [C.c_void_p] * 6 + [C.POINTER(C.c_uint)])
         lib.fmq_test_sizes(L, C.byref(nbytes), sizes)
         assert nbytes.value == C.sizeof(_Consts), (nbytes.value, C.sizeof(_Consts))
+        assert sizes[2] == T * D and sizes[3] == TILE * D, "quality_model.T does not match the library's FMQ_T"
         self.c, self.ct = _Consts(), _Consts()
         lane = np.zeros(sizes[0], np.float32)
         apow = np.zeros(sizes[1], np.float32)

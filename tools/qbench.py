@@ -24,6 +24,8 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 CASES = {
+    "quality_m1": dict(sig="cfg1", rate=192e3, kw=dict(sampleRate=192000.0, lowpassOut=20000.0),
+                       what="192 kS/s IQ -> -Q -r192000 -S192000 -l20000 (M=1: no decimation, 4 B out per sample)"),
     "quality_cfg1": dict(sig="cfg1", rate=192e3, kw=dict(sampleRate=96000.0, lowpassOut=12500.0),
                          what="192 kS/s IQ -> -Q -r192000 -S96000 -l12500 (M=2, output cascade only)"),
     "quality_cfg2": dict(sig="cfg2", rate=192e3, kw=dict(sampleRate=96000.0, lowpassOut=6500.0, lowpassIn=12500.0),
