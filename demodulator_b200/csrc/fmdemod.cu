@@ -21,9 +21,6 @@
 #include "fmd_internal.h"
 #include "fmd_kernels.cuh"
 #include "fmd_quality.cuh"
-#ifdef FMD_EXPERIMENT_FAST2
-#include "../../tools/experiments/fmd_fast2.cuh" /* tuning experiment, never in the product build */
-#endif
 
 /* ------------------------------------------------------------------ errors */
 
@@ -486,18 +483,7 @@ static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned
     if (!fast_ok) return launch_exact(c, d_in, d_out, g, s);
 
     g.fast_out = fast_out;
-#ifdef FMD_EXPERIMENT_FAST2
-    /* experiment: 8 outputs per lane per trip (256 per warp); FMD_FAST2=1 selects it */
-    bool fast2 = false;
-    if (getenv("FMD_FAST2") && atoi(getenv("FMD_FAST2")) && fast_out % 256u == 0 && c->nto == 2 && c->atan_terms <= 6 &&
-        !c->sec.conditioner && (c->nti == 0 || c->nti == 2)) {
-        fn = c->nti ? fmd_fast2_kernel<2, 2, 6> : fmd_fast2_kernel<0, 2, 6>;
-        fast2 = true;
-    }
-    const unsigned iters_chunk = g.fast_out >> (fast2 ? 8 : 7);
-#else
     const unsigned iters_chunk = g.fast_out >> 7;
-#endif
     /* passes per warp segment: long enough to amortise the one extra (drain) pass, short
      * enough that the grid still holds a few waves of warps for small inputs */
     const unsigned long long total_iters = (unsigned long long) iters_chunk * nchunks;
@@ -507,9 +493,6 @@ static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned
      * with it the kernel is pipe-bound and longer segments amortise the drain pass (64: 5.6 TB/s,
      * 16: 5.4) */
     unsigned ips = c->nti ? 64u : 16u;
-#ifdef FMD_EXPERIMENT_FAST2
-    if (fast2) ips >>= 1; /* a trip is two passes */
-#endif
     if (const char *e = getenv("FMD_IPS")) ips = (unsigned) atoi(e); /* tuning experiments only */
     if (ips < 1) ips = 1;
     while (ips > 4 && total_iters / ips < want_warps / 4) ips >>= 1;

@@ -1,11 +1,17 @@
 /*
  * tools/experiments/fmd_fast2.cuh -- NOT part of the product build.
  *
- * Unfinished experiment: a streaming kernel in which a lane owns 32 contiguous input bytes per
+ * Measured and dropped: a streaming kernel in which a lane owns 32 contiguous input bytes per
  * trip (8 outputs) instead of 16, so that only one halo word and one neighbour value per 8
  * outputs cross lanes.  Compiles against demodulator_b200/csrc/fmd_kernels.cuh (include it
- * after that header); 64 registers, 4 bytes of spill for <2,2,6>.  Never wired into the
- * dispatcher and never run on a GPU: the host geometry would have to count trips of 256 outputs.
+ * after that header); 64 registers, 4 bytes of spill for <2,2,6>.
+ *
+ * [B200] wired under -DFMD_EXPERIMENT_FAST2 / FMD_FAST2=1 (commit "experiment: 8-outputs-per-lane
+ * streaming kernel ..."; the host counts trips of 256 outputs, iters_per_seg halved): all 101
+ * parity tests green, but 832 us vs 742 us (cfg2) and 725 us vs 646 us (cfg1) per 1 Gi samples
+ * at the best segment length -- every warp-level load and store touches 32 half-used sectors
+ * (lanes are 32 bytes apart, accesses are 16 bytes), which costs more than the saved shuffles.
+ * tools/gpu_fast2.sh is the session that measured it.
  */
 /* ------------------------------------------------ double-pass streaming kernel (experiment) */
 
