@@ -71,14 +71,20 @@ __device__ __forceinline__ void fmq_load_sample(const uint8_t *__restrict__ in, 
     sq = (float) (h >> 8) - 127.5f;
 }
 
-/* one sample through L sections, direct form II transposed; q = (s1_0, s2_0, s1_1, ...) */
-template <int L>
+/* one sample through L sections, direct form II transposed; q = (s1_0, s2_0, s1_1, ...).
+ * FO: the last section is first order (odd degree: b2 = a2 = 0, src/filter.c zp2Sos), its second
+ * state stays 0 and is not touched -- two instructions less per sample and cascade */
+template <int L, bool FO>
 __device__ __forceinline__ float fmq_step(const fmq_consts &c, float (&q)[2 * L], float u) {
 #pragma unroll
     for (int i = 0; i < L; ++i) {
         const float w = fmaf(c.sos[i][0], u, q[2 * i]);
-        q[2 * i] = fmaf(-c.sos[i][3], w, fmaf(c.sos[i][1], u, q[2 * i + 1]));
-        q[2 * i + 1] = fmaf(-c.sos[i][4], w, c.sos[i][2] * u);
+        if (FO && i == L - 1) {
+            q[2 * i] = fmaf(-c.sos[i][3], w, c.sos[i][1] * u);
+        } else {
+            q[2 * i] = fmaf(-c.sos[i][3], w, fmaf(c.sos[i][1], u, q[2 * i + 1]));
+            q[2 * i + 1] = fmaf(-c.sos[i][4], w, c.sos[i][2] * u);
+        }
         u = w;
     }
     return u;
@@ -211,14 +217,14 @@ __device__ __forceinline__ uint4 fmq_load_group(const uint8_t *__restrict__ in, 
  * Input cascade from a zero state over the thread's SHIFTED span: the halo sample (F-1), then
  * samples F .. F+cnt-2.  cnt = number of samples of the x span (0 for a thread past the end).
  */
-template <int LIN>
+template <int LIN, bool FOI>
 __device__ __forceinline__ void fmq_in_zero_state(const fmq_consts &cin, const uint8_t *__restrict__ in, unsigned F,
                                                   unsigned cnt, float hi, float hq, float (&e)[2][2 * LIN]) {
 #pragma unroll
     for (int i = 0; i < 2 * LIN; ++i) e[0][i] = e[1][i] = 0.0f;
     if (cnt == FMQ_T) {
-        fmq_step<LIN>(cin, e[0], hi);
-        fmq_step<LIN>(cin, e[1], hq);
+        fmq_step<LIN, FOI>(cin, e[0], hi);
+        fmq_step<LIN, FOI>(cin, e[1], hq);
         uint4 nx = fmq_load_group(in, F, 0);
 #pragma unroll 1
         for (int grp = 0; grp < FMQ_GROUPS; ++grp) {
@@ -226,23 +232,23 @@ __device__ __forceinline__ void fmq_in_zero_state(const fmq_consts &cin, const u
             if (grp + 1 < FMQ_GROUPS) nx = fmq_load_group(in, F, grp + 1);
 #pragma unroll
             for (int i = 0; i < 7; ++i) {
-                fmq_step<LIN>(cin, e[0], FMQ_SI(v, i));
-                fmq_step<LIN>(cin, e[1], FMQ_SQ(v, i));
+                fmq_step<LIN, FOI>(cin, e[0], FMQ_SI(v, i));
+                fmq_step<LIN, FOI>(cin, e[1], FMQ_SQ(v, i));
             }
             if (grp + 1 < FMQ_GROUPS) { /* the span's very last sample belongs to the next thread's span */
-                fmq_step<LIN>(cin, e[0], FMQ_SI(v, 7));
-                fmq_step<LIN>(cin, e[1], FMQ_SQ(v, 7));
+                fmq_step<LIN, FOI>(cin, e[0], FMQ_SI(v, 7));
+                fmq_step<LIN, FOI>(cin, e[1], FMQ_SQ(v, 7));
             }
         }
     } else if (cnt) {
-        fmq_step<LIN>(cin, e[0], hi);
-        fmq_step<LIN>(cin, e[1], hq);
+        fmq_step<LIN, FOI>(cin, e[0], hi);
+        fmq_step<LIN, FOI>(cin, e[1], hq);
 #pragma unroll 1
         for (unsigned i = 0; i + 1 < cnt; ++i) {
             float si, sq;
             fmq_load_sample(in, F + i, si, sq);
-            fmq_step<LIN>(cin, e[0], si);
-            fmq_step<LIN>(cin, e[1], sq);
+            fmq_step<LIN, FOI>(cin, e[0], si);
+            fmq_step<LIN, FOI>(cin, e[1], sq);
         }
     }
 }
@@ -276,18 +282,19 @@ __device__ __forceinline__ void fmq_halo(const uint8_t *__restrict__ in, const F
 
 /* ------------------------------------------------ input cascade: per-tile end state (zero state in) */
 
-template <int LIN>
+template <int NIN> /* degree of the input cascade */
 __global__ void __launch_bounds__(FMQ_THREADS)
 fmq_in_aggregate_kernel(const uint8_t *__restrict__ in, const FmqGeom g, const fmq_consts cin,
                         const float *__restrict__ lane_tab, const float *__restrict__ apow,
                         const FmqState *__restrict__ st, float *__restrict__ e_tile /* [ntiles][2][D] */) {
+    constexpr int LIN = (NIN + 1) / 2;
     constexpr int D = 2 * LIN;
     __shared__ float tot[FMQ_WARPS * 2 * D];
     const FmqSpan sp = fmq_span(g);
     float hi, hq;
     fmq_halo(in, st, sp.F, sp.cnt, hi, hq);
     float e[2][D], q[2][D];
-    fmq_in_zero_state<LIN>(cin, in, sp.F, sp.cnt, hi, hq, e);
+    fmq_in_zero_state<LIN, (NIN & 1) != 0>(cin, in, sp.F, sp.cnt, hi, hq, e);
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -323,14 +330,17 @@ __device__ __forceinline__ void fmq_discriminate2(float pr, float pi, float z0r,
 #define FMQ_MINB (1024 / FMQ_THREADS) /* resident CTAs per SM the register budget of the main kernel is cut for: 32 warps */
 #endif
 
-template <int LIN, int LOUT>
+template <int NIN, int NOUT> /* degrees of the input (0 = none) and output cascades */
 __global__ void __launch_bounds__(FMQ_THREADS, FMQ_MINB)
 fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const FmqGeom g, const fmq_consts cin,
                 const fmq_consts cout, const float *__restrict__ lane_in, const float *__restrict__ lane_out,
                 const float *__restrict__ apow_out, const float *__restrict__ ck_out,
                 const float *__restrict__ qin_tile /* [ntiles][2][DIN], state at F-1 of thread 0 */,
                 float *__restrict__ eout_tile /* [ntiles][DOUT] */, const FmqState *__restrict__ st) {
-    constexpr int DI = LIN > 0 ? 2 * LIN : 2;
+    constexpr int LIN = (NIN + 1) / 2, LOUT = (NOUT + 1) / 2; /* sections */
+    constexpr int LI1 = LIN > 0 ? LIN : 1;
+    constexpr bool FOI = (NIN & 1) != 0, FOO = (NOUT & 1) != 0;
+    constexpr int DI = 2 * LI1;
     constexpr int DO = 2 * LOUT;
     extern __shared__ float ybuf[];                    /* kept v of this tile, zero state at the tile start */
     __shared__ float qs[FMQ_THREADS * DO];             /* output-cascade state at the start of every thread */
@@ -349,7 +359,7 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     float qi[2][DI];
     if (LIN > 0) {
         float e[2][DI];
-        fmq_in_zero_state<(LIN > 0 ? LIN : 1)>(cin, in, sp.F, sp.cnt, hi, hq, e);
+        fmq_in_zero_state<LI1, FOI>(cin, in, sp.F, sp.cnt, hi, hq, e);
         float carry[2][DI];
         const float *__restrict__ src = qin_tile + (size_t) blockIdx.x * 2 * DI;
 #pragma unroll
@@ -375,8 +385,8 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     /* second pass: z (from the right state), x, v from a zero state; v kept every M-th sample */
     float pr, pi; /* z[F-1] */
     if (LIN > 0) {
-        pr = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[0], hi);
-        pi = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[1], hq);
+        pr = fmq_step<LI1, FOI>(cin, qi[0], hi);
+        pi = fmq_step<LI1, FOI>(cin, qi[1], hq);
     } else {
         pr = hi;
         pi = hq;
@@ -399,22 +409,22 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
             for (int i = 0; i < 8; i += 2) {
                 float z0r = FMQ_SI(v, i), z0i = FMQ_SQ(v, i), z1r = FMQ_SI(v, i + 1), z1i = FMQ_SQ(v, i + 1);
                 if (LIN > 0) {
-                    z0r = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[0], z0r);
-                    z0i = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[1], z0i);
-                    z1r = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[0], z1r);
-                    z1i = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[1], z1i);
+                    z0r = fmq_step<LI1, FOI>(cin, qi[0], z0r);
+                    z0i = fmq_step<LI1, FOI>(cin, qi[1], z0i);
+                    z1r = fmq_step<LI1, FOI>(cin, qi[0], z1r);
+                    z1i = fmq_step<LI1, FOI>(cin, qi[1], z1i);
                 }
                 float x0, x1;
                 fmq_discriminate2(pr, pi, z0r, z0i, z1r, z1i, x0, x1);
                 pr = z1r;
                 pi = z1i;
-                const float v0 = fmq_step<LOUT>(cout, eo, x0);
+                const float v0 = fmq_step<LOUT, FOO>(cout, eo, x0);
                 if (i0 + (unsigned) i == next) {
                     ybuf[FMQ_PAD(slot)] = v0;
                     ++slot;
                     next += g.decim;
                 }
-                const float v1 = fmq_step<LOUT>(cout, eo, x1);
+                const float v1 = fmq_step<LOUT, FOO>(cout, eo, x1);
                 if (i0 + (unsigned) (i + 1) == next) {
                     ybuf[FMQ_PAD(slot)] = v1;
                     ++slot;
@@ -428,13 +438,13 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
             float zr, zi;
             fmq_load_sample(in, sp.F + i, zr, zi);
             if (LIN > 0) {
-                zr = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[0], zr);
-                zi = fmq_step<(LIN > 0 ? LIN : 1)>(cin, qi[1], zi);
+                zr = fmq_step<LI1, FOI>(cin, qi[0], zr);
+                zi = fmq_step<LI1, FOI>(cin, qi[1], zi);
             }
             const float re = fmaf(zr, pr, zi * pi), im = fmaf(zi, pr, -(zr * pi));
             pr = zr;
             pi = zi;
-            const float v = fmq_step<LOUT>(cout, eo, fmd_atan2(im, re));
+            const float v = fmq_step<LOUT, FOO>(cout, eo, fmd_atan2(im, re));
             if (i == next) {
                 ybuf[FMQ_PAD(slot)] = v;
                 ++slot;

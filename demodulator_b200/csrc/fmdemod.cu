@@ -554,6 +554,10 @@ static int quality_setup(fmd_ctx *c, unsigned decim) {
     int rc = quality_upload_filter(q->fout, &c->sec.out[0][0], q->lout);
     if (!rc && q->lin) rc = quality_upload_filter(q->fin, &c->sec.in[0][0], q->lin);
     if (rc) return rc;
+    /* the kernels for odd degrees skip the second state of the last (first-order) section */
+    if (((c->cfg.out_degree & 1u) && (c->sec.out[q->lout - 1][2] != 0.0f || c->sec.out[q->lout - 1][5] != 0.0f)) ||
+        (q->lin && (c->cfg.in_degree & 1u) && (c->sec.in[q->lin - 1][2] != 0.0f || c->sec.in[q->lin - 1][5] != 0.0f)))
+        return fmd_set_error(FMD_EINVAL, "odd-degree design whose last section is not first order");
     FMD_CUDA(cudaMalloc(&q->d_state, sizeof(FmqState)));
     FMD_CUDA(cudaMemset(q->d_state, 0, sizeof(FmqState)));
     return FMD_OK;
@@ -601,22 +605,44 @@ static size_t quality_out_count(unsigned long long pos, size_t nsamp, unsigned M
 typedef void (*fmq_main_fn)(const uint8_t *, float *, const FmqGeom, const fmq_consts, const fmq_consts, const float *,
                             const float *, const float *, const float *, const float *, float *, const FmqState *);
 
-template <int LIN>
-static fmq_main_fn quality_pick_out(unsigned lout) {
-    switch (lout) {
-        case 1: return fmq_main_kernel<LIN, 1>;
-        case 2: return fmq_main_kernel<LIN, 2>;
-        case 3: return fmq_main_kernel<LIN, 3>;
+template <int NIN>
+static fmq_main_fn quality_pick_out(unsigned nout) {
+    switch (nout) {
+        case 1: return fmq_main_kernel<NIN, 1>;
+        case 2: return fmq_main_kernel<NIN, 2>;
+        case 3: return fmq_main_kernel<NIN, 3>;
+        case 4: return fmq_main_kernel<NIN, 4>;
+        case 5: return fmq_main_kernel<NIN, 5>;
+        case 6: return fmq_main_kernel<NIN, 6>;
         default: return nullptr;
     }
 }
 
-static fmq_main_fn quality_pick_main(unsigned lin, unsigned lout) {
-    switch (lin) {
-        case 0: return quality_pick_out<0>(lout);
-        case 1: return quality_pick_out<1>(lout);
-        case 2: return quality_pick_out<2>(lout);
-        case 3: return quality_pick_out<3>(lout);
+/* by filter DEGREE: an odd degree ends in a first-order section, which the kernels exploit */
+static fmq_main_fn quality_pick_main(unsigned nin, unsigned nout) {
+    switch (nin) {
+        case 0: return quality_pick_out<0>(nout);
+        case 1: return quality_pick_out<1>(nout);
+        case 2: return quality_pick_out<2>(nout);
+        case 3: return quality_pick_out<3>(nout);
+        case 4: return quality_pick_out<4>(nout);
+        case 5: return quality_pick_out<5>(nout);
+        case 6: return quality_pick_out<6>(nout);
+        default: return nullptr;
+    }
+}
+
+typedef void (*fmq_agg_fn)(const uint8_t *, const FmqGeom, const fmq_consts, const float *, const float *,
+                           const FmqState *, float *);
+
+static fmq_agg_fn quality_pick_aggregate(unsigned nin) {
+    switch (nin) {
+        case 1: return fmq_in_aggregate_kernel<1>;
+        case 2: return fmq_in_aggregate_kernel<2>;
+        case 3: return fmq_in_aggregate_kernel<3>;
+        case 4: return fmq_in_aggregate_kernel<4>;
+        case 5: return fmq_in_aggregate_kernel<5>;
+        case 6: return fmq_in_aggregate_kernel<6>;
         default: return nullptr;
     }
 }
@@ -645,17 +671,17 @@ static int quality_launch(fmd_ctx *c, const uint8_t *d_in, unsigned n, float *d_
         fmq_matpow_f(&q->fin.des, (unsigned long long) FMQ_TILE * runlen, prun.m);
         fmq_matpow_f(&q->fin.des, len_last, pl.m);
         float *cin = &q->d_state->in_q[0][0];
+        fmq_agg_fn agg = quality_pick_aggregate(c->cfg.in_degree);
+        if (!agg) return fmd_set_error(FMD_EINVAL, "no quality kernel for input degree %u", c->cfg.in_degree);
+        agg<<<g.ntiles, FMQ_THREADS, 0, s>>>(d_in, g, q->fin.c, q->fin.lane(), q->fin.apow(), q->d_state, q->d_ein);
         switch (q->lin) {
             case 1:
-                fmq_in_aggregate_kernel<1><<<g.ntiles, FMQ_THREADS, 0, s>>>(d_in, g, q->fin.c, q->fin.lane(), q->fin.apow(), q->d_state, q->d_ein);
                 fmq_scan_tiles_kernel<2, 2><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_ein, q->d_qin, cin, q->fin.c_tile, q->fin.lane_tile(), prun, pl, g.ntiles, runlen, nullptr, nullptr);
                 break;
             case 2:
-                fmq_in_aggregate_kernel<2><<<g.ntiles, FMQ_THREADS, 0, s>>>(d_in, g, q->fin.c, q->fin.lane(), q->fin.apow(), q->d_state, q->d_ein);
                 fmq_scan_tiles_kernel<4, 2><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_ein, q->d_qin, cin, q->fin.c_tile, q->fin.lane_tile(), prun, pl, g.ntiles, runlen, nullptr, nullptr);
                 break;
             default:
-                fmq_in_aggregate_kernel<3><<<g.ntiles, FMQ_THREADS, 0, s>>>(d_in, g, q->fin.c, q->fin.lane(), q->fin.apow(), q->d_state, q->d_ein);
                 fmq_scan_tiles_kernel<6, 2><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_ein, q->d_qin, cin, q->fin.c_tile, q->fin.lane_tile(), prun, pl, g.ntiles, runlen, nullptr, nullptr);
                 break;
         }
@@ -663,8 +689,8 @@ static int quality_launch(fmd_ctx *c, const uint8_t *d_in, unsigned n, float *d_
         c->launches += 2;
     }
 
-    fmq_main_fn fn = quality_pick_main(q->lin, q->lout);
-    if (!fn) return fmd_set_error(FMD_EINVAL, "no quality kernel for %u/%u sections", q->lin, q->lout);
+    fmq_main_fn fn = quality_pick_main(q->lin ? c->cfg.in_degree : 0u, c->cfg.out_degree);
+    if (!fn) return fmd_set_error(FMD_EINVAL, "no quality kernel for degrees %u/%u", c->cfg.in_degree, c->cfg.out_degree);
     /* shared memory for the kept samples of one tile */
     const unsigned keep_cap = FMQ_TILE / q->decim + 2u;
     const unsigned keep = keep_cap < FMQ_TILE ? keep_cap : FMQ_TILE;

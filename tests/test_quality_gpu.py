@@ -70,6 +70,50 @@ def test_quality_stream_continues_across_calls(name, sizes, oracle_port):
             d.reset()
 
 
+def test_quality_every_degree_combination(oracle_port):
+    """one kernel instantiation per (input degree 0..6, output degree 1..6): all of them, Butterworth
+    and Chebyshev, against the oracle, in two calls that split a tile"""
+    rate, fs = 192e3, 48000.0
+    c = synth.CONFIGS["cfg2"]
+    raw = synth.fm_iq_u8(40000, c["fs_sig"], c["df"], c["fm"], 21)
+    worst = 0.0
+    for deg_in in range(0, 7):
+        for deg_out in range(1, 7):
+            mode = 3 if (deg_in + deg_out) % 3 == 0 else 0
+            cfg = po.Config(fs=fs, fc_out=9000.0 + 500.0 * deg_out, fc_in=30000.0 if deg_in else 0.0,
+                            deg_in=deg_in, deg_out=deg_out, mode=mode, eps=0.1)
+            want = oracle_port.quality(cfg, rate).run(raw)
+            with fm.Demodulator(**quality_kwargs(cfg, rate)) as d:
+                out = np.concatenate([d.process(raw[:2 * 17001]), d.process(raw[2 * 17001:])])
+            err = max_err(out, want)
+            worst = max(worst, err)
+            assert err <= TOL, (deg_in, deg_out, mode, err)
+    print(f"42 degree combinations: worst max-abs {worst:.2e}")
+
+
+def test_quality_edge_geometry(oracle_port):
+    """decimation larger than a tile, calls shorter than the decimation, empty calls, odd byte counts"""
+    rate = 2.4e6
+    cfg = po.Config(fs=100.0, fc_out=15000.0)  # M = 24000 > 16384 samples per tile
+    c = synth.CONFIGS["cfg3"]
+    raw = synth.fm_iq_u8(120000, c["fs_sig"], c["df"], c["fm"], 22)
+    q = oracle_port.quality(cfg, rate)
+    assert q.decim == 24000
+    with fm.Demodulator(**quality_kwargs(cfg, rate)) as d:
+        off, got, want = 0, [], []
+        for n in (0, 5, 23990, 10, 0, 50000, 45995):
+            seg = raw[2 * off:2 * (off + n)]
+            w = q.run(seg)
+            assert d.out_count(seg.size) == w.size
+            got.append(d.process(seg))
+            want.append(w)
+            off += n
+        assert max_err(np.concatenate(got), np.concatenate(want)) <= TOL
+        assert np.concatenate(want).size == 5  # samples 0, 24000, ..., 96000
+        with pytest.raises(fm.FmdError, match="even number of bytes"):
+            d.process(raw[:7])
+
+
 def test_quality_device_resident_many_tiles(oracle_port):
     """16 Mi samples resident in HBM, one call: 2048 tiles through the tile-level scan"""
     import torch

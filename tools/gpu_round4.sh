@@ -25,7 +25,7 @@ d=json.load(open("gpurun_out/$1.json"))
 print("$1", d["value"], "MS/s  ms/step", d["ms_per_step"], "main_ms", d["roofline"]["kernel_ms_avg"], "frac", d["roofline"]["frac"], "e2e", d["e2e"]["value"], "cpu", d["cpu_baseline"] and d["cpu_baseline"]["value"], "err", d["cpu_baseline"] and d["cpu_baseline"]["max_abs_err_vs_gpu"])
 PY
 }
-for c in quality_cfg3 quality_cfg1 quality_cfg2; do
+for c in quality_cfg3 quality_cfg1 quality_cfg2 quality_m1; do
   timeout 300 python tools/qbench.py --config $c > gpurun_out/qbench_$c.json 2> gpurun_out/qbench_$c.err || tail -5 gpurun_out/qbench_$c.err
   QB qbench_$c
 done

@@ -2,7 +2,7 @@
 # copy the judged artefacts of the quality pipeline from gpurun_out/ (scratch) into profiles/ (tracked)
 R=${1:-r01}
 cd "$(dirname "$0")/.."
-for c in quality_cfg1 quality_cfg2 quality_cfg3; do cp gpurun_out/qbench_$c.json profiles/${R}_qbench_$c.json; done
+for c in quality_cfg1 quality_cfg2 quality_cfg3 quality_m1; do cp gpurun_out/qbench_$c.json profiles/${R}_qbench_$c.json; done
 cp gpurun_out/quality_cli_stream.txt profiles/${R}_quality_cli_stream.txt 2>/dev/null
 for c in quality_cfg3 quality_cfg2; do
   cp gpurun_out/qlaunches_$c.csv profiles/${R}_quality_launches_$c.csv
