@@ -115,7 +115,7 @@ def test_quality_edge_geometry(oracle_port):
 
 
 def test_quality_device_resident_many_tiles(oracle_port):
-    """16 Mi samples resident in HBM, one call: 2048 tiles through the tile-level scan"""
+    """16 Mi samples resident in HBM, one call: 1024 tiles through the tile-level scan"""
     import torch
     cfg, rate = po.Config(fs=48000.0, fc_out=15000.0), 2.4e6
     n = 16 << 20
@@ -136,7 +136,7 @@ def test_quality_device_resident_many_tiles(oracle_port):
 
 
 def test_quality_with_input_filter_many_tiles(oracle_port):
-    """both cascades over 4 Mi samples (512 tiles), in two unequal calls"""
+    """both cascades over 4 Mi samples (256 tiles), in two unequal calls"""
     cfg, rate = po.Config(fs=96000.0, fc_out=6500.0, fc_in=12500.0), 192e3
     n = 4 << 20
     c = synth.CONFIGS["cfg2"]
