@@ -16,9 +16,10 @@
  *           of the previous call in, leaves the carry for the next call behind)
  *
  * Input lowpass (a scan whose result feeds a non-linearity, so it has to be resolved first):
- *   fmq_in_aggregate_kernel  per-tile end state from a zero state       reads the input once
- *   fmq_scan_tiles_kernel    state at the start of every tile
- *   fmq_main_kernel          re-runs the cascade from the right state and goes on to x and v
+ *   fmq_main_kernel          thread- and CTA-level scan, then a decoupled look-back over the end
+ *                            states the earlier tiles of the launch have published (FmqLookback):
+ *                            the input is read once; re-runs the cascade from the right state and
+ *                            goes on to x and v
  * Output lowpass (linear in x, so the carry can be added afterwards, to the kept samples only):
  *   fmq_main_kernel          v from a zero state at the tile start (thread-level carry applied
  *                            in shared memory), decimated; per-tile end state
@@ -29,7 +30,8 @@
  * F = first sample of its x span): re-running it from the state at F-1 yields z[F-1], the
  * neighbour the discriminator needs for x[F], with no exchange between threads.
  *
- * No spin-waits, no inter-CTA dependencies inside a kernel: the carries travel between launches.
+ * The only inter-CTA dependency is the look-back of the input cascade (tiles in ticket order,
+ * bounded waits); every other carry travels between launches.
  */
 #ifndef FMD_QUALITY_CUH
 #define FMD_QUALITY_CUH
@@ -42,9 +44,10 @@
 
 /* the carry between calls (one per context, device memory) */
 struct FmqState {
-    float in_q[2][FMQ_MAXD]; /* input cascade, lanes I and Q: state BEFORE the sample s_prev   */
-    float out_q[FMQ_MAXD];   /* output cascade: state before the next x                        */
-    float s_prev[2];         /* the centred sample that precedes the next call (0,0 at start)  */
+    float in_q[2 * FMQ_MAXD]; /* input cascade, [lane][D] packed: state BEFORE the sample s_prev */
+    float out_q[FMQ_MAXD];    /* output cascade: state before the next x                        */
+    float s_prev[2];          /* the centred sample that precedes the next call (0,0 at start)  */
+    unsigned error;           /* raised by a look-back that gave up waiting (never seen so far)  */
 };
 
 struct FmqGeom {
@@ -259,9 +262,9 @@ struct FmqSpan {
     bool last;          /* this thread's span reaches the end of the tile's valid samples          */
 };
 
-__device__ __forceinline__ FmqSpan fmq_span(const FmqGeom &g) {
+__device__ __forceinline__ FmqSpan fmq_span(const FmqGeom &g, const unsigned tile) {
     FmqSpan s;
-    s.S = blockIdx.x * (unsigned) FMQ_TILE;
+    s.S = tile * (unsigned) FMQ_TILE;
     s.F = s.S + threadIdx.x * (unsigned) FMQ_T;
     s.cnt = s.F >= g.n ? 0u : min((unsigned) FMQ_T, g.n - s.F);
     s.last = s.cnt != 0u && (threadIdx.x == FMQ_THREADS - 1 || s.F + FMQ_T >= g.n);
@@ -280,35 +283,112 @@ __device__ __forceinline__ void fmq_halo(const uint8_t *__restrict__ in, const F
     }
 }
 
-/* ------------------------------------------------ input cascade: per-tile end state (zero state in) */
+/* ------------------------------------------ input cascade: carry between the tiles of a launch */
 
-template <int NIN> /* degree of the input cascade */
-__global__ void __launch_bounds__(FMQ_THREADS)
-fmq_in_aggregate_kernel(const uint8_t *__restrict__ in, const FmqGeom g, const fmq_consts cin,
-                        const float *__restrict__ lane_tab, const float *__restrict__ apow,
-                        const FmqState *__restrict__ st, float *__restrict__ e_tile /* [ntiles][2][D] */) {
-    constexpr int LIN = (NIN + 1) / 2;
-    constexpr int D = 2 * LIN;
-    __shared__ float tot[FMQ_WARPS * 2 * D];
-    const FmqSpan sp = fmq_span(g);
-    float hi, hq;
-    fmq_halo(in, st, sp.F, sp.cnt, hi, hq);
-    float e[2][D], q[2][D];
-    fmq_in_zero_state<LIN, (NIN & 1) != 0>(cin, in, sp.F, sp.cnt, hi, hq, e);
+/*
+ * The input cascade feeds a non-linearity, so its state at the start of a tile has to be known
+ * INSIDE the main kernel.  Decoupled look-back (Merrill & Garland) over affine maps with a constant
+ * matrix: every tile publishes its end state from a zero state (E, flag 1) as soon as it has it,
+ * then walks back over its predecessors until it meets one that has already published its true
+ * end state (S, flag 2), replays  q <- P q + E_m  forward from there, and publishes its own S.
+ * Tile numbers are handed out by an atomic ticket, so every predecessor of a running tile is
+ * itself running or done: no deadlock.  The wait is bounded anyway (FMQ_SPIN_LIMIT polls): on
+ * expiry the kernel raises FmqState::error and carries on with a zero carry instead of hanging.
+ */
+struct FmqLookback {
+    unsigned *ticket;  /* [1]  zeroed before every launch together with `flag`            */
+    unsigned *flag;    /* [ntiles] 0 = nothing, 1 = E published, 2 = S published            */
+    float *E;          /* [ntiles][2][D]                                                    */
+    float *S;          /* [ntiles][2][D]                                                    */
+};
+
+#define FMQ_SPIN_LIMIT (1u << 22)
+
+__device__ __forceinline__ unsigned fmq_poll_flag(const unsigned *flag, unsigned *error) {
+    unsigned f = 0;
+    for (unsigned spin = 0; spin < FMQ_SPIN_LIMIT; ++spin) {
+        f = *reinterpret_cast<const volatile unsigned *>(flag);
+        if (f) return f;
+        __nanosleep(64);
+    }
+    atomicExch(error, 1u);
+    return 0u;
+}
+
+/*
+ * State of the input cascade at the start of `tile` (before sample S-1), lanes I and Q.  Called by
+ * ONE WHOLE WARP after E[tile] has been published.  Lane l inspects predecessor tile-1-l (32 per
+ * round, one L2 round trip for all of them): records up to the nearest one that already holds its
+ * true end state S count, each advanced by (A^TILE)^l (`lane_tile`) and, from the second round
+ * on, by A^(32 TILE) per round (`wtile`); a butterfly sum gives every lane the result.
+ */
+template <int D>
+__device__ __forceinline__ void fmq_lookback(const FmqLookback &lb, const unsigned tile, const unsigned lane,
+                                             const float *__restrict__ lane_tile, const FmqMat &wtile,
+                                             float (&q)[2][D], unsigned *error) {
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int i = 0; i < D; ++i) q[a][i] = e[a][i];
-    float zero[2][D];
+        for (int i = 0; i < D; ++i) q[a][i] = 0.0f;
+    float lp[D * D];
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int i = 0; i < D * D; ++i) lp[i] = __ldg(lane_tile + lane * (D * D) + i);
+    long long base = (long long) tile - 1;
+    for (unsigned round = 0;; ++round) {
+        const long long idx = base - (long long) lane;
+        unsigned f = 0u;
+        if (idx >= 0) f = fmq_poll_flag(lb.flag + idx, error);
+        __threadfence();
+        const unsigned have_s = __ballot_sync(0xffffffffu, idx >= 0 && f == 2u);
+        const unsigned gave_up = __ballot_sync(0xffffffffu, idx >= 0 && f == 0u);
+        const unsigned first_s = have_s ? (unsigned) __ffs((int) have_s) - 1u : 32u;
+        float v[2][D];
 #pragma unroll
-        for (int i = 0; i < D; ++i) zero[a][i] = 0.0f;
-    fmq_block_scan<D, 2>(q, cin, lane_tab, zero, tot);
-    if (sp.last) {
-        float *dst = e_tile + (size_t) blockIdx.x * 2 * D;
-        fmq_span_end<D>(apow, sp.cnt, q[0], e[0], dst);
-        fmq_span_end<D>(apow, sp.cnt, q[1], e[1], dst + D);
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                float x = 0.0f;
+                if (idx >= 0 && lane <= first_s && f != 0u) {
+                    const float *src = (lane == first_s ? lb.S : lb.E) + ((size_t) idx * 2 + a) * D + i;
+                    x = __ldcg(src);
+                }
+                v[a][i] = x;
+            }
+        /* (A^TILE)^lane, butterfly sum over the lanes, then A^(32 TILE) once per earlier round */
+        float t[2][D];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int k = 0; k < D; ++k) acc = fmaf(lp[i * D + k], v[a][k], acc);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                t[a][i] = acc;
+            }
+        for (unsigned r = 0; r < round; ++r) {
+            float n2[2][D];
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) acc = fmaf(wtile.m[i * D + k], t[a][k], acc);
+                    n2[a][i] = acc;
+                }
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int i = 0; i < D; ++i) t[a][i] = n2[a][i];
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int i = 0; i < D; ++i) q[a][i] += t[a][i];
+        if (have_s || gave_up || base < 32) break;
+        base -= 32;
     }
 }
 
@@ -335,8 +415,9 @@ __global__ void __launch_bounds__(FMQ_THREADS, FMQ_MINB)
 fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const FmqGeom g, const fmq_consts cin,
                 const fmq_consts cout, const float *__restrict__ lane_in, const float *__restrict__ lane_out,
                 const float *__restrict__ apow_out, const float *__restrict__ ck_out,
-                const float *__restrict__ qin_tile /* [ntiles][2][DIN], state at F-1 of thread 0 */,
-                float *__restrict__ eout_tile /* [ntiles][DOUT] */, const FmqState *__restrict__ st) {
+                const float *__restrict__ apow_in, const float *__restrict__ lane_tile_in, const FmqLookback lb,
+                const FmqMat plast_in, const FmqMat wtile_in,
+                float *__restrict__ eout_tile /* [ntiles][DOUT] */, FmqState *__restrict__ st) {
     constexpr int LIN = (NIN + 1) / 2, LOUT = (NOUT + 1) / 2; /* sections */
     constexpr int LI1 = LIN > 0 ? LIN : 1;
     constexpr bool FOI = (NIN & 1) != 0, FOO = (NOUT & 1) != 0;
@@ -348,8 +429,14 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     __shared__ float tot_in[FMQ_WARPS * 2 * DI];
     __shared__ float tot_out[FMQ_WARPS * DO];
 
-    const FmqSpan sp = fmq_span(g);
+    __shared__ unsigned tile_s;
+    __shared__ float carry_s[2 * DI];
+    /* tiles in ticket order: a tile's predecessors have all started (the look-back relies on it) */
+    if (threadIdx.x == 0) tile_s = LIN > 0 ? atomicAdd(lb.ticket, 1u) : blockIdx.x;
     for (unsigned i = threadIdx.x; i < FMQ_T * DO; i += FMQ_THREADS) ck[i] = __ldg(ck_out + i);
+    __syncthreads();
+    const unsigned tile = tile_s;
+    const FmqSpan sp = fmq_span(g, tile);
 
     const bool full = sp.cnt == FMQ_T;
     float hi, hq;
@@ -358,18 +445,108 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     /* input cascade: state at F-1 */
     float qi[2][DI];
     if (LIN > 0) {
-        float e[2][DI];
+        float e[2][DI], zero[2][DI];
         fmq_in_zero_state<LI1, FOI>(cin, in, sp.F, sp.cnt, hi, hq, e);
-        float carry[2][DI];
-        const float *__restrict__ src = qin_tile + (size_t) blockIdx.x * 2 * DI;
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
             for (int i = 0; i < DI; ++i) {
                 qi[a][i] = e[a][i];
-                carry[a][i] = __ldg(src + a * DI + i);
+                zero[a][i] = 0.0f;
             }
-        fmq_block_scan<DI, 2>(qi, cin, lane_in, carry, tot_in);
+        /* relative to a zero state at the tile start ... */
+        fmq_block_scan<DI, 2>(qi, cin, lane_in, zero, tot_in);
+        /* ... which gives the tile's end state from a zero state (E, held by the last thread with
+         * samples).  Its warp publishes E, finds the true state at the tile start by look-back,
+         * publishes the true end state S. */
+        const unsigned tile_samples = min((unsigned) FMQ_TILE, g.n - sp.S);
+        const unsigned last_t = (tile_samples + FMQ_T - 1u) / FMQ_T - 1u;
+        if ((threadIdx.x >> 5) == (last_t >> 5)) {
+            const unsigned lane = threadIdx.x & 31u, src_lane = last_t & 31u;
+            float E[2][DI], q0[2][DI];
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int i = 0; i < DI; ++i) E[a][i] = 0.0f;
+            if (sp.last) {
+                fmq_span_end<DI>(apow_in, sp.cnt, qi[0], e[0], E[0]);
+                fmq_span_end<DI>(apow_in, sp.cnt, qi[1], e[1], E[1]);
+            }
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int i = 0; i < DI; ++i) E[a][i] = __shfl_sync(0xffffffffu, E[a][i], src_lane);
+            if (tile == 0u) {
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int i = 0; i < DI; ++i) q0[a][i] = st->in_q[a * DI + i];
+            } else {
+                if (lane == 0u) {
+#pragma unroll
+                    for (int a = 0; a < 2; ++a)
+#pragma unroll
+                        for (int i = 0; i < DI; ++i) lb.E[((size_t) tile * 2 + a) * DI + i] = E[a][i];
+                    __threadfence();
+                    atomicExch(lb.flag + tile, 1u);
+                }
+                fmq_lookback<DI>(lb, tile, lane, lane_tile_in, wtile_in, q0, &st->error);
+            }
+            const bool final_tile = tile + 1u == g.ntiles;
+            if (lane == 0u) {
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int i = 0; i < DI; ++i) {
+                        float acc = E[a][i];
+#pragma unroll
+                        for (int k = 0; k < DI; ++k)
+                            acc = fmaf(final_tile ? plast_in.m[i * DI + k] : cin.tile[i * DI + k], q0[a][k], acc);
+                        if (final_tile) st->in_q[a * DI + i] = acc; /* the carry of the next call */
+                        else lb.S[((size_t) tile * 2 + a) * DI + i] = acc;
+                        carry_s[a * DI + i] = q0[a][i];
+                    }
+                if (!final_tile) {
+                    __threadfence();
+                    atomicExch(lb.flag + tile, 2u);
+                }
+            }
+        }
+        __syncthreads();
+        /* thread state = (relative state) + (A^T)^t * carry, t = thread index in the tile */
+        {
+            const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+            float wq[2][DI];
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int i = 0; i < DI; ++i) wq[a][i] = carry_s[a * DI + i];
+            for (unsigned w = 0; w < warp; ++w) {
+                float nw[2][DI];
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int i = 0; i < DI; ++i) {
+                        float acc = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < DI; ++k) acc = fmaf(cin.warp[i * DI + k], wq[a][k], acc);
+                        nw[a][i] = acc;
+                    }
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int i = 0; i < DI; ++i) wq[a][i] = nw[a][i];
+            }
+            const float *__restrict__ lt = lane_in + lane * (DI * DI);
+#pragma unroll
+            for (int i = 0; i < DI; ++i)
+#pragma unroll
+                for (int k = 0; k < DI; ++k) {
+                    const float m = __ldg(lt + i * DI + k);
+                    qi[0][i] = fmaf(m, wq[0][k], qi[0][i]);
+                    qi[1][i] = fmaf(m, wq[1][k], qi[1][i]);
+                }
+        }
     }
 
     /* kept samples of this thread: offset of the first one in its span, and its slot in ybuf */
@@ -463,7 +640,7 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     fmq_block_scan<DO, 1>(qo, cout, lane_out, zero, tot_out);
 #pragma unroll
     for (int i = 0; i < DO; ++i) qs[threadIdx.x * DO + i] = qo[0][i];
-    if (sp.last) fmq_span_end<DO>(apow_out, sp.cnt, qo[0], eo, eout_tile + (size_t) blockIdx.x * DO);
+    if (sp.last) fmq_span_end<DO>(apow_out, sp.cnt, qo[0], eo, eout_tile + (size_t) tile * DO);
     __syncthreads();
 
     /* kept samples: add the thread-level zero-input response, store coalesced */

@@ -82,6 +82,7 @@ struct fmq_ctx {
     fmq_filter fin, fout;
     FmqState *d_state = nullptr;
     float *d_ein = nullptr, *d_qin = nullptr, *d_eout = nullptr, *d_qout = nullptr; /* per-tile scratch */
+    unsigned *d_lb = nullptr; /* look-back ticket + per-tile flags */
     unsigned tile_cap = 0;
     bool smem_opted_in = false;
     unsigned long long pos = 0; /* stream position: global index of the next input sample */
@@ -573,6 +574,7 @@ static void quality_free(fmd_ctx *c) {
     if (q->d_qin) cudaFree(q->d_qin);
     if (q->d_eout) cudaFree(q->d_eout);
     if (q->d_qout) cudaFree(q->d_qout);
+    if (q->d_lb) cudaFree(q->d_lb);
     delete q;
     c->q = nullptr;
 }
@@ -584,6 +586,8 @@ static int quality_reserve_tiles(fmq_ctx *q, unsigned ntiles) {
     if (q->d_qin) cudaFree(q->d_qin);
     if (q->d_eout) cudaFree(q->d_eout);
     if (q->d_qout) cudaFree(q->d_qout);
+    if (q->d_lb) cudaFree(q->d_lb);
+    q->d_lb = nullptr;
     q->d_ein = q->d_qin = q->d_eout = q->d_qout = nullptr;
     q->tile_cap = 0;
     const unsigned cap = ntiles < 4096u ? 4096u : ntiles;
@@ -592,6 +596,7 @@ static int quality_reserve_tiles(fmq_ctx *q, unsigned ntiles) {
     FMD_CUDA(cudaMalloc(&q->d_qin, per_in));
     FMD_CUDA(cudaMalloc(&q->d_eout, per_out));
     FMD_CUDA(cudaMalloc(&q->d_qout, per_out));
+    FMD_CUDA(cudaMalloc(&q->d_lb, ((size_t) cap + 1u) * sizeof(unsigned)));
     q->tile_cap = cap;
     return FMD_OK;
 }
@@ -603,7 +608,8 @@ static size_t quality_out_count(unsigned long long pos, size_t nsamp, unsigned M
 }
 
 typedef void (*fmq_main_fn)(const uint8_t *, float *, const FmqGeom, const fmq_consts, const fmq_consts, const float *,
-                            const float *, const float *, const float *, const float *, float *, const FmqState *);
+                            const float *, const float *, const float *, const float *, const float *,
+                            const FmqLookback, const FmqMat, const FmqMat, float *, FmqState *);
 
 template <int NIN>
 static fmq_main_fn quality_pick_out(unsigned nout) {
@@ -632,21 +638,6 @@ static fmq_main_fn quality_pick_main(unsigned nin, unsigned nout) {
     }
 }
 
-typedef void (*fmq_agg_fn)(const uint8_t *, const FmqGeom, const fmq_consts, const float *, const float *,
-                           const FmqState *, float *);
-
-static fmq_agg_fn quality_pick_aggregate(unsigned nin) {
-    switch (nin) {
-        case 1: return fmq_in_aggregate_kernel<1>;
-        case 2: return fmq_in_aggregate_kernel<2>;
-        case 3: return fmq_in_aggregate_kernel<3>;
-        case 4: return fmq_in_aggregate_kernel<4>;
-        case 5: return fmq_in_aggregate_kernel<5>;
-        case 6: return fmq_in_aggregate_kernel<6>;
-        default: return nullptr;
-    }
-}
-
 /* one launch group: `n` samples (< 2^31) that continue the stream; *nout = floats written */
 static int quality_launch(fmd_ctx *c, const uint8_t *d_in, unsigned n, float *d_out, cudaStream_t s, size_t *nout) {
     fmq_ctx *q = c->q;
@@ -665,28 +656,20 @@ static int quality_launch(fmd_ctx *c, const uint8_t *d_in, unsigned n, float *d_
     const unsigned runlen = ((g.ntiles + nwarps - 1u) / nwarps + 31u) & ~31u;
     FmqMat prun, pl;
 
+    FmqLookback lb = {nullptr, nullptr, nullptr, nullptr};
+    FmqMat pl_in, wtile_in;
+    memset(&pl_in, 0, sizeof pl_in);
+    memset(&wtile_in, 0, sizeof wtile_in);
     if (q->lin) {
-        memset(&prun, 0, sizeof prun);
-        memset(&pl, 0, sizeof pl);
-        fmq_matpow_f(&q->fin.des, (unsigned long long) FMQ_TILE * runlen, prun.m);
-        fmq_matpow_f(&q->fin.des, len_last, pl.m);
-        float *cin = &q->d_state->in_q[0][0];
-        fmq_agg_fn agg = quality_pick_aggregate(c->cfg.in_degree);
-        if (!agg) return fmd_set_error(FMD_EINVAL, "no quality kernel for input degree %u", c->cfg.in_degree);
-        agg<<<g.ntiles, FMQ_THREADS, 0, s>>>(d_in, g, q->fin.c, q->fin.lane(), q->fin.apow(), q->d_state, q->d_ein);
-        switch (q->lin) {
-            case 1:
-                fmq_scan_tiles_kernel<2, 2><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_ein, q->d_qin, cin, q->fin.c_tile, q->fin.lane_tile(), prun, pl, g.ntiles, runlen, nullptr, nullptr);
-                break;
-            case 2:
-                fmq_scan_tiles_kernel<4, 2><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_ein, q->d_qin, cin, q->fin.c_tile, q->fin.lane_tile(), prun, pl, g.ntiles, runlen, nullptr, nullptr);
-                break;
-            default:
-                fmq_scan_tiles_kernel<6, 2><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_ein, q->d_qin, cin, q->fin.c_tile, q->fin.lane_tile(), prun, pl, g.ntiles, runlen, nullptr, nullptr);
-                break;
-        }
-        FMD_CUDA(cudaGetLastError());
-        c->launches += 2;
+        /* the input cascade's carry travels between the tiles INSIDE the main kernel (look-back):
+         * ticket + one flag per tile, cleared per launch; E and S records per tile */
+        FMD_CUDA(cudaMemsetAsync(q->d_lb, 0, ((size_t) g.ntiles + 1u) * sizeof(unsigned), s));
+        lb.ticket = q->d_lb;
+        lb.flag = q->d_lb + 1;
+        lb.E = q->d_ein;
+        lb.S = q->d_qin;
+        fmq_matpow_f(&q->fin.des, len_last, pl_in.m);
+        memcpy(wtile_in.m, q->fin.c_tile.warp, sizeof wtile_in.m); /* A^(32 TILE): one look-back round */
     }
 
     fmq_main_fn fn = quality_pick_main(q->lin ? c->cfg.in_degree : 0u, c->cfg.out_degree);
@@ -710,7 +693,8 @@ static int quality_launch(fmd_ctx *c, const uint8_t *d_in, unsigned n, float *d_
     }
     fn<<<g.ntiles, FMQ_THREADS, smem, s>>>(d_in, d_out, g, q->lin ? q->fin.c : q->fout.c, q->fout.c,
                                            q->lin ? q->fin.lane() : nullptr, q->fout.lane(), q->fout.apow(),
-                                           q->fout.ck(), q->d_qin, q->d_eout, q->d_state);
+                                           q->fout.ck(), q->lin ? q->fin.apow() : nullptr,
+                                           q->lin ? q->fin.lane_tile() : nullptr, lb, pl_in, wtile_in, q->d_eout, q->d_state);
     FMD_CUDA(cudaGetLastError());
     if (pe) FMD_CUDA(cudaEventRecord(pe[1], s));
 
@@ -868,6 +852,11 @@ extern "C" int fmd_wait(fmd_ctx *c, unsigned slot) {
     if (!s.busy) return FMD_OK;
     FMD_CUDA(cudaEventSynchronize(s.ev_out));
     s.busy = false;
+    if (c->q && c->q->lin) { /* a look-back that gave up waiting raises a device-side flag */
+        unsigned err = 0;
+        FMD_CUDA(cudaMemcpy(&err, &c->q->d_state->error, sizeof err, cudaMemcpyDeviceToHost));
+        if (err) return fmd_set_error(FMD_ECUDA, "quality pipeline: a tile gave up waiting for its predecessor's carry");
+    }
     return FMD_OK;
 }
 

@@ -195,7 +195,9 @@ class Stream:
                     q2 = e[lanei].copy()
                     f.step(q2, u)
                     e[lanei][act] = q2[act]
-            # fmq_in_aggregate_kernel + scan
+            # per-tile end states from a zero state, then the carry from tile to tile (on the GPU: the
+            # decoupled look-back inside fmq_main_kernel -- the same recurrence q <- P q + E, resolved
+            # in a different order)
             Ein = np.zeros((ntiles, 2, f.D))
             for lanei in range(2):
                 ex = block_scan(f, e[lanei].reshape(ntiles, THREADS, f.D), np.zeros((ntiles, f.D))).reshape(nthr, f.D)
