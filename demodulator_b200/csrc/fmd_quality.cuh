@@ -292,7 +292,9 @@ __device__ __forceinline__ void fmq_halo(const uint8_t *__restrict__ in, const F
  * then walks back over its predecessors until it meets one that has already published its true
  * end state (S, flag 2), replays  q <- P q + E_m  forward from there, and publishes its own S.
  * Tile numbers are handed out by an atomic ticket, so every predecessor of a running tile is
- * itself running or done: no deadlock.  The wait is bounded anyway (FMQ_SPIN_LIMIT polls): on
+ * itself running or done: no deadlock.  (Measured and dropped: persistent CTAs that run phase A
+ * of their NEXT tile before the look-back of the current one, so that no look-back ever waits for
+ * an E -- 1.25 ms vs 1.23 ms for the -L configuration, and 4 % slower without -L.)  The wait is bounded anyway (FMQ_SPIN_LIMIT polls): on
  * expiry the kernel raises FmqState::error and carries on with a zero carry instead of hanging.
  */
 struct FmqLookback {
@@ -414,58 +416,6 @@ __device__ __forceinline__ void fmq_discriminate2(float pr, float pi, float z0r,
 #define FMQ_MINB (1024 / FMQ_THREADS) /* resident CTAs per SM the register budget of the main kernel is cut for: 32 warps */
 #endif
 
-/*
- * Phase A of a tile (input cascade only): every thread runs its shifted span from a zero state,
- * the CTA scans the end states, and the warp that holds the last samples publishes the tile's end
- * state from a zero state (E, flag 1) for the look-backs of the later tiles.  Leaves behind, in
- * shared memory: per thread the state relative to a zero tile start and the halo sample (`stash`,
- * FMQ_THREADS x (2 D + 2)), and E (`e_s`, 2 D).  Contains __syncthreads: whole CTA calls it.
- */
-template <int LI1, bool FOI>
-__device__ __forceinline__ void fmq_phase_a(const uint8_t *__restrict__ in, const FmqGeom &g, const fmq_consts &cin,
-                                            const float *__restrict__ lane_in, const float *__restrict__ apow_in,
-                                            const FmqLookback &lb, const FmqState *__restrict__ st, const unsigned tile,
-                                            float *tot_in, float *stash, float *e_s) {
-    constexpr int DI = 2 * LI1;
-    const FmqSpan sp = fmq_span(g, tile);
-    float hi, hq;
-    fmq_halo(in, st, sp.F, sp.cnt, hi, hq);
-    float e[2][DI], qi[2][DI], zero[2][DI];
-    fmq_in_zero_state<LI1, FOI>(cin, in, sp.F, sp.cnt, hi, hq, e);
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int i = 0; i < DI; ++i) {
-            qi[a][i] = e[a][i];
-            zero[a][i] = 0.0f;
-        }
-    fmq_block_scan<DI, 2>(qi, cin, lane_in, zero, tot_in);
-    float *mine = stash + threadIdx.x * (2 * DI + 2);
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int i = 0; i < DI; ++i) mine[a * DI + i] = qi[a][i];
-    mine[2 * DI] = hi;
-    mine[2 * DI + 1] = hq;
-    if (sp.last) { /* exactly one thread: the end state of the tile from a zero state */
-        float E[2][DI];
-        fmq_span_end<DI>(apow_in, sp.cnt, qi[0], e[0], E[0]);
-        fmq_span_end<DI>(apow_in, sp.cnt, qi[1], e[1], E[1]);
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-            for (int i = 0; i < DI; ++i) e_s[a * DI + i] = E[a][i];
-        if (tile != 0u) { /* tile 0 goes straight to its true end state */
-#pragma unroll
-            for (int a = 0; a < 2; ++a)
-#pragma unroll
-                for (int i = 0; i < DI; ++i) lb.E[((size_t) tile * 2 + a) * DI + i] = E[a][i];
-            __threadfence();
-            atomicExch(lb.flag + tile, 1u);
-        }
-    }
-}
-
 template <int NIN, int NOUT> /* degrees of the input (0 = none) and output cascades */
 __global__ void __launch_bounds__(FMQ_THREADS, FMQ_MINB)
 fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const FmqGeom g, const fmq_consts cin,
@@ -484,65 +434,68 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     __shared__ float ck[FMQ_T * DO];
     __shared__ float tot_in[FMQ_WARPS * 2 * DI];
     __shared__ float tot_out[FMQ_WARPS * DO];
-    __shared__ float stash[LIN > 0 ? FMQ_THREADS * (2 * DI + 2) : 1];
-    __shared__ float e_s[2][2 * DI];                   /* E of the tile in phase A / of the current tile */
-    __shared__ unsigned ticket_s;
+
+    __shared__ unsigned tile_s;
     __shared__ float carry_s[2 * DI];
-
+    /* tiles in ticket order: a tile's predecessors have all started (the look-back relies on it) */
+    if (threadIdx.x == 0) tile_s = LIN > 0 ? atomicAdd(lb.ticket, 1u) : blockIdx.x;
     for (unsigned i = threadIdx.x; i < FMQ_T * DO; i += FMQ_THREADS) ck[i] = __ldg(ck_out + i);
-
-    /*
-     * Without the input cascade: one tile per CTA, tile = blockIdx.x.
-     * With it: persistent CTAs, tiles in atomic-ticket order (a tile's predecessors have all started:
-     * the look-back relies on it), software-pipelined -- phase A of the NEXT tile runs before the
-     * look-back of the current one, so that by the time a tile looks back, the end states (E) of
-     * its predecessors have long been published and the look-back does not wait for them.
-     */
-    unsigned tile, par = 0;
-    if (LIN > 0) {
-        if (threadIdx.x == 0) ticket_s = atomicAdd(lb.ticket, 1u);
-        __syncthreads();
-        tile = ticket_s;
-        if (tile < g.ntiles) fmq_phase_a<LI1, FOI>(in, g, cin, lane_in, apow_in, lb, st, tile, tot_in, stash, e_s[0]);
-    } else {
-        tile = blockIdx.x;
-    }
-
-    while (tile < g.ntiles) {
+    __syncthreads();
+    const unsigned tile = tile_s;
     const FmqSpan sp = fmq_span(g, tile);
+
     const bool full = sp.cnt == FMQ_T;
     float hi, hq;
-    unsigned next_tile = g.ntiles;
+    fmq_halo(in, st, sp.F, sp.cnt, hi, hq);
 
     /* input cascade: state at F-1 */
     float qi[2][DI];
     if (LIN > 0) {
-        __syncthreads(); /* phase A of this tile is complete: stash and e_s[par] are visible */
-        {
-            const float *mine = stash + threadIdx.x * (2 * DI + 2);
+        float e[2][DI], zero[2][DI];
+        fmq_in_zero_state<LI1, FOI>(cin, in, sp.F, sp.cnt, hi, hq, e);
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int i = 0; i < DI; ++i) {
+                qi[a][i] = e[a][i];
+                zero[a][i] = 0.0f;
+            }
+        /* relative to a zero state at the tile start ... */
+        fmq_block_scan<DI, 2>(qi, cin, lane_in, zero, tot_in);
+        /* ... which gives the tile's end state from a zero state (E, held by the last thread with
+         * samples).  Its warp publishes E, finds the true state at the tile start by look-back,
+         * publishes the true end state S. */
+        const unsigned tile_samples = min((unsigned) FMQ_TILE, g.n - sp.S);
+        const unsigned last_t = (tile_samples + FMQ_T - 1u) / FMQ_T - 1u;
+        if ((threadIdx.x >> 5) == (last_t >> 5)) {
+            const unsigned lane = threadIdx.x & 31u, src_lane = last_t & 31u;
+            float E[2][DI], q0[2][DI];
 #pragma unroll
             for (int a = 0; a < 2; ++a)
 #pragma unroll
-                for (int i = 0; i < DI; ++i) qi[a][i] = mine[a * DI + i];
-            hi = mine[2 * DI];
-            hq = mine[2 * DI + 1];
-        }
-        if (threadIdx.x == 0) ticket_s = atomicAdd(lb.ticket, 1u);
-        __syncthreads(); /* everybody has read its stash; the next ticket is visible */
-        next_tile = ticket_s;
-        if (next_tile < g.ntiles)
-            fmq_phase_a<LI1, FOI>(in, g, cin, lane_in, apow_in, lb, st, next_tile, tot_in, stash, e_s[par ^ 1u]);
-
-        /* one warp finds the true state at the start of the current tile and publishes its true end state */
-        if (threadIdx.x < 32u) {
-            const unsigned lane = threadIdx.x;
-            float q0[2][DI];
+                for (int i = 0; i < DI; ++i) E[a][i] = 0.0f;
+            if (sp.last) {
+                fmq_span_end<DI>(apow_in, sp.cnt, qi[0], e[0], E[0]);
+                fmq_span_end<DI>(apow_in, sp.cnt, qi[1], e[1], E[1]);
+            }
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int i = 0; i < DI; ++i) E[a][i] = __shfl_sync(0xffffffffu, E[a][i], src_lane);
             if (tile == 0u) {
 #pragma unroll
                 for (int a = 0; a < 2; ++a)
 #pragma unroll
                     for (int i = 0; i < DI; ++i) q0[a][i] = st->in_q[a * DI + i];
             } else {
+                if (lane == 0u) {
+#pragma unroll
+                    for (int a = 0; a < 2; ++a)
+#pragma unroll
+                        for (int i = 0; i < DI; ++i) lb.E[((size_t) tile * 2 + a) * DI + i] = E[a][i];
+                    __threadfence();
+                    atomicExch(lb.flag + tile, 1u);
+                }
                 fmq_lookback<DI>(lb, tile, lane, lane_tile_in, wtile_in, q0, &st->error);
             }
             const bool final_tile = tile + 1u == g.ntiles;
@@ -551,7 +504,7 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
                 for (int a = 0; a < 2; ++a)
 #pragma unroll
                     for (int i = 0; i < DI; ++i) {
-                        float acc = e_s[par][a * DI + i];
+                        float acc = E[a][i];
 #pragma unroll
                         for (int k = 0; k < DI; ++k)
                             acc = fmaf(final_tile ? plast_in.m[i * DI + k] : cin.tile[i * DI + k], q0[a][k], acc);
@@ -600,9 +553,6 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
                     qi[1][i] = fmaf(m, wq[1][k], qi[1][i]);
                 }
         }
-    } else {
-        __syncthreads(); /* ck is loaded */
-        fmq_halo(in, st, sp.F, sp.cnt, hi, hq);
     }
 
     /* kept samples of this thread: offset of the first one in its span, and its slot in ybuf */
@@ -710,10 +660,6 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
         for (int i = 0; i < DO; ++i) y = fmaf(ck[k * DO + i], qs[owner * DO + i], y);
         out[o_tile + o] = y;
     }
-    tile = next_tile;
-    par ^= 1u;
-    __syncthreads(); /* ybuf, qs and the scan scratch are free for the next tile */
-    } /* while (tile < g.ntiles) */
 }
 
 /* ------------------------------------------- tile-level zero-input response on the kept samples */

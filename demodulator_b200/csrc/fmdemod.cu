@@ -687,14 +687,11 @@ static int quality_launch(fmd_ctx *c, const uint8_t *d_in, unsigned n, float *d_
         pe = &c->pev[2 * c->pev_used++];
         FMD_CUDA(cudaEventRecord(pe[0], s));
     }
-    if (smem > 48u * 1024u && !q->smem_opted_in) { /* M = 1 keeps a whole tile: 64 KiB */
+    if (!q->smem_opted_in) { /* static + dynamic shared memory may pass 48 KiB for small M (M = 1 keeps a whole tile) */
         FMD_CUDA(cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         q->smem_opted_in = true;
     }
-    /* with the input cascade the CTAs are persistent (tiles by ticket, software-pipelined) */
-    const unsigned resident = (unsigned) c->sm_count * FMQ_MINB;
-    const unsigned grid = (q->lin && g.ntiles > resident) ? resident : g.ntiles;
-    fn<<<grid, FMQ_THREADS, smem, s>>>(d_in, d_out, g, q->lin ? q->fin.c : q->fout.c, q->fout.c,
+    fn<<<g.ntiles, FMQ_THREADS, smem, s>>>(d_in, d_out, g, q->lin ? q->fin.c : q->fout.c, q->fout.c,
                                            q->lin ? q->fin.lane() : nullptr, q->fout.lane(), q->fout.apow(),
                                            q->fout.ck(), q->lin ? q->fin.apow() : nullptr,
                                            q->lin ? q->fin.lane_tile() : nullptr, lb, pl_in, wtile_in, q->d_eout, q->d_state);

@@ -29,19 +29,11 @@ for c in quality_cfg3 quality_cfg1 quality_cfg2 quality_m1; do
   timeout 300 python tools/qbench.py --config $c > gpurun_out/qbench_$c.json 2> gpurun_out/qbench_$c.err || tail -5 gpurun_out/qbench_$c.err
   QB qbench_$c
 done
-if [ -f variants/t64/libfmdemod.so ]; then
-  FMD_LIB=$PWD/variants/t64/libfmdemod.so timeout 600 python -m pytest tests/test_quality_gpu.py -m gpu -q 2>&1 | tail -3
-  for c in quality_cfg3 quality_cfg2; do
-    FMD_LIB=$PWD/variants/t64/libfmdemod.so timeout 300 python tools/qbench.py --config $c --no-cpu --no-e2e > gpurun_out/qbench_${c}_t64.json 2> gpurun_out/qbench_${c}_t64.err
-    QB qbench_${c}_t64
-  done
-fi
 for c in quality_cfg3 quality_cfg2; do
   CMD="python tools/qbench.py --config $c --steps 2 --warmup 3 --no-cpu --no-e2e"
   $CMD > gpurun_out/qplain_$c.log 2>&1 || { tail -5 gpurun_out/qplain_$c.log; continue; }
   ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/qlaunches_$c.csv $CMD > gpurun_out/qncu_list_$c.log 2>&1
-  for k in fmq_main fmq_in_aggregate; do
-    [ $k = fmq_in_aggregate ] && [ $c = quality_cfg3 ] && continue
+  for k in fmq_main; do
     ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o /tmp/qprof_${c}_$k $CMD > gpurun_out/qncu_full_${c}_$k.log 2>&1
     ncu -i /tmp/qprof_${c}_$k.ncu-rep --page raw --csv > gpurun_out/qprof_${c}_${k}_raw.csv 2>/dev/null
     ncu -i /tmp/qprof_${c}_$k.ncu-rep --page details > gpurun_out/qprof_${c}_${k}_details.txt 2>/dev/null

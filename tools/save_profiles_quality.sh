@@ -6,7 +6,7 @@ for c in quality_cfg1 quality_cfg2 quality_cfg3 quality_m1; do cp gpurun_out/qbe
 cp gpurun_out/quality_cli_stream.txt profiles/${R}_quality_cli_stream.txt 2>/dev/null
 for c in quality_cfg3 quality_cfg2; do
   cp gpurun_out/qlaunches_$c.csv profiles/${R}_quality_launches_$c.csv
-  for k in fmq_main fmq_in_aggregate; do
+  for k in fmq_main; do
     [ -f gpurun_out/qprof_${c}_${k}_raw.csv ] || continue
     cp gpurun_out/qprof_${c}_${k}_raw.csv profiles/${R}_${k}_${c}_raw.csv
     cp gpurun_out/qprof_${c}_${k}_details.txt profiles/${R}_${k}_${c}_details.txt
@@ -38,7 +38,7 @@ KEYS = ['gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum',
  'sm__throughput.avg.pct_of_peak_sustained_elapsed','dram__cycles_active.avg.pct_of_peak_sustained_elapsed']
 STALL = 'smsp__average_warps_issue_stalled_'
 import os
-for f in ("fmq_main_quality_cfg3", "fmq_main_quality_cfg2", "fmq_in_aggregate_quality_cfg2"):
+for f in ("fmq_main_quality_cfg3", "fmq_main_quality_cfg2"):
     p = f"profiles/${R}_{f}_raw.csv"
     if not os.path.exists(p): continue
     rows = list(csv.reader(open(p)))
