@@ -408,9 +408,9 @@ __device__ __forceinline__ void fmq_discriminate2(float pr, float pi, float z0r,
     fmd_atan2_x2<8>(fmd_pk(im0, im1), fmd_pk(re0, re1), x0, x1);
 }
 
-/* kept samples of thread t start at slot t*T/M: one word of padding per 32 keeps those starts on
- * different shared-memory banks (M = 2 had 80 M bank conflicts per launch without it) */
-#define FMQ_PAD(o) ((o) + ((o) >> 5))
+/* Kept samples of thread t start at slot t*T/M and are stored at (slot + t): one word of padding
+ * per owning thread keeps the threads of a warp on different shared-memory banks (M = 2 had 80 M
+ * bank conflicts per launch without padding) and leaves the writer a plain post-increment. */
 
 #ifndef FMQ_MINB
 #define FMQ_MINB (1024 / FMQ_THREADS) /* resident CTAs per SM the register budget of the main kernel is cut for: 32 warps */
@@ -557,12 +557,13 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
 
     /* kept samples of this thread: offset of the first one in its span, and its slot in ybuf */
     const unsigned o_tile = fmq_kept_below(sp.S, g.r0, g.decim);
-    unsigned next, slot;
+    unsigned next;
+    float *yp; /* where this thread's next kept sample goes */
     {
         const unsigned o_first = fmq_kept_below(sp.F, g.r0, g.decim);
         const unsigned long long kfirst = (unsigned long long) g.r0 + (unsigned long long) o_first * g.decim;
         next = kfirst - sp.F >= (unsigned long long) FMQ_T ? 0xffffffffu : (unsigned) (kfirst - sp.F);
-        slot = o_first - o_tile;
+        yp = ybuf + (o_first - o_tile) + threadIdx.x;
     }
 
     /* second pass: z (from the right state), x, v from a zero state; v kept every M-th sample */
@@ -603,14 +604,12 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
                 pi = z1i;
                 const float v0 = fmq_step<LOUT, FOO>(cout, eo, x0);
                 if (i0 + (unsigned) i == next) {
-                    ybuf[FMQ_PAD(slot)] = v0;
-                    ++slot;
+                    *yp++ = v0;
                     next += g.decim;
                 }
                 const float v1 = fmq_step<LOUT, FOO>(cout, eo, x1);
                 if (i0 + (unsigned) (i + 1) == next) {
-                    ybuf[FMQ_PAD(slot)] = v1;
-                    ++slot;
+                    *yp++ = v1;
                     next += g.decim;
                 }
             }
@@ -629,8 +628,7 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
             pi = zi;
             const float v = fmq_step<LOUT, FOO>(cout, eo, fmd_atan2(im, re));
             if (i == next) {
-                ybuf[FMQ_PAD(slot)] = v;
-                ++slot;
+                *yp++ = v;
                 next += g.decim;
             }
         }
@@ -655,7 +653,7 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     for (unsigned o = threadIdx.x; o < count; o += FMQ_THREADS) {
         const unsigned ks = (unsigned) ((unsigned long long) g.r0 + (unsigned long long) (o_tile + o) * g.decim - sp.S);
         const unsigned owner = ks / FMQ_T, k = ks % FMQ_T;
-        float y = ybuf[FMQ_PAD(o)];
+        float y = ybuf[o + owner];
 #pragma unroll
         for (int i = 0; i < DO; ++i) y = fmaf(ck[k * DO + i], qs[owner * DO + i], y);
         out[o_tile + o] = y;

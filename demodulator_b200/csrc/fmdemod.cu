@@ -677,7 +677,7 @@ static int quality_launch(fmd_ctx *c, const uint8_t *d_in, unsigned n, float *d_
     /* shared memory for the kept samples of one tile */
     const unsigned keep_cap = FMQ_TILE / q->decim + 2u;
     const unsigned keep = keep_cap < FMQ_TILE ? keep_cap : FMQ_TILE;
-    const size_t smem = (size_t) (keep + (keep >> 5) + 1u) * sizeof(float); /* FMQ_PAD */
+    const size_t smem = (size_t) (keep + FMQ_THREADS) * sizeof(float); /* one pad word per owning thread */
     cudaEvent_t *pe = nullptr;
     if (c->profile) {
         if (c->pev_used == c->pev_cap) {
