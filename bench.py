@@ -56,6 +56,7 @@ CLI_FLAGS = {
     "cfg2": ["-S96000", "-l6500", "-L12500"],
     "cfg3": ["-S48000", "-l15000"],
 }
+QUALITY_CONFIGS = ["quality_cfg1", "quality_cfg2", "quality_cfg3", "quality_m1"]
 WORKLOAD = {
     "cfg1": "synthetic u8 IQ FM tone 192 kS/s, -S96000 -l12500, no input lowpass",
     "cfg2": "synthetic u8 IQ FM tone 192 kS/s, -L12500 -l6500 -S96000 (input + output lowpass)",
@@ -480,11 +481,20 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=sorted(FLAGS))
+    ap.add_argument("--config", default="cfg2", choices=sorted(FLAGS) + QUALITY_CONFIGS,
+                    help="cfg1..cfg3: the reference-compatible path (BASELINE.json configs[0..2]); quality_*: "
+                         "the opt-in quality pipeline, one stream on one GPU (handed to tools/qbench.py)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--per-channel-launch", action="store_true",
                     help="one call per channel instead of one call for the GPU's whole batch of channels")
     args = ap.parse_args()
+    if args.config in QUALITY_CONFIGS:
+        # not a BASELINE.json workload: same JSON shape, measured by tools/qbench.py (rank 0 only)
+        if int(os.environ.get("RANK", "0")) != 0 or args.impl == "reference":
+            return
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "qbench.py"), "--config", args.config,
+               "--steps", str(args.steps), "--warmup", str(args.warmup)] + (["--no-cpu"] if args.no_cpu else [])
+        sys.exit(subprocess.call(cmd))
     # stdout carries exactly ONE JSON line: anything a library prints meanwhile (NCCL's version
     # banner, torchrun chatter) is sent to stderr
     sys.stdout.flush()
