@@ -27,3 +27,18 @@ for name in GOLDEN_CASES + ["edge", "edge_L"]:
             es = err
         snr = 10 * np.log10((want[m].astype(np.float64) ** 2).sum() / max((err ** 2).sum(), 1e-300))
         print(f"{name:10s} {'exact' if exact else 'fast '}: max-abs {err.max():.3e} (steady state {es.max():.3e}, p99.99 {np.quantile(es, 0.9999):.2e})  SNR {snr:6.1f} dB  |out|max {np.abs(want[m]).max():.3g}")
+
+# ---- the opt-in quality pipeline against its serial double-precision oracle (pinned to scipy fixtures) ----
+from test_quality_oracle import QUALITY_CASES, load_quality
+print("\nquality pipeline (FMD_FLAG_QUALITY) vs oracle/fm_quality_oracle.c:")
+for name in QUALITY_CASES:
+    g, cfg, raw, rate = load_quality(name)
+    want = po.port().quality(cfg, rate).run(raw)
+    with fm.Demodulator(sampleRate=cfg.fs, lowpassIn=cfg.fc_in, lowpassOut=cfg.fc_out, epsilon=cfg.eps,
+                        inFilterDegree=cfg.deg_in, outFilterDegree=cfg.deg_out, mode=cfg.mode, quality=True,
+                        inputRate=rate) as d:
+        out = np.concatenate([d.process(raw[: 2 * 100003]), d.process(raw[2 * 100003:])]) if raw.size > 2 * 100003 else d.process(raw)
+    err = np.abs(out.astype(np.float64) - want)
+    snr = 10 * np.log10((want.astype(np.float64) ** 2).sum() / max((err ** 2).sum(), 1e-300))
+    print(f"{name:14s}: {out.size:7d} floats (M = {int(g['decim'])}), max-abs {err.max():.3e}, p99.99 {np.quantile(err, 0.9999):.2e}, "
+          f"SNR {snr:6.1f} dB, |out|max {np.abs(want).max():.3g}")
