@@ -39,7 +39,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "fmd_kernels.cuh"
+#include "fmd_math.cuh"
 #include "fmd_quality.h"
 
 /* the carry between calls (one per context, device memory) */

@@ -18,9 +18,8 @@
 #include <cstring>
 #include <new>
 
-#include "fmd_internal.h"
+#include "fmd_ctx.h"
 #include "fmd_kernels.cuh"
-#include "fmd_quality.cuh"
 
 /* ------------------------------------------------------------------ errors */
 
@@ -36,83 +35,7 @@ extern "C" int fmd_set_error(int code, const char *fmt, ...) {
 
 extern "C" const char *fmd_last_error(void) { return g_err; }
 
-#define FMD_CUDA(call)                                                                              \
-    do {                                                                                            \
-        cudaError_t e__ = (call);                                                                   \
-        if (e__ != cudaSuccess)                                                                     \
-            return fmd_set_error(FMD_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
-                                 __FILE__, __LINE__);                                               \
-    } while (0)
-
 /* ----------------------------------------------------------------- context */
-
-struct fmd_ctx;
-static int quality_setup(fmd_ctx *c, unsigned decim);
-static void quality_free(fmd_ctx *c);
-static size_t quality_out_count(unsigned long long pos, size_t nsamp, unsigned M);
-
-struct fmd_slot {
-    uint8_t *d_in = nullptr;
-    float *d_out = nullptr;
-    cudaEvent_t ev_in = nullptr;   /* H2D landed              */
-    cudaEvent_t ev_k = nullptr;    /* kernels done            */
-    cudaEvent_t ev_out = nullptr;  /* D2H landed              */
-    bool busy = false;
-};
-
-/* one cascade of the quality pipeline: host design + constants + device tables */
-struct fmq_filter {
-    fmq_design des;
-    fmq_consts c;      /* scan over the threads of a CTA (unit T)   */
-    fmq_consts c_tile; /* scan over the tiles of a launch (unit TILE) */
-    fmq_table_sizes sz;
-    unsigned zir_len = FMQ_TILE; /* tile offsets whose zero-input response is not negligible */
-    float *d_tab = nullptr; /* lane | apow | ck | ckn | lane_tile */
-    const float *lane() const { return d_tab; }
-    const float *apow() const { return d_tab + sz.lane; }
-    const float *ck() const { return d_tab + sz.lane + sz.apow; }
-    const float *ckn() const { return d_tab + sz.lane + sz.apow + sz.ck; }
-    const float *lane_tile() const { return d_tab + sz.lane + sz.apow + sz.ck + sz.ckn; }
-};
-
-/* FMD_FLAG_QUALITY state of a context (fmd_quality.cuh) */
-struct fmq_ctx {
-    unsigned decim = 1;
-    unsigned lin = 0, lout = 0; /* sections */
-    fmq_filter fin, fout;
-    FmqState *d_state = nullptr;
-    float *d_ein = nullptr, *d_qin = nullptr, *d_eout = nullptr, *d_qout = nullptr; /* per-tile scratch */
-    unsigned *d_lb = nullptr; /* look-back ticket + per-tile flags */
-    unsigned tile_cap = 0;
-    bool smem_opted_in = false;
-    unsigned long long pos = 0; /* stream position: global index of the next input sample */
-};
-
-struct fmd_ctx {
-    fmd_config cfg;
-    fmq_ctx *q = nullptr;
-    int device = 0;
-    unsigned lin = 0, lout = 0;
-    FmdSections sec;
-    FmdSections *d_sec = nullptr; /* device copy, read by the exact path */
-    FmdStencil st;
-    unsigned nti = 0, nto = 0;
-    unsigned atan_terms = 6;
-    bool fast_in_ok = true; /* input stencil could be normalised by its first tap */
-    unsigned head = 0; /* outputs at the start of every chunk that are not in steady state */
-    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
-    fmd_slot *slots = nullptr;
-    unsigned nslots = 0;
-    size_t slot_bytes = 0;
-    uint64_t launches = 0;
-    int sm_count = 148;
-    /* optional per-launch event timing of the fast kernel */
-    bool profile = false;
-    cudaEvent_t *pev = nullptr; /* pairs: [2*i] before, [2*i+1] after */
-    unsigned pev_used = 0, pev_cap = 0;
-    double prof_ms = 0.0;
-    uint64_t prof_n = 0;
-};
 
 static int prof_flush(fmd_ctx *c) {
     for (unsigned i = 0; i < c->pev_used; ++i) {
@@ -123,6 +46,17 @@ static int prof_flush(fmd_ctx *c) {
         c->prof_n++;
     }
     c->pev_used = 0;
+    return FMD_OK;
+}
+
+int fmd_prof_events(fmd_ctx *c, cudaEvent_t **pe) {
+    *pe = nullptr;
+    if (!c->profile) return FMD_OK;
+    if (c->pev_used == c->pev_cap) {
+        int rc = prof_flush(c);
+        if (rc) return rc;
+    }
+    *pe = &c->pev[2 * c->pev_used++];
     return FMD_OK;
 }
 
@@ -302,7 +236,7 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
         return fmd_set_error(FMD_ECUDA, "coefficient upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     if (quality) {
-        rc = quality_setup(c, q_decim);
+        rc = fmq_setup(c, q_decim);
         if (rc) {
             fmd_destroy(c);
             return rc;
@@ -338,7 +272,7 @@ extern "C" void fmd_destroy(fmd_ctx *c) {
         delete[] c->pev;
     }
     if (c->d_sec) cudaFree(c->d_sec);
-    quality_free(c);
+    fmq_free(c);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_k) cudaStreamDestroy(c->s_k);
     if (c->s_out) cudaStreamDestroy(c->s_out);
@@ -387,12 +321,12 @@ extern "C" int fmd_host_unregister(void *ptr) {
 /* ---------------------------------------------------------------- launching */
 
 extern "C" size_t fmd_out_count(const fmd_ctx *c, size_t nbytes) {
-    if (c && c->q) return quality_out_count(c->q->pos, nbytes / 2, c->q->decim);
+    if (c && c->q) return fmq_out_count(c, nbytes / 2);
     return nbytes >> 2; /* whole chunks give B/4 each; the ragged tail gives r/4 */
 }
 
 extern "C" size_t fmd_max_out_count(const fmd_ctx *c, size_t nbytes) {
-    if (c && c->q) return quality_out_count(0, nbytes / 2, c->q->decim);
+    if (c && c->q) return fmq_max_out_count(c, nbytes / 2);
     return nbytes >> 2;
 }
 
@@ -525,233 +459,9 @@ static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned
 }
 
 
-/* ------------------------------------------------------------ quality pipeline (opt-in) */
-
-static int quality_upload_filter(fmq_filter &f, const float *sos6, unsigned sections) {
-    int rc = fmq_design_from_sos(sos6, sections, &f.des);
-    if (rc) return rc;
-    fmq_build_consts(&f.des, FMQ_T, &f.c);
-    fmq_build_consts(&f.des, FMQ_TILE, &f.c_tile);
-    fmq_table_layout(&f.des, &f.sz);
-    const size_t n = (size_t) f.sz.lane + f.sz.apow + f.sz.ck + f.sz.ckn + f.sz.lane_tile;
-    float *h = (float *) malloc(n * sizeof(float));
-    if (!h) return fmd_set_error(FMD_ENOMEM, "out of host memory");
-    f.zir_len = fmq_build_tables(&f.des, h, h + f.sz.lane, h + f.sz.lane + f.sz.apow, h + f.sz.lane + f.sz.apow + f.sz.ck,
-                                 h + f.sz.lane + f.sz.apow + f.sz.ck + f.sz.ckn);
-    cudaError_t e = cudaMalloc(&f.d_tab, n * sizeof(float));
-    if (e == cudaSuccess) e = cudaMemcpy(f.d_tab, h, n * sizeof(float), cudaMemcpyHostToDevice);
-    free(h);
-    if (e != cudaSuccess) return fmd_set_error(FMD_ECUDA, "quality table upload failed: %s", cudaGetErrorString(e));
-    return FMD_OK;
-}
-
-static int quality_setup(fmd_ctx *c, unsigned decim) {
-    fmq_ctx *q = new (std::nothrow) fmq_ctx();
-    if (!q) return fmd_set_error(FMD_ENOMEM, "out of host memory");
-    c->q = q;
-    q->decim = decim;
-    q->lout = c->lout;
-    q->lin = c->lin;
-    int rc = quality_upload_filter(q->fout, &c->sec.out[0][0], q->lout);
-    if (!rc && q->lin) rc = quality_upload_filter(q->fin, &c->sec.in[0][0], q->lin);
-    if (rc) return rc;
-    /* the kernels for odd degrees skip the second state of the last (first-order) section */
-    if (((c->cfg.out_degree & 1u) && (c->sec.out[q->lout - 1][2] != 0.0f || c->sec.out[q->lout - 1][5] != 0.0f)) ||
-        (q->lin && (c->cfg.in_degree & 1u) && (c->sec.in[q->lin - 1][2] != 0.0f || c->sec.in[q->lin - 1][5] != 0.0f)))
-        return fmd_set_error(FMD_EINVAL, "odd-degree design whose last section is not first order");
-    FMD_CUDA(cudaMalloc(&q->d_state, sizeof(FmqState)));
-    FMD_CUDA(cudaMemset(q->d_state, 0, sizeof(FmqState)));
-    return FMD_OK;
-}
-
-static void quality_free(fmd_ctx *c) {
-    fmq_ctx *q = c->q;
-    if (!q) return;
-    if (q->fin.d_tab) cudaFree(q->fin.d_tab);
-    if (q->fout.d_tab) cudaFree(q->fout.d_tab);
-    if (q->d_state) cudaFree(q->d_state);
-    if (q->d_ein) cudaFree(q->d_ein);
-    if (q->d_qin) cudaFree(q->d_qin);
-    if (q->d_eout) cudaFree(q->d_eout);
-    if (q->d_qout) cudaFree(q->d_qout);
-    if (q->d_lb) cudaFree(q->d_lb);
-    delete q;
-    c->q = nullptr;
-}
-
-static int quality_reserve_tiles(fmq_ctx *q, unsigned ntiles) {
-    if (ntiles <= q->tile_cap) return FMD_OK;
-    /* cudaFree waits for the kernels that may still read the old scratch */
-    if (q->d_ein) cudaFree(q->d_ein);
-    if (q->d_qin) cudaFree(q->d_qin);
-    if (q->d_eout) cudaFree(q->d_eout);
-    if (q->d_qout) cudaFree(q->d_qout);
-    if (q->d_lb) cudaFree(q->d_lb);
-    q->d_lb = nullptr;
-    q->d_ein = q->d_qin = q->d_eout = q->d_qout = nullptr;
-    q->tile_cap = 0;
-    const unsigned cap = ntiles < 4096u ? 4096u : ntiles;
-    const size_t per_in = (size_t) cap * 2 * FMQ_MAXD * sizeof(float), per_out = (size_t) cap * FMQ_MAXD * sizeof(float);
-    FMD_CUDA(cudaMalloc(&q->d_ein, per_in));
-    FMD_CUDA(cudaMalloc(&q->d_qin, per_in));
-    FMD_CUDA(cudaMalloc(&q->d_eout, per_out));
-    FMD_CUDA(cudaMalloc(&q->d_qout, per_out));
-    FMD_CUDA(cudaMalloc(&q->d_lb, ((size_t) cap + 1u) * sizeof(unsigned)));
-    q->tile_cap = cap;
-    return FMD_OK;
-}
-
-/* outputs of the next `nsamp` samples when the stream stands at `pos` */
-static size_t quality_out_count(unsigned long long pos, size_t nsamp, unsigned M) {
-    const unsigned long long r0 = (M - pos % M) % M;
-    return nsamp > r0 ? (size_t) ((nsamp - r0 + M - 1) / M) : 0;
-}
-
-typedef void (*fmq_main_fn)(const uint8_t *, float *, const FmqGeom, const fmq_consts, const fmq_consts, const float *,
-                            const float *, const float *, const float *, const float *, const float *,
-                            const FmqLookback, const FmqMat, const FmqMat, float *, FmqState *);
-
-template <int NIN>
-static fmq_main_fn quality_pick_out(unsigned nout) {
-    switch (nout) {
-        case 1: return fmq_main_kernel<NIN, 1>;
-        case 2: return fmq_main_kernel<NIN, 2>;
-        case 3: return fmq_main_kernel<NIN, 3>;
-        case 4: return fmq_main_kernel<NIN, 4>;
-        case 5: return fmq_main_kernel<NIN, 5>;
-        case 6: return fmq_main_kernel<NIN, 6>;
-        default: return nullptr;
-    }
-}
-
-/* by filter DEGREE: an odd degree ends in a first-order section, which the kernels exploit */
-static fmq_main_fn quality_pick_main(unsigned nin, unsigned nout) {
-    switch (nin) {
-        case 0: return quality_pick_out<0>(nout);
-        case 1: return quality_pick_out<1>(nout);
-        case 2: return quality_pick_out<2>(nout);
-        case 3: return quality_pick_out<3>(nout);
-        case 4: return quality_pick_out<4>(nout);
-        case 5: return quality_pick_out<5>(nout);
-        case 6: return quality_pick_out<6>(nout);
-        default: return nullptr;
-    }
-}
-
-/* one launch group: `n` samples (< 2^31) that continue the stream; *nout = floats written */
-static int quality_launch(fmd_ctx *c, const uint8_t *d_in, unsigned n, float *d_out, cudaStream_t s, size_t *nout) {
-    fmq_ctx *q = c->q;
-    FmqGeom g;
-    g.n = n;
-    g.ntiles = (n + FMQ_TILE - 1) / FMQ_TILE;
-    g.decim = q->decim;
-    g.r0 = (unsigned) ((q->decim - q->pos % q->decim) % q->decim);
-    g.n_out = (unsigned) quality_out_count(q->pos, n, q->decim);
-    *nout = g.n_out;
-    int rc = quality_reserve_tiles(q, g.ntiles);
-    if (rc) return rc;
-    const unsigned len_last = n - (g.ntiles - 1u) * FMQ_TILE;
-    /* the scan over tiles: 32 warps, each a run of `runlen` tiles (a multiple of 32) */
-    const unsigned nwarps = FMQ_SCAN_THREADS / 32;
-    const unsigned runlen = ((g.ntiles + nwarps - 1u) / nwarps + 31u) & ~31u;
-    FmqMat prun, pl;
-
-    FmqLookback lb = {nullptr, nullptr, nullptr, nullptr};
-    FmqMat pl_in, wtile_in;
-    memset(&pl_in, 0, sizeof pl_in);
-    memset(&wtile_in, 0, sizeof wtile_in);
-    if (q->lin) {
-        /* the input cascade's carry travels between the tiles INSIDE the main kernel (look-back):
-         * ticket + one flag per tile, cleared per launch; E and S records per tile */
-        FMD_CUDA(cudaMemsetAsync(q->d_lb, 0, ((size_t) g.ntiles + 1u) * sizeof(unsigned), s));
-        lb.ticket = q->d_lb;
-        lb.flag = q->d_lb + 1;
-        lb.E = q->d_ein;
-        lb.S = q->d_qin;
-        fmq_matpow_f(&q->fin.des, len_last, pl_in.m);
-        memcpy(wtile_in.m, q->fin.c_tile.warp, sizeof wtile_in.m); /* A^(32 TILE): one look-back round */
-    }
-
-    fmq_main_fn fn = quality_pick_main(q->lin ? c->cfg.in_degree : 0u, c->cfg.out_degree);
-    if (!fn) return fmd_set_error(FMD_EINVAL, "no quality kernel for degrees %u/%u", c->cfg.in_degree, c->cfg.out_degree);
-    /* shared memory for the kept samples of one tile */
-    const unsigned keep_cap = FMQ_TILE / q->decim + 2u;
-    const unsigned keep = keep_cap < FMQ_TILE ? keep_cap : FMQ_TILE;
-    const size_t smem = (size_t) (keep + FMQ_THREADS) * sizeof(float); /* one pad word per owning thread */
-    cudaEvent_t *pe = nullptr;
-    if (c->profile) {
-        if (c->pev_used == c->pev_cap) {
-            rc = prof_flush(c);
-            if (rc) return rc;
-        }
-        pe = &c->pev[2 * c->pev_used++];
-        FMD_CUDA(cudaEventRecord(pe[0], s));
-    }
-    if (!q->smem_opted_in) { /* static + dynamic shared memory may pass 48 KiB for small M (M = 1 keeps a whole tile) */
-        FMD_CUDA(cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        q->smem_opted_in = true;
-    }
-    fn<<<g.ntiles, FMQ_THREADS, smem, s>>>(d_in, d_out, g, q->lin ? q->fin.c : q->fout.c, q->fout.c,
-                                           q->lin ? q->fin.lane() : nullptr, q->fout.lane(), q->fout.apow(),
-                                           q->fout.ck(), q->lin ? q->fin.apow() : nullptr,
-                                           q->lin ? q->fin.lane_tile() : nullptr, lb, pl_in, wtile_in, q->d_eout, q->d_state);
-    FMD_CUDA(cudaGetLastError());
-    if (pe) FMD_CUDA(cudaEventRecord(pe[1], s));
-
-    memset(&prun, 0, sizeof prun);
-    memset(&pl, 0, sizeof pl);
-    fmq_matpow_f(&q->fout.des, (unsigned long long) FMQ_TILE * runlen, prun.m);
-    fmq_matpow_f(&q->fout.des, len_last, pl.m);
-    const uint8_t *last = d_in + 2ull * (n - 1u);
-    /* zero-input response of the tile carry: only the leading zir_len offsets of every tile */
-    const unsigned zl = q->fout.zir_len < FMQ_TILE ? q->fout.zir_len : FMQ_TILE;
-    const dim3 zgrid(g.ntiles, (zl / q->decim + 1u + 255u) / 256u);
-    switch (q->lout) {
-        case 1:
-            fmq_scan_tiles_kernel<2, 1><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_eout, q->d_qout, q->d_state->out_q, q->fout.c_tile, q->fout.lane_tile(), prun, pl, g.ntiles, runlen, last, q->d_state->s_prev);
-            if (g.n_out) fmq_zir_kernel<2><<<zgrid, 256, 0, s>>>(d_out, g, zl, q->fout.ckn(), q->d_qout);
-            break;
-        case 2:
-            fmq_scan_tiles_kernel<4, 1><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_eout, q->d_qout, q->d_state->out_q, q->fout.c_tile, q->fout.lane_tile(), prun, pl, g.ntiles, runlen, last, q->d_state->s_prev);
-            if (g.n_out) fmq_zir_kernel<4><<<zgrid, 256, 0, s>>>(d_out, g, zl, q->fout.ckn(), q->d_qout);
-            break;
-        default:
-            fmq_scan_tiles_kernel<6, 1><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_eout, q->d_qout, q->d_state->out_q, q->fout.c_tile, q->fout.lane_tile(), prun, pl, g.ntiles, runlen, last, q->d_state->s_prev);
-            if (g.n_out) fmq_zir_kernel<6><<<zgrid, 256, 0, s>>>(d_out, g, zl, q->fout.ckn(), q->d_qout);
-            break;
-    }
-    FMD_CUDA(cudaGetLastError());
-    c->launches += g.n_out ? 3 : 2;
-    q->pos += n;
-    return FMD_OK;
-}
-
-static int quality_demod_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, float *d_out, cudaStream_t s) {
-    if (nbytes & 1u) return fmd_set_error(FMD_EINVAL, "quality mode takes whole IQ samples (an even number of bytes)");
-    if (((uintptr_t) d_in % 16) || ((uintptr_t) d_out % 4))
-        return fmd_set_error(FMD_EINVAL, "quality mode needs a 16-byte aligned input and a 4-byte aligned output");
-    size_t left = nbytes / 2;
-    const size_t step = (size_t) 1 << 30; /* a multiple of the tile: later groups stay 16-byte aligned */
-    while (left) {
-        const unsigned n = (unsigned) (left < step ? left : step);
-        size_t nout = 0;
-        int rc = quality_launch(c, d_in, n, d_out, s, &nout);
-        if (rc) return rc;
-        d_in += 2ull * n;
-        d_out += nout;
-        left -= n;
-    }
-    return FMD_OK;
-}
-
 extern "C" int fmd_reset(fmd_ctx *c) {
     if (!c) return fmd_set_error(FMD_EINVAL, "null argument");
-    if (!c->q) return FMD_OK;
-    FMD_CUDA(cudaSetDevice(c->device));
-    FMD_CUDA(cudaDeviceSynchronize());
-    FMD_CUDA(cudaMemset(c->q->d_state, 0, sizeof(FmqState)));
-    c->q->pos = 0;
-    return FMD_OK;
+    return c->q ? fmq_reset(c) : FMD_OK;
 }
 
 extern "C" int fmd_demod_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, float *d_out, void *stream) {
@@ -767,7 +477,7 @@ extern "C" int fmd_demod_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, 
     if (prev != c->device) FMD_CUDA(cudaSetDevice(c->device));
     int rc;
     if (c->q) {
-        rc = quality_demod_device(c, d_in, nbytes, d_out, s);
+        rc = fmq_demod_device(c, d_in, nbytes, d_out, s);
     } else {
         rc = launch_chunks(c, d_in, d_out, (unsigned) nfull, (unsigned) (B >> 2), B, s);
         if (!rc && rem)
@@ -852,11 +562,7 @@ extern "C" int fmd_wait(fmd_ctx *c, unsigned slot) {
     if (!s.busy) return FMD_OK;
     FMD_CUDA(cudaEventSynchronize(s.ev_out));
     s.busy = false;
-    if (c->q && c->q->lin) { /* a look-back that gave up waiting raises a device-side flag */
-        unsigned err = 0;
-        FMD_CUDA(cudaMemcpy(&err, &c->q->d_state->error, sizeof err, cudaMemcpyDeviceToHost));
-        if (err) return fmd_set_error(FMD_ECUDA, "quality pipeline: a tile gave up waiting for its predecessor's carry");
-    }
+    if (c->q) return fmq_check_error(c); /* a look-back that gave up waiting raises a device-side flag */
     return FMD_OK;
 }
 

@@ -11,8 +11,11 @@ for spec in "$@"; do
   defs=$(for f in $flags; do case $f in -D*) echo -n "$f ";; esac; done)  # gcc sees the -D flags only
   gcc -O2 -std=gnu99 -fPIC -ffp-contract=off $defs -Iinclude -Idemodulator_b200/csrc -c -o $d/fmd_quality.o demodulator_b200/csrc/fmd_quality.c
   $NVCC -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC $flags -Iinclude -Idemodulator_b200/csrc \
-      -c -o $d/fmdemod.o demodulator_b200/csrc/fmdemod.cu
-  $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $d/libfmdemod.so $d/fmdemod.o $d/fmd_design.o $d/fmd_quality.o -lm
+      -c -o $d/fmdemod.o demodulator_b200/csrc/fmdemod.cu &
+  $NVCC -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC $flags -Iinclude -Idemodulator_b200/csrc \
+      -c -o $d/fmd_quality_host.o demodulator_b200/csrc/fmd_quality_host.cu &
+  wait
+  $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o $d/libfmdemod.so $d/fmdemod.o $d/fmd_quality_host.o $d/fmd_design.o $d/fmd_quality.o -lm
   rm -f $d/*.o
   echo "built $d ($flags)"
 done
