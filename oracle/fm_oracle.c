@@ -236,70 +236,94 @@ void fmo_sweep_lane(const float *x, float *y, size_t n, size_t L, const float *s
 /* ---------------------------------------------------------- chunk pipeline */
 
 /*
- * src/matrix.c:236-273, default mode (-q0, demodulation on), one chunk.
- *
- * Without -L (:253-258): shift -> discriminate -> real sweep into a zeroed y.
- *
- * With -L (:259-270) the three float regions x | y_c | y_o are adjacent thirds
- * of one arena (x=arena, y_c=arena+B, y_o=arena+2B), which makes two overruns
- * observable: the complex sweep READS x[B+t], i.e. the already-final head of
- * y_c, and WRITES y_c[B .. B+4L-3], i.e. the head of y_o, which the real sweep
- * then uses as its initial accumulator contents.  Modelled as: (1) sweep the
- * chunk with zero extension (valid outputs never see the extension: everything
- * they read past the end is the never-rewritten zero head), (2) re-sweep just
- * the indices >= nc with the extension set to the final head, (3) seed the
- * output sweep with those values.
+ * One pass of applyComplexFilter (src/filter.c:233-259) as the reference's buffers make it behave.
+ *   xs    : B interleaved floats (nc = B/2 complex samples), the x region
+ *   init  : initial contents of the first `ninit` floats of the y region (what an earlier pass
+ *           spilled there), zero elsewhere
+ *   alias : 1 -- the y region follows the x region in the same arena (src/matrix.c:260-267), so what
+ *               the sweep READS as x[B+t] is the already-final head of y;
+ *           0 -- x is a buffer of its own whose slack is zero (highpassDc, src/matrix.c:142-157: a
+ *               calloc'd block of B floats; the reference reads a few floats past it)
+ *   ys    : B floats, the valid outputs;  spill : the 4L-2 floats the sweep WRITES past y[B-1]
+ * Modelled as: (1) sweep with the extension every valid output can see -- the never-rewritten head
+ * of y (= init) when aliased, zero otherwise; (2) when aliased, re-sweep just the indices >= nc with
+ * the extension set to the final head.
+ */
+static void complex_pass(const float *xs, size_t nc, size_t L, const float *sos, const float *init, size_t ninit,
+                         int alias, float *ys, float *spill) {
+    const size_t clen = nc + 2 * L;
+    float *lane_x = calloc(clen, sizeof(float)), *lane_y = calloc(clen, sizeof(float));
+    float *tail_x = calloc(2 * L + 1, sizeof(float)), *tail_y = calloc(2 * L + 1, sizeof(float));
+    size_t i;
+    int q;
+    for (q = 0; q < 2; ++q) {
+        memset(lane_x, 0, clen * sizeof(float));
+        memset(lane_y, 0, clen * sizeof(float));
+        for (i = 0; i < nc; ++i) lane_x[i] = xs[2 * i + (size_t) q];
+        for (i = 0; 2 * i + (size_t) q < ninit && i < nc; ++i) lane_y[i] = init[2 * i + (size_t) q];
+        if (alias)
+            for (i = 0; i < L; ++i) lane_x[nc + i] = lane_y[i]; /* heads are never rewritten */
+        sweep_range(lane_x, lane_y, 0, clen, nc, L, sos, q == 0);
+        for (i = 0; i < nc; ++i) ys[2 * i + (size_t) q] = lane_y[i];
+        if (alias) {
+            for (i = 0; i < 2 * L + 1; ++i) {
+                tail_x[i] = i < 2 * L ? lane_y[i] : 0.f;
+                tail_y[i] = 0.f;
+            }
+            sweep_range(tail_x, tail_y, nc, 2 * L + 1, nc, L, sos, q == 0);
+        }
+        /* float f past the end of y is lane f&1 of complex index nc + f/2 */
+        for (i = 0; i + 1 < 2 * L; ++i) spill[2 * i + (size_t) q] = alias ? tail_y[i] : lane_y[nc + i];
+    }
+    free(lane_x);
+    free(lane_y);
+    free(tail_x);
+    free(tail_y);
+}
+
+/*
+ * src/matrix.c:236-273 (demodulation on), one chunk:
+ *   conditioner (-q0 shiftOrigin, -q3 normalizeInput, -q2 highpassDc = shiftOrigin + a degree-3
+ *   Butterworth HIGHPASS at fc = 1 designed at -S, applied like any complex filter)
+ *   -> [input filter, -L] -> discriminator -> output filter.
+ * Every complex pass writes 4L-2 floats past its output region; those land at the start of the
+ * region the NEXT pass accumulates into (y_c of the input filter, or y_o of the output filter),
+ * whose first L entries are never rewritten -- so they are observable in the first outputs of
+ * every chunk.
  */
 static int one_chunk(const uint8_t *in, size_t B, const fmo_config *cfg,
                      size_t Lin, size_t Lout, const float *sos_in, const float *sos_out,
                      float *out) {
     const size_t n_out = B >> 2, nc = B >> 1;
     const size_t ylen = n_out + 2 * Lout;
-    float *xs = malloc(B * sizeof(float));
+    const unsigned conditioner = (cfg->mode >> 2) & 3u;
+    float *xs = malloc(B * sizeof(float)), *ys = malloc(B * sizeof(float));
     float *dem = calloc(ylen, sizeof(float));
     float *y = calloc(ylen, sizeof(float));
-    size_t i;
-    if (!xs || !dem || !y) return -1;
-    if (((cfg->mode >> 2) & 3u) == 3u) fmo_normalize(in, B, xs);   /* matrix.c:208-222 */
+    float spill[4 * 8], sos_hp[2 * 6];
+    size_t nspill = 0, i;
+    if (!xs || !ys || !dem || !y) return -1;
+    if (conditioner == 3u) fmo_normalize(in, B, xs);   /* matrix.c:208-222 */
     else fmo_shift(in, B, xs);
-
-    if (Lin) {
-        const size_t clen = nc + 2 * Lin;
-        float *lane_x[2], *lane_y[2];
-        float *tail_x = calloc(2 * Lin + 1, sizeof(float));
-        float *tail_y = calloc(2 * Lin + 1, sizeof(float));
-        int q;
-        for (q = 0; q < 2; ++q) {
-            lane_x[q] = calloc(clen, sizeof(float));
-            lane_y[q] = calloc(clen, sizeof(float));
-            for (i = 0; i < nc; ++i) lane_x[q][i] = xs[2 * i + q];
-            sweep_range(lane_x[q], lane_y[q], 0, clen, nc, Lin, sos_in, q == 0);
-        }
-        for (q = 0; q < 2; ++q) {
-            /* (2): indices nc .. nc+2L-1 with x[nc+t] := final y_c[t] */
-            for (i = 0; i < 2 * Lin + 1; ++i) {
-                tail_x[i] = i < 2 * Lin ? lane_y[q][i] : 0.f;
-                tail_y[i] = 0.f;
-            }
-            sweep_range(tail_x, tail_y, nc, 2 * Lin + 1, nc, Lin, sos_in, q == 0);
-            /* (3): float f of y_o is lane f&1 of complex index nc + f/2 */
-            for (i = 0; i + 1 < 2 * Lin; ++i) {
-                const size_t f = 2 * i + (size_t) q;
-                if (f < ylen) y[f] = tail_y[i];
-            }
-        }
-        for (i = 0; i < nc; ++i) {
-            xs[2 * i] = lane_y[0][i];
-            xs[2 * i + 1] = lane_y[1][i];
-        }
-        for (q = 0; q < 2; ++q) { free(lane_x[q]); free(lane_y[q]); }
-        free(tail_x);
-        free(tail_y);
+    if (conditioner == 2u) {                           /* matrix.c:142-157 */
+        fmo_design_sos(FMO_BUTTER_HP, 3, 1., cfg->fs, 0., sos_hp);
+        complex_pass(xs, nc, 2, sos_hp, NULL, 0, 0, ys, spill);
+        nspill = 4 * 2 - 2;
+        memcpy(xs, ys, B * sizeof(float));
     }
+    if (Lin) {
+        float next[4 * 8];
+        complex_pass(xs, nc, Lin, sos_in, spill, nspill, 1, ys, next);
+        nspill = 4 * Lin - 2;
+        memcpy(spill, next, nspill * sizeof(float));
+        memcpy(xs, ys, B * sizeof(float));
+    }
+    for (i = 0; i < nspill && i < ylen; ++i) y[i] = spill[i];
     fmo_discriminate(xs, B, dem);
     sweep_range(dem, y, 0, ylen, n_out, Lout, sos_out, 1);
     memcpy(out, y, n_out * sizeof(float));
     free(xs);
+    free(ys);
     free(dem);
     free(y);
     return 0;
@@ -313,7 +337,7 @@ size_t fmo_process_chunks(const uint8_t *in, size_t nchunks, size_t B,
     if (cfg->fc_in != 0. && !deg_in) deg_in = cfg->deg_out;          /* matrix.c:190-192 */
     if (cfg->fc_in == 0. && deg_in) return 0;                        /* reference: undefined */
     if (!cfg->deg_out || (B & 3)) return 0;
-    if (((cfg->mode >> 2) & 3u) == 1u || ((cfg->mode >> 2) & 3u) == 2u) return 0; /* -q1/-q2: not restated */
+    if (((cfg->mode >> 2) & 3u) == 1u) return 0; /* -q1 (correctIq, a serial recurrence across chunks): not restated */
     Lin = fmo_sections(deg_in);
     Lout = fmo_sections(cfg->deg_out);
     /* the aliasing model above assumes the chunk is longer than the head it re-reads */

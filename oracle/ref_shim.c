@@ -20,8 +20,21 @@
  *   processMatrix loop    src/matrix.c:236-273 (driven here one chunk at a
  *                         time, synchronously, with the same scratch layout)
  */
+#include <stdlib.h>
+
+/* highpassDc (-q2, src/matrix.c:142-157) reads a few floats past its own calloc'd scratch.  In the
+ * reference process that scratch (bufSize floats >= 128 KiB, allocated before anything is freed)
+ * is a fresh mmap'd block whose slack is zero -- the reference CLI's output, which the fixtures
+ * are generated from, shows exactly that.  Inside another process (Python) the same calloc may be
+ * served from a recycled heap chunk, so the allocator behaviour is pinned here: every calloc made
+ * by the included sources gets 64 zeroed bytes of slack.  The sources themselves are untouched. */
+static void *shim_calloc(size_t n, size_t size) {
+    return calloc(n * size + 64, 1);
+}
+#define calloc(n, size) shim_calloc((n), (size))
 #include "src/filter.c"
 #include "src/matrix.c"
+#undef calloc
 
 static size_t sectionsFor(size_t degree) {
     return (degree >> 1) + (degree & 1);
@@ -69,7 +82,15 @@ size_t ref_run_chunks(const uint8_t *in, size_t nchunks, size_t bufSize, unsigne
     if (fcIn != 0. && !degIn) degIn = degOut;            /* src/matrix.c:190-192 */
     if (fcIn == 0. && degIn) return 0;  /* -D without -L: reference reads an undesigned filter */
     if (!degOut || (bufSize & 3)) return 0;
-    if (((mode >> 2) & 3) == 1 || ((mode >> 2) & 3) == 2) return 0; /* -q1/-q2: stateful / heap overrun */
+    if (((mode >> 2) & 3) == 1) return 0; /* -q1: state in a function-local static, cannot be driven chunk by chunk from here */
+    if (((mode >> 2) & 3) == 2) {
+        /* -q2: highpassDc allocates its scratch once, on its first call, for that call's length:
+         * one chunk size per process (see shim_calloc above for the slack it reads) */
+        static size_t q2_len = 0;
+        if (q2_len && q2_len != bufSize) return 0;
+        q2_len = bufSize;
+        samplingRate = (LREAL) fs; /* src/matrix.c:206 */
+    }
     const size_t nOut = bufSize >> 2;
     const size_t secOut = sectionsFor(degOut), secIn = sectionsFor(degIn);
     REAL sosOut[secOut ? secOut : 1][6];
@@ -87,6 +108,7 @@ size_t ref_run_chunks(const uint8_t *in, size_t nchunks, size_t bufSize, unsigne
     for (c = 0; c < nchunks; ++c) {
         REAL *res;
         if (((mode >> 2) & 3) == 3) normalizeInput((void *) (in + c * bufSize), bufSize, arena);  /* -q3 */
+        else if (((mode >> 2) & 3) == 2) highpassDc((void *) (in + c * bufSize), bufSize, arena); /* -q2 */
         else shiftOrigin((void *) (in + c * bufSize), bufSize, arena);
         if (!degIn) {
             res = arena + bufSize;

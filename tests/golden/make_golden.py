@@ -15,7 +15,7 @@ checks (1) == (2) bit for bit, and stores the input recipe, sha256 digests and a
 strided subset of the output as the fixture.  The fixtures are what pins the
 oracle port and the CUDA path on the GPU box, where /root/reference is absent.
 
-Usage:  python tests/golden/make_golden.py
+Usage:  python tests/golden/make_golden.py [case ...]     (no argument: every fixture)
 """
 from __future__ import annotations
 
@@ -56,6 +56,14 @@ CASES = [
     ("q3", "cfg1", 2, ["-S96000", "-l12500", "-q3"], dict(fs=96000.0, fc_out=12500.0, mode=12)),
     ("q3_L", "cfg2", 2, ["-S96000", "-l6500", "-L12500", "-q3"],
      dict(fs=96000.0, fc_out=6500.0, fc_in=12500.0, mode=12)),
+    # -q2: highpassDc (shiftOrigin + a Butterworth highpass at 1 Hz through applyComplexFilter); its
+    # overrun lands in the accumulator of the next stage.  All -q2 cases share -S and the chunk size:
+    # the reference designs that filter and allocates its scratch once per process.
+    ("q2", "cfg1", 2, ["-S96000", "-l12500", "-q2"], dict(fs=96000.0, fc_out=12500.0, mode=8)),
+    ("q2_L", "cfg2", 2, ["-S96000", "-l6500", "-L12500", "-q2"],
+     dict(fs=96000.0, fc_out=6500.0, fc_in=12500.0, mode=8)),
+    ("q2_d5_D4_L_m3", "cfg2", 2, ["-S96000", "-l9600", "-L12500", "-q2", "-d5", "-D4", "-m3"],
+     dict(fs=96000.0, fc_out=9600.0, fc_in=12500.0, deg_out=5, deg_in=4, mode=8 | 3)),
 ]
 
 # byte patterns exercising the int8 wrap (255 -> -128), signed zeros and the +-pi cut
@@ -102,7 +110,10 @@ def sha(a: np.ndarray) -> str:
 def main() -> None:
     po.build(ref=True)
     R = po.ref()
+    only = set(sys.argv[1:])
     for name, sig_name, nchunks, flags, kw in CASES:
+        if only and name not in only:
+            continue
         raw = synth.config_signal(sig_name, nchunks)
         cfg = po.Config(**kw)
         out = R.run(raw, cfg)
@@ -113,6 +124,8 @@ def main() -> None:
         assert same, f"{name}: CLI binary and shim disagree"
         _save(name, raw, out, cfg, flags, sig=dict(kind=sig_name, nchunks=nchunks), binary_checked=True)
         print(f"{name}: {out.size} floats, binary == shim, extra floats from CLI = {outb.size - out.size}")
+    if only:
+        return
     raw = edge_bytes()
     for name, flags, kw in (("edge", ["-S96000", "-l12500"], dict(fs=96000.0, fc_out=12500.0)),
                             ("edge_L", ["-S96000", "-l6500", "-L12500"],
