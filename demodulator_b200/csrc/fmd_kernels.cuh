@@ -97,20 +97,53 @@ struct FmdShiftedLane {
     }
 };
 
-/* final y_c lane value at complex index c < nc (input lowpass on), or the shifted sample */
-struct FmdComplexLane {
+/*
+ * What the conditioner leaves in the x region, lane q, at complex index c.
+ *   -q0 / -q3: the shifted / normalised sample, zero past the end of the chunk.
+ *   -q2 (highpassDc, matrix.c:142-157): shiftOrigin, then a degree-3 Butterworth highpass at 1 Hz
+ *       swept like any complex filter (filter.c:242-258) from a scratch buffer whose slack is zero.
+ *       Indices nc .. nc+2 are what that sweep WRITES past its output region -- the start of the
+ *       region the next stage accumulates into -- and 0 beyond (no section reaches them).
+ */
+struct FmdConditionedLane {
     const uint8_t *cin;
     long long nc;
     const FmdSections *sec;
     int q;
     __device__ float operator()(long long c) const {
         FmdShiftedLane sl{cin, nc, q, sec->conditioner};
-        if (sec->lin == 0) return sl(c);
-        return fmd_sweep_cone(c, nc, sec->lin, sec->in, q == 0, sl, FmdZeroInit());
+        if (sec->conditioner != 2) return sl(c);
+        return fmd_sweep_cone(c, nc, 2, sec->hp, q == 0, sl, FmdZeroInit());
     }
 };
 
-/* what the complex sweep reads as x[nc + t]: the already-final head of y_c */
+/* initial contents of the region a stage accumulates into, lane q, complex index c: what the
+ * stage before it spilled there (only -q2 spills ahead of the input filter) */
+struct FmdConditionerSpill {
+    FmdConditionedLane x;
+    __device__ float operator()(long long c) const {
+        if (x.sec->conditioner != 2 || c >= 3) return 0.0f;
+        return x(x.nc + c);
+    }
+};
+
+/* final y_c lane value at complex index c < nc (input lowpass on), or the conditioned sample.
+ * Past the end of the chunk the input sweep reads the head of its own output region, which it
+ * never rewrites: zero, or what -q2 spilled there -- FmdConditionedLane at c >= nc is exactly that. */
+struct FmdComplexLane {
+    const uint8_t *cin;
+    long long nc;
+    const FmdSections *sec;
+    int q;
+    __device__ float operator()(long long c) const {
+        FmdConditionedLane xl{cin, nc, sec, q};
+        if (sec->lin == 0) return xl(c);
+        return fmd_sweep_cone(c, nc, sec->lin, sec->in, q == 0, xl, FmdConditionerSpill{xl});
+    }
+};
+
+/* what the complex sweep reads as x[nc + t] while it produces its own spill: the already-final
+ * head of y_c */
 struct FmdAliasedLane {
     FmdComplexLane z;
     __device__ float operator()(long long c) const { return z(c - z.nc); }
@@ -131,16 +164,18 @@ struct FmdDemodX {
     }
 };
 
-/* initial contents of the output accumulator region: what the complex sweep spilled past
- * the end of y_c (matrix.c:260-267 + filter.c:242-258), zero elsewhere */
+/* initial contents of the output accumulator region: what the LAST complex sweep spilled past
+ * the end of its output region (matrix.c:260-267 + filter.c:242-258; with -q2 and no -L that is
+ * the conditioner's own sweep), zero elsewhere */
 struct FmdSpillInit {
     const uint8_t *cin;
     long long nc;
     const FmdSections *sec;
     __device__ float operator()(long long f) const {
         const int L = sec->lin;
-        if (L == 0 || f >= 4 * L - 2) return 0.0f;
         const int q = (int) (f & 1);
+        if (L == 0) return FmdConditionerSpill{FmdConditionedLane{cin, nc, sec, q}}(f >> 1);
+        if (f >= 4 * L - 2) return 0.0f;
         FmdAliasedLane al{FmdComplexLane{cin, nc, sec, q}};
         return fmd_sweep_cone(nc + (f >> 1), nc, L, sec->in, q == 0, al, FmdZeroInit());
     }

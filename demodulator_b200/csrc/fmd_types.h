@@ -34,7 +34,8 @@ struct FmdSections {
     float in[FMD_MAX_SECTIONS][6];
     float out[FMD_MAX_SECTIONS][6];
     int lin, lout;
-    int conditioner; /* consumerArgs.mode bits 2-3 (-q): 0 shiftOrigin, 3 normalizeInput */
+    int conditioner; /* consumerArgs.mode bits 2-3 (-q): 0 shiftOrigin, 2 highpassDc, 3 normalizeInput */
+    float hp[2][6];  /* -q2: the degree-3 Butterworth highpass at 1 Hz (matrix.c:151) */
 };
 
 #endif /* FMD_TYPES_H */

@@ -146,11 +146,14 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
                                  "quality mode keeps the filter state in float32: cut-offs must lie in "
                                  "[input_rate/1000, input_rate/2)");
     }
-    if (conditioner == 1u || conditioner == 2u)
+    if (conditioner == 1u)
         return fmd_set_error(FMD_EINVAL,
-                             "input conditioner -q%u is outside the accelerated path (-q0 and -q3 only: -q1 is a "
-                             "serial recurrence across chunks, -q2 reads past its buffer in the reference)",
-                             conditioner);
+                             "input conditioner -q1 (correctIq) is outside the accelerated path: a serial recurrence "
+                             "whose state crosses chunks (-q0, -q2 and -q3 are served)");
+    if (conditioner == 2u && cfg.chunk_bytes * sizeof(float) < (128u << 10))
+        return fmd_set_error(FMD_EINVAL,
+                             "-q2 with chunks under 32 KiB: the reference's highpassDc reads past a scratch buffer "
+                             "that is then a recycled heap chunk (undefined); with larger chunks its slack is zero");
     if (((cfg.mode >> 4) & 3u) == 0)
         return fmd_set_error(FMD_EINVAL, "demodulation off (-c) is unreachable in the reference CLI and unsupported");
 
@@ -182,6 +185,10 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
     /* -q3 (normalizeInput) streams without the input filter; with it the zero extension past a
      * chunk is not a byte value (no u8 normalises to 0.0), so that combination stays op-for-op */
     if (conditioner == 3u && c->lin) c->fast_in_ok = false;
+    /* -q2 (highpassDc) is one more complex sweep: without -L it IS the input stencil of the streaming
+     * kernel (folded below); stacked under -L its spill reaches the last outputs of every chunk
+     * through the input filter's aliased reads, so that combination stays op-for-op */
+    if (conditioner == 2u && c->lin) c->fast_in_ok = false;
 
     /* quality mode runs both filters at the input rate (the output one BEFORE the decimation) */
     const double design_rate = quality ? cfg.input_rate : cfg.sample_rate;
@@ -209,6 +216,25 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
             c->fast_in_ok = false;
         }
     }
+    if (!rc && conditioner == 2u) {
+        /* matrix.c:151: processFilterOption(2, 3, sos, 1., samplingRate, 0.) */
+        rc = fmd_design_sos(FMD_BUTTER_HP, 3, 1.0, cfg.sample_rate, 0.0, &c->sec.hp[0][0]);
+        if (!rc && !c->lin) {
+            float dci = 0.f, taps_q[FMD_MAX_TAPS];
+            unsigned nti_q = 0;
+            rc = fmd_fold_taps(&c->sec.hp[0][0], 2, 1, c->st.tin, &dci, &c->nti);
+            if (!rc) rc = fmd_fold_taps(&c->sec.hp[0][0], 2, 0, taps_q, &c->st.dcq, &nti_q);
+            c->st.dci = dci;
+            const float c0 = c->st.tin[0];
+            if (!rc && c->nti >= 1 && std::isfinite(c0) && c0 != 0.0f && dci == 0.0f && std::isfinite(c->st.dcq)) {
+                for (unsigned t = 1; t < c->nti; ++t) c->st.tin[t] = (float) ((double) c->st.tin[t] / (double) c0);
+                c->st.dcq = (float) ((double) c->st.dcq / (double) c0);
+                c->st.tin[0] = 1.0f;
+            } else if (!rc) {
+                c->fast_in_ok = false;
+            }
+        }
+    }
     if (rc) {
         delete c;
         return rc;
@@ -222,6 +248,7 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
     }
     c->head = 2 * c->lout - 1;
     if (c->lin && 4 * c->lin - 2 > c->head) c->head = 4 * c->lin - 2;
+    if (conditioner == 2u && 4 * 2 - 2 > c->head) c->head = 4 * 2 - 2; /* the highpass sweep's spill */
     c->head = (c->head + 7u) & ~7u;
 
     if (cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking) != cudaSuccess ||

@@ -75,8 +75,8 @@ typedef struct fmd_config {
     uint32_t in_degree;   /* -D  consumerArgs.inFilterDegree; 0 with -L => out_degree             */
     uint32_t out_degree;  /* -d  consumerArgs.outFilterDegree (default 3)                         */
     uint32_t mode;        /* consumerArgs.mode: bit0 out Chebyshev, bit1 in Chebyshev,
-                             bits2-3 input conditioner (-q: 0 shiftOrigin, 3 normalizeInput; 1 and 2
-                             are rejected), bits4-5 demod (-c) */
+                             bits2-3 input conditioner (-q: 0 shiftOrigin, 2 highpassDc, 3 normalizeInput;
+                             1 correctIq is rejected), bits4-5 demod (-c) */
     uint32_t flags;       /* FMD_FLAG_*                                                           */
     uint64_t chunk_bytes; /* consumerArgs.bufSize (default 262144); multiple of 4                 */
     double input_rate;    /* -r  rate of the IQ input; read only under FMD_FLAG_QUALITY (the

@@ -43,6 +43,7 @@ CASES = [
      dict(fs=96000.0, fc_out=12500.0, fc_in=12500.0, deg_out=5, mode=3)),
     ("cfg1", [], dict()),
     ("cfg2", ["-S96000", "-l6500", "-L12500", "-q3"], dict(fs=96000.0, fc_out=6500.0, fc_in=12500.0, mode=12)),
+    ("cfg1", ["-S96000", "-l12500", "-q2"], dict(fs=96000.0, fc_out=12500.0, mode=8)),
 ]
 
 

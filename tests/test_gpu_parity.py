@@ -50,7 +50,7 @@ def test_edge_bytes(name):
         assert snr_db(out[~bad], want[~bad]) > 80.0
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "d5_L", "D7_d4_L", "m1_d4"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "d5_L", "D7_d4_L", "m1_d4", "q2", "q2_L"])
 def test_exact_kernel_matches_oracle_tightly(name, oracle_best):
     """FMD_FLAG_EXACT evaluates the section sweep op for op: only atan2 differs from libm."""
     g, cfg = load_golden(name)
@@ -176,7 +176,7 @@ def test_rejects_what_the_reference_leaves_undefined():
     with pytest.raises(fm.FmdError):
         fm.Demodulator(mode=0x4)  # -q1
     with pytest.raises(fm.FmdError):
-        fm.Demodulator(mode=0x8)  # -q2
+        fm.Demodulator(mode=0x8, bufSize=16384)  # -q2 with a scratch buffer small enough to be a recycled heap chunk
 
 
 def test_atan2_special_values():
