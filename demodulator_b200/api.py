@@ -119,7 +119,7 @@ class Demodulator:
 
     sampleRate (-S), lowpassIn (-L), lowpassOut (-l), epsilon (-e, already divided by 10),
     inFilterDegree (-D), outFilterDegree (-d), mode (bit0 -m1 output Chebyshev, bit1 -m2 input
-    Chebyshev, bits 2-3 the -q conditioner: 0, 2 or 3; the demod bit 0x10 is always on, as in
+    Chebyshev, bits 2-3 the -q conditioner 0..3; the demod bit 0x10 is always on, as in
     src/main.c:112), bufSize (-b result).
     """
 

@@ -295,7 +295,8 @@ int main(int argc, char **argv) {
          * (only its last slot is short); a stream may cut slots short, so its output stays sequential */
         h.n_writers = (h.out_regular && h.in_regular) ? want : 1;
         if (!(h.out_regular && h.in_regular)) h.out_regular = 0;
-        if (cfg.flags & FMD_FLAG_QUALITY) { /* one ordered stream: output sizes depend on the position */
+        if ((cfg.flags & FMD_FLAG_QUALITY) || ((cfg.mode >> 2) & 3u) == 1u) {
+            /* one ordered stream: -Q output sizes depend on the position; -q1 carries its offsets on */
             h.n_writers = 1;
             h.out_regular = 0;
         }
@@ -304,8 +305,8 @@ int main(int argc, char **argv) {
 
     h.ndev = parse_devices(getenv("FMD_DEVICES"), devs);
     if (h.ndev <= 0) die("no CUDA device");
-    if ((cfg.flags & FMD_FLAG_QUALITY) && h.ndev > 1) {
-        fprintf(stderr, "demodulator: -Q carries filter state through the stream: using device %d only\n", devs[0]);
+    if (((cfg.flags & FMD_FLAG_QUALITY) || ((cfg.mode >> 2) & 3u) == 1u) && h.ndev > 1) {
+        fprintf(stderr, "demodulator: -Q / -q1 carry state through the stream: using device %d only\n", devs[0]);
         h.ndev = 1;
     }
     for (int d = 0; d < h.ndev; ++d)
@@ -362,6 +363,7 @@ int main(int argc, char **argv) {
         sem_wait(&s->filled);
         /* tail policy: a final partial chunk of r bytes is a chunk of r&~3 bytes */
         s->nbytes &= ~(size_t) 3;
+        if (((cfg.mode >> 2) & 3u) == 1u) s->nbytes -= s->nbytes % h.chunk; /* -q1 works on whole chunks only */
         s->nout = fmd_out_count(h.ctx[s->dev], s->nbytes); /* before the submit moves a -Q stream on */
         if (s->nbytes && fmd_submit(h.ctx[s->dev], s->ring, s->in, s->nbytes, s->out)) die("fmd_submit");
         const int last = s->last;

@@ -1,0 +1,94 @@
+/*
+ * fmd_correctiq.cuh -- the -q1 input conditioner (correctIq, /root/reference/src/matrix.c:120-140) on
+ * the GPU.
+ *
+ * The reference walks a chunk from both ends: step k (complex k from the front, complex nc-1-k from
+ * the back) subtracts the running offsets (one per lane) and then moves them,
+ *     off += ((u_front - off) + (u_back - off)) * esr,         esr = (float)(50 / -S),
+ * and the offsets live on from chunk to chunk.  In exact arithmetic that is the affine recurrence
+ *     off' = (1 - 2 esr) off + esr (u_front + u_back)
+ * over all steps of the stream, i.e. a scan with a constant scalar "matrix" -- the D = 1 case of the
+ * machinery of fmd_quality.h:
+ *   fmd_correctiq_kernel<false>   per tile (256 threads x FMQ_T steps) the offsets' end value from zero
+ *   fmq_scan_tiles_kernel<1, 2>   the offsets at the start of every tile; carry in from the previous
+ *                                 call, carry out for the next
+ *   fmd_correctiq_kernel<true>    every thread starts from its scanned offsets and walks its steps
+ *                                 with the reference's own float operations in the reference's order,
+ *                                 writing the conditioned samples as floats
+ * The conditioned floats (one per input byte, same layout) then go through the op-for-op path, whose
+ * base lane reads them instead of shifting bytes (FmdShiftedLane, conditioner 1).
+ *
+ * Not bit-exact: the scan associates the additions differently from the serial float32 loop, and the
+ * recurrence contracts (factor 1 - 2 esr per step), so the offsets agree to about 1e-4 of ~127 and
+ * the demodulated output to about 1e-6 -- inside the 1e-4 bar, like everything else on the fast side.
+ */
+#ifndef FMD_CORRECTIQ_CUH
+#define FMD_CORRECTIQ_CUH
+
+#include "fmd_quality.cuh"
+
+struct FmdQ1Geom {
+    unsigned long long nsteps;      /* steps in this call: nchunks * steps_per_chunk           */
+    unsigned long long chunk_bytes; /* B: bytes per chunk (= floats per chunk of the output)   */
+    unsigned steps_per_chunk;       /* B / 4                                                    */
+    float esr, a;                   /* (float)(50 / -S), 1 - 2 esr                               */
+};
+
+template <bool APPLY>
+__global__ void __launch_bounds__(FMQ_THREADS)
+fmd_correctiq_kernel(const uint8_t *__restrict__ in, float *__restrict__ sbuf, const FmdQ1Geom g, const fmq_consts c,
+                     const float *__restrict__ lane_tab, const float *__restrict__ apow,
+                     const float *__restrict__ q_tile /* [ntiles][2], APPLY only */,
+                     float *__restrict__ e_tile /* [ntiles][2], !APPLY only */) {
+    __shared__ float tot[FMQ_WARPS * 2];
+    const unsigned long long first = ((unsigned long long) blockIdx.x * FMQ_THREADS + threadIdx.x) * FMQ_T;
+    const unsigned cnt = first >= g.nsteps ? 0u : (unsigned) min((unsigned long long) FMQ_T, g.nsteps - first);
+    const bool last = cnt != 0u && (threadIdx.x == FMQ_THREADS - 1 || first + FMQ_T >= g.nsteps);
+    /* FMQ_T divides steps_per_chunk (the host checks): a thread's steps lie in one chunk */
+    const unsigned long long chunk = first / g.steps_per_chunk;
+    const unsigned k0 = (unsigned) (first - chunk * g.steps_per_chunk);
+    const unsigned nc = 2u * g.steps_per_chunk;
+    const uint8_t *__restrict__ cin = in + chunk * g.chunk_bytes;
+    const unsigned short *__restrict__ front = reinterpret_cast<const unsigned short *>(cin) + k0;
+    const unsigned short *__restrict__ back = reinterpret_cast<const unsigned short *>(cin) + (nc - 1u - k0);
+
+    /* end value of the offsets after this thread's steps, from zero */
+    float v[2][1] = {{0.0f}, {0.0f}};
+#pragma unroll 4
+    for (unsigned k = 0; k < cnt; ++k) {
+        const unsigned f = front[k], b = back[-(int) k];
+        v[0][0] = fmaf(g.a, v[0][0], g.esr * (float) ((f & 0xffu) + (b & 0xffu)));
+        v[1][0] = fmaf(g.a, v[1][0], g.esr * (float) ((f >> 8) + (b >> 8)));
+    }
+    const float e0 = v[0][0], e1 = v[1][0];
+    float carry[2][1] = {{0.0f}, {0.0f}};
+    if (APPLY) {
+        carry[0][0] = __ldg(q_tile + 2 * (size_t) blockIdx.x);
+        carry[1][0] = __ldg(q_tile + 2 * (size_t) blockIdx.x + 1);
+    }
+    fmq_block_scan<1, 2>(v, c, lane_tab, carry, tot); /* -> offsets at the start of this thread's steps */
+    if (!APPLY) {
+        if (last) {
+            const float p = __ldg(apow + cnt); /* a^cnt */
+            e_tile[2 * (size_t) blockIdx.x] = fmaf(p, v[0][0], e0);
+            e_tile[2 * (size_t) blockIdx.x + 1] = fmaf(p, v[1][0], e1);
+        }
+        return;
+    }
+    /* the reference's loop body, operation for operation (matrix.c:129-138) */
+    float off0 = v[0][0], off1 = v[1][0];
+    float2 *__restrict__ sf = reinterpret_cast<float2 *>(sbuf + chunk * g.chunk_bytes) + k0;
+    float2 *__restrict__ sb = reinterpret_cast<float2 *>(sbuf + chunk * g.chunk_bytes) + (nc - 1u - k0);
+#pragma unroll 4
+    for (unsigned k = 0; k < cnt; ++k) {
+        const unsigned f = front[k], b = back[-(int) k];
+        const float fi = __fsub_rn((float) (f & 0xffu), off0), bi = __fsub_rn((float) (b & 0xffu), off0);
+        const float fq = __fsub_rn((float) (f >> 8), off1), bq = __fsub_rn((float) (b >> 8), off1);
+        sf[k] = make_float2(fi, fq);
+        sb[-(int) k] = make_float2(bi, bq);
+        off0 = __fadd_rn(off0, __fmul_rn(__fadd_rn(fi, bi), g.esr));
+        off1 = __fadd_rn(off1, __fmul_rn(__fadd_rn(fq, bq), g.esr));
+    }
+}
+
+#endif /* FMD_CORRECTIQ_CUH */

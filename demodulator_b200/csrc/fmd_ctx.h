@@ -30,11 +30,13 @@ struct fmd_slot {
     bool busy = false;
 };
 
-struct fmq_ctx; /* FMD_FLAG_QUALITY state, fmd_quality_host.cu */
+struct fmq_ctx;  /* FMD_FLAG_QUALITY state, fmd_quality_host.cu */
+struct fmq1_ctx; /* -q1 (correctIq) state, fmd_quality_host.cu */
 
 struct fmd_ctx {
     fmd_config cfg;
     fmq_ctx *q = nullptr;
+    fmq1_ctx *q1 = nullptr;
     int device = 0;
     unsigned lin = 0, lout = 0;
     FmdSections sec;
@@ -71,5 +73,13 @@ int fmq_demod_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, float *d_ou
 int fmq_reset(fmd_ctx *c);
 /* 0, or FMD_ECUDA if a look-back gave up waiting (reads a device-side flag: synchronises) */
 int fmq_check_error(fmd_ctx *c);
+
+/* ---- -q1 (correctIq): offsets that live on from chunk to chunk, as a scan; fmd_quality_host.cu ---- */
+int fmq1_setup(fmd_ctx *c);
+void fmq1_free(fmd_ctx *c);
+int fmq1_reset(fmd_ctx *c);
+/* conditions `nchunks` whole chunks (continuing the stream) into floats, one per input byte; *sbuf is
+ * owned by the context and valid until the next call on it */
+int fmq1_condition(fmd_ctx *c, const uint8_t *d_in, unsigned long long nchunks, cudaStream_t s, const float **sbuf);
 
 #endif /* FMD_CTX_H */

@@ -89,6 +89,9 @@ struct FmdShiftedLane {
     int conditioner;
     __device__ float operator()(long long c) const {
         if (c >= nc) return 0.0f;
+        /* -q1 (correctIq): the samples were conditioned by fmd_correctiq_kernel; `cin` then points at
+         * floats, one per input byte, same layout */
+        if (conditioner == 1) return reinterpret_cast<const float *>(cin)[2 * c + q];
         const uint8_t u = cin[2 * c + q];
         /* -q3, matrix.c:100-118: (float)((double)((float)u * (float)(2/255)) - 1.0); the double
          * subtraction of a float and 1 is exact, so one rounded float subtraction is the same */

@@ -10,6 +10,7 @@
 #include <new>
 
 #include "fmd_ctx.h"
+#include "fmd_correctiq.cuh"
 #include "fmd_quality.cuh"
 
 /* one cascade of the quality pipeline: host design + constants + device tables */
@@ -269,5 +270,118 @@ int fmq_check_error(fmd_ctx *c) {
     unsigned err = 0;
     FMD_CUDA(cudaMemcpy(&err, &c->q->d_state->error, sizeof err, cudaMemcpyDeviceToHost));
     if (err) return fmd_set_error(FMD_ECUDA, "quality pipeline: a tile gave up waiting for its predecessor's carry");
+    return FMD_OK;
+}
+
+/* ---------------------------------------------------------------- -q1 (correctIq) as a scan */
+
+struct fmq1_ctx {
+    fmq_design des;       /* D = 1: A = [1 - 2 esr] */
+    fmq_consts c, c_tile;
+    fmq_table_sizes sz;
+    float *d_tab = nullptr; /* lane | apow | ck | ckn | lane_tile (ck, ckn unused) */
+    float *d_off = nullptr; /* the two running offsets: the carry between calls */
+    float *d_e = nullptr, *d_q = nullptr; /* per-tile end values / start values */
+    unsigned tile_cap = 0;
+    float *d_sbuf = nullptr; /* conditioned samples of the current call */
+    size_t sbuf_cap = 0;
+    float esr = 0.f, a = 0.f;
+};
+
+int fmq1_setup(fmd_ctx *c) {
+    fmq1_ctx *q = new (std::nothrow) fmq1_ctx();
+    if (!q) return fmd_set_error(FMD_ENOMEM, "out of host memory");
+    c->q1 = q;
+    q->esr = (float) (50. / c->cfg.sample_rate); /* matrix.c:210 */
+    const double a = 1.0 - 2.0 * (double) q->esr;
+    q->a = (float) a;
+    memset(&q->des, 0, sizeof q->des);
+    q->des.L = 1;
+    q->des.D = 1;
+    q->des.A[0][0] = (long double) a;
+    q->des.C[0] = 1.0L;
+    fmq_build_consts(&q->des, FMQ_T, &q->c);
+    fmq_build_consts(&q->des, FMQ_TILE, &q->c_tile);
+    fmq_table_layout(&q->des, &q->sz);
+    const size_t n = (size_t) q->sz.lane + q->sz.apow + q->sz.ck + q->sz.ckn + q->sz.lane_tile;
+    float *h = (float *) malloc(n * sizeof(float));
+    if (!h) return fmd_set_error(FMD_ENOMEM, "out of host memory");
+    fmq_build_tables(&q->des, h, h + q->sz.lane, h + q->sz.lane + q->sz.apow, h + q->sz.lane + q->sz.apow + q->sz.ck,
+                     h + q->sz.lane + q->sz.apow + q->sz.ck + q->sz.ckn);
+    cudaError_t e = cudaMalloc(&q->d_tab, n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(q->d_tab, h, n * sizeof(float), cudaMemcpyHostToDevice);
+    free(h);
+    if (e != cudaSuccess) return fmd_set_error(FMD_ECUDA, "-q1 table upload failed: %s", cudaGetErrorString(e));
+    FMD_CUDA(cudaMalloc(&q->d_off, 2 * sizeof(float)));
+    FMD_CUDA(cudaMemset(q->d_off, 0, 2 * sizeof(float))); /* static REAL off[2] = {} */
+    return FMD_OK;
+}
+
+void fmq1_free(fmd_ctx *c) {
+    fmq1_ctx *q = c->q1;
+    if (!q) return;
+    if (q->d_tab) cudaFree(q->d_tab);
+    if (q->d_off) cudaFree(q->d_off);
+    if (q->d_e) cudaFree(q->d_e);
+    if (q->d_q) cudaFree(q->d_q);
+    if (q->d_sbuf) cudaFree(q->d_sbuf);
+    delete q;
+    c->q1 = nullptr;
+}
+
+int fmq1_reset(fmd_ctx *c) {
+    FMD_CUDA(cudaSetDevice(c->device));
+    FMD_CUDA(cudaDeviceSynchronize());
+    FMD_CUDA(cudaMemset(c->q1->d_off, 0, 2 * sizeof(float)));
+    return FMD_OK;
+}
+
+int fmq1_condition(fmd_ctx *c, const uint8_t *d_in, unsigned long long nchunks, cudaStream_t s, const float **sbuf) {
+    fmq1_ctx *q = c->q1;
+    const unsigned long long B = c->cfg.chunk_bytes;
+    FmdQ1Geom g;
+    g.chunk_bytes = B;
+    g.steps_per_chunk = (unsigned) (B >> 2);
+    g.nsteps = nchunks * g.steps_per_chunk;
+    g.esr = q->esr;
+    g.a = q->a;
+    const unsigned long long ntiles64 = (g.nsteps + FMQ_TILE - 1) / FMQ_TILE;
+    if (ntiles64 > 0x7fffffffull) return fmd_set_error(FMD_EINVAL, "too many chunks in one -q1 call");
+    const unsigned ntiles = (unsigned) ntiles64;
+    if (ntiles > q->tile_cap) {
+        if (q->d_e) cudaFree(q->d_e);
+        if (q->d_q) cudaFree(q->d_q);
+        q->d_e = q->d_q = nullptr;
+        q->tile_cap = 0;
+        const unsigned cap = ntiles < 4096u ? 4096u : ntiles;
+        FMD_CUDA(cudaMalloc(&q->d_e, (size_t) cap * 2 * sizeof(float)));
+        FMD_CUDA(cudaMalloc(&q->d_q, (size_t) cap * 2 * sizeof(float)));
+        q->tile_cap = cap;
+    }
+    const size_t need = (size_t) (nchunks * B); /* floats: one per input byte */
+    if (need > q->sbuf_cap) {
+        if (q->d_sbuf) cudaFree(q->d_sbuf);
+        q->d_sbuf = nullptr;
+        q->sbuf_cap = 0;
+        FMD_CUDA(cudaMalloc(&q->d_sbuf, need * sizeof(float)));
+        q->sbuf_cap = need;
+    }
+    const float *lane = q->d_tab, *apow = q->d_tab + q->sz.lane;
+    const float *lane_tile = q->d_tab + q->sz.lane + q->sz.apow + q->sz.ck + q->sz.ckn;
+    const unsigned nwarps = FMQ_SCAN_THREADS / 32;
+    const unsigned runlen = ((ntiles + nwarps - 1u) / nwarps + 31u) & ~31u;
+    const unsigned long long len_last = g.nsteps - (unsigned long long) (ntiles - 1u) * FMQ_TILE;
+    FmqMat prun, pl;
+    memset(&prun, 0, sizeof prun);
+    memset(&pl, 0, sizeof pl);
+    fmq_matpow_f(&q->des, (unsigned long long) FMQ_TILE * runlen, prun.m);
+    fmq_matpow_f(&q->des, len_last, pl.m);
+    fmd_correctiq_kernel<false><<<ntiles, FMQ_THREADS, 0, s>>>(d_in, nullptr, g, q->c, lane, apow, nullptr, q->d_e);
+    fmq_scan_tiles_kernel<1, 2><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_e, q->d_q, q->d_off, q->c_tile, lane_tile, prun, pl, ntiles,
+                                                                runlen, nullptr, nullptr);
+    fmd_correctiq_kernel<true><<<ntiles, FMQ_THREADS, 0, s>>>(d_in, q->d_sbuf, g, q->c, lane, apow, q->d_q, nullptr);
+    FMD_CUDA(cudaGetLastError());
+    c->launches += 3;
+    *sbuf = q->d_sbuf;
     return FMD_OK;
 }

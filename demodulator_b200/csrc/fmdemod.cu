@@ -146,10 +146,8 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
                                  "quality mode keeps the filter state in float32: cut-offs must lie in "
                                  "[input_rate/1000, input_rate/2)");
     }
-    if (conditioner == 1u)
-        return fmd_set_error(FMD_EINVAL,
-                             "input conditioner -q1 (correctIq) is outside the accelerated path: a serial recurrence "
-                             "whose state crosses chunks (-q0, -q2 and -q3 are served)");
+    if (conditioner == 1u && (quality || (cfg.chunk_bytes % (4u * FMQ_T)) != 0))
+        return fmd_set_error(FMD_EINVAL, "-q1 (correctIq) needs chunks that are a multiple of %u bytes (and no -Q)", 4u * FMQ_T);
     if (conditioner == 2u && cfg.chunk_bytes * sizeof(float) < (128u << 10))
         return fmd_set_error(FMD_EINVAL,
                              "-q2 with chunks under 32 KiB: the reference's highpassDc reads past a scratch buffer "
@@ -189,6 +187,9 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
      * kernel (folded below); stacked under -L its spill reaches the last outputs of every chunk
      * through the input filter's aliased reads, so that combination stays op-for-op */
     if (conditioner == 2u && c->lin) c->fast_in_ok = false;
+    /* -q1 (correctIq): the samples are conditioned by a scan of their own (fmd_correctiq.cuh) and the
+     * rest runs op for op on the conditioned floats */
+    if (conditioner == 1u) c->fast_in_ok = false;
 
     /* quality mode runs both filters at the input rate (the output one BEFORE the decimation) */
     const double design_rate = quality ? cfg.input_rate : cfg.sample_rate;
@@ -269,6 +270,13 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
             return rc;
         }
     }
+    if (conditioner == 1u) {
+        rc = fmq1_setup(c);
+        if (rc) {
+            fmd_destroy(c);
+            return rc;
+        }
+    }
     *out = c;
     return FMD_OK;
 }
@@ -300,6 +308,7 @@ extern "C" void fmd_destroy(fmd_ctx *c) {
     }
     if (c->d_sec) cudaFree(c->d_sec);
     fmq_free(c);
+    fmq1_free(c);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_k) cudaStreamDestroy(c->s_k);
     if (c->s_out) cudaStreamDestroy(c->s_out);
@@ -488,6 +497,7 @@ static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned
 
 extern "C" int fmd_reset(fmd_ctx *c) {
     if (!c) return fmd_set_error(FMD_EINVAL, "null argument");
+    if (c->q1) return fmq1_reset(c);
     return c->q ? fmq_reset(c) : FMD_OK;
 }
 
@@ -505,6 +515,25 @@ extern "C" int fmd_demod_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, 
     int rc;
     if (c->q) {
         rc = fmq_demod_device(c, d_in, nbytes, d_out, s);
+    } else if (c->q1) {
+        /* -q1: the offsets live on from chunk to chunk, so a call is a run of WHOLE chunks that
+         * continues the stream; condition them, then the op-for-op path on the conditioned floats */
+        if (rem || nbytes != nfull * B)
+            rc = fmd_set_error(FMD_EINVAL, "-q1 takes whole chunks (%llu bytes each)", B);
+        else if (!nfull)
+            rc = FMD_OK;
+        else {
+            const float *sbuf = nullptr;
+            rc = fmq1_condition(c, d_in, nfull, s, &sbuf);
+            if (!rc) {
+                FmdGeom g;
+                memset(&g, 0, sizeof g);
+                g.chunk_stride = B * sizeof(float);
+                g.chunk_out = (unsigned) (B >> 2);
+                g.nchunks = (unsigned) nfull;
+                rc = launch_exact(c, reinterpret_cast<const uint8_t *>(sbuf), d_out, g, s);
+            }
+        }
     } else {
         rc = launch_chunks(c, d_in, d_out, (unsigned) nfull, (unsigned) (B >> 2), B, s);
         if (!rc && rem)

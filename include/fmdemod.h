@@ -75,8 +75,10 @@ typedef struct fmd_config {
     uint32_t in_degree;   /* -D  consumerArgs.inFilterDegree; 0 with -L => out_degree             */
     uint32_t out_degree;  /* -d  consumerArgs.outFilterDegree (default 3)                         */
     uint32_t mode;        /* consumerArgs.mode: bit0 out Chebyshev, bit1 in Chebyshev,
-                             bits2-3 input conditioner (-q: 0 shiftOrigin, 2 highpassDc, 3 normalizeInput;
-                             1 correctIq is rejected), bits4-5 demod (-c) */
+                             bits2-3 input conditioner (-q: 0 shiftOrigin, 1 correctIq, 2 highpassDc,
+                             3 normalizeInput).  -q1 makes the context a STREAM like the reference's
+                             static offsets do: calls take whole chunks and continue it, fmd_reset
+                             starts over.  bits4-5 demod (-c) */
     uint32_t flags;       /* FMD_FLAG_*                                                           */
     uint64_t chunk_bytes; /* consumerArgs.bufSize (default 262144); multiple of 4                 */
     double input_rate;    /* -r  rate of the IQ input; read only under FMD_FLAG_QUALITY (the
@@ -131,7 +133,7 @@ int fmd_host_unregister(void *ptr);
 size_t fmd_out_count(const fmd_ctx *ctx, size_t nbytes);
 /* upper bound of fmd_out_count over every stream position (sizes output buffers) */
 size_t fmd_max_out_count(const fmd_ctx *ctx, size_t nbytes);
-/* FMD_FLAG_QUALITY: forget the carried filter state and stream position (waits for the device).
+/* FMD_FLAG_QUALITY / -q1: forget the carried state and stream position (waits for the device).
  * No effect otherwise: the reference keeps no state between chunks (src/matrix.c:272). */
 int fmd_reset(fmd_ctx *ctx);
 

@@ -162,6 +162,30 @@ void fmo_normalize(const uint8_t *in, size_t n, float *out) {
 }
 
 /* src/matrix.c:159-176: s0*conj(s1) over NON-overlapping pairs, atan2f, NaN->0 */
+/*
+ * src/matrix.c:120-140 (-q1, correctIq): walks the chunk from both ends; sample pair k (complex k
+ * from the front, complex nc-1-k from the back) is reduced by the running offsets off[0] (I) and
+ * off[1] (Q), which then move towards the mean of what they were subtracted from:
+ *     off += ((u_front - off) + (u_back - off)) * esr,        esr = (float)(50 / -S)
+ * `off` is a function-local static in the reference: it lives on from chunk to chunk.
+ */
+void fmo_correct_iq(const uint8_t *in, size_t n, float esr, float off[2], float *out) {
+    const size_t half = n >> 1;
+    size_t i;
+    for (i = 0; i < half; i += 2) {
+        out[i] = (float) in[i] - off[0];
+        out[n - i - 2] = (float) in[n - i - 2] - off[0];
+        out[i + 1] = (float) in[i + 1] - off[1];
+        out[n - i - 1] = (float) in[n - i - 1] - off[1];
+        {
+            const float s0 = out[i] + out[n - i - 2], s1 = out[i + 1] + out[n - i - 1];
+            const float d0 = s0 * esr, d1 = s1 * esr;
+            off[0] = off[0] + d0;
+            off[1] = off[1] + d1;
+        }
+    }
+}
+
 void fmo_discriminate(const float *iq, size_t n, float *out) {
     size_t p;
     for (p = 0; p + 3 < n; p += 4) {
@@ -293,7 +317,7 @@ static void complex_pass(const float *xs, size_t nc, size_t L, const float *sos,
  */
 static int one_chunk(const uint8_t *in, size_t B, const fmo_config *cfg,
                      size_t Lin, size_t Lout, const float *sos_in, const float *sos_out,
-                     float *out) {
+                     float off[2], float *out) {
     const size_t n_out = B >> 2, nc = B >> 1;
     const size_t ylen = n_out + 2 * Lout;
     const unsigned conditioner = (cfg->mode >> 2) & 3u;
@@ -304,6 +328,7 @@ static int one_chunk(const uint8_t *in, size_t B, const fmo_config *cfg,
     size_t nspill = 0, i;
     if (!xs || !ys || !dem || !y) return -1;
     if (conditioner == 3u) fmo_normalize(in, B, xs);   /* matrix.c:208-222 */
+    else if (conditioner == 1u) fmo_correct_iq(in, B, (float) (50. / cfg->fs), off, xs); /* matrix.c:209-212 */
     else fmo_shift(in, B, xs);
     if (conditioner == 2u) {                           /* matrix.c:142-157 */
         fmo_design_sos(FMO_BUTTER_HP, 3, 1., cfg->fs, 0., sos_hp);
@@ -337,7 +362,6 @@ size_t fmo_process_chunks(const uint8_t *in, size_t nchunks, size_t B,
     if (cfg->fc_in != 0. && !deg_in) deg_in = cfg->deg_out;          /* matrix.c:190-192 */
     if (cfg->fc_in == 0. && deg_in) return 0;                        /* reference: undefined */
     if (!cfg->deg_out || (B & 3)) return 0;
-    if (((cfg->mode >> 2) & 3u) == 1u) return 0; /* -q1 (correctIq, a serial recurrence across chunks): not restated */
     Lin = fmo_sections(deg_in);
     Lout = fmo_sections(cfg->deg_out);
     /* the aliasing model above assumes the chunk is longer than the head it re-reads */
@@ -348,8 +372,11 @@ size_t fmo_process_chunks(const uint8_t *in, size_t nchunks, size_t B,
         sos_in = malloc(Lin * 6 * sizeof(float));
         fmo_design_sos((cfg->mode >> 1) & 1u, deg_in, cfg->fc_in, cfg->fs, cfg->eps, sos_in);
     }
-    for (c = 0; c < nchunks; ++c)
-        if (one_chunk(in + c * B, B, cfg, Lin, Lout, sos_in, sos_out, out + c * (B >> 2))) return 0;
+    {
+        float off[2] = {0.f, 0.f}; /* -q1: the reference's static offsets, zero at process start */
+        for (c = 0; c < nchunks; ++c)
+            if (one_chunk(in + c * B, B, cfg, Lin, Lout, sos_in, sos_out, off, out + c * (B >> 2))) return 0;
+    }
     free(sos_in);
     free(sos_out);
     return nchunks * (B >> 2);

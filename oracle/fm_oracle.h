@@ -34,7 +34,9 @@ typedef struct {
     unsigned deg_in;  /* -D  (0 = inherit deg_out when fc_in != 0) */
     unsigned deg_out; /* -d                            */
     unsigned mode;    /* bit0: output filter Chebyshev, bit1: input filter Chebyshev,
-                         bits 2-3: input conditioner (-q): 0 shiftOrigin, 3 normalizeInput */
+                         bits 2-3: input conditioner (-q): 0 shiftOrigin, 1 correctIq (state
+                         crosses chunks: one fmo_process_chunks call = one process run),
+                         2 highpassDc, 3 normalizeInput */
 } fmo_config;
 
 size_t fmo_sections(unsigned degree);
@@ -46,6 +48,9 @@ void fmo_design_sos(unsigned kind, unsigned degree, double fc, double fs, double
 void fmo_shift(const uint8_t *in, size_t n, float *out);
 /* u8 -> float in [-1, 1] (-q3) */
 void fmo_normalize(const uint8_t *in, size_t n, float *out);
+
+/* u8 -> float minus a running offset per lane (-q1); `off` carries on from chunk to chunk */
+void fmo_correct_iq(const uint8_t *in, size_t n, float esr, float off[2], float *out);
 
 /* n floats (n/2 complex, n/4 pairs) -> n/4 phase differences */
 void fmo_discriminate(const float *iq, size_t n, float *out);

@@ -62,6 +62,13 @@ CASES = [
     ("q2", "cfg1", 2, ["-S96000", "-l12500", "-q2"], dict(fs=96000.0, fc_out=12500.0, mode=8)),
     ("q2_L", "cfg2", 2, ["-S96000", "-l6500", "-L12500", "-q2"],
      dict(fs=96000.0, fc_out=6500.0, fc_in=12500.0, mode=8)),
+    # -q1: correctIq keeps its offsets in a function-local static, so the shim cannot be driven case
+    # by case in one process: these outputs are the reference CLI's alone, and the oracle PORT is what
+    # is checked against them here.
+    ("q1", "cfg1", 3, ["-S96000", "-l12500", "-q1"], dict(fs=96000.0, fc_out=12500.0, mode=4)),
+    ("q1_L", "cfg2", 3, ["-S96000", "-l6500", "-L12500", "-q1"],
+     dict(fs=96000.0, fc_out=6500.0, fc_in=12500.0, mode=4)),
+    ("q1_cfg3", "cfg3", 2, ["-S48000", "-l15000", "-q1"], dict(fs=48000.0, fc_out=15000.0, mode=4)),
     ("q2_d5_D4_L_m3", "cfg2", 2, ["-S96000", "-l9600", "-L12500", "-q2", "-d5", "-D4", "-m3"],
      dict(fs=96000.0, fc_out=9600.0, fc_in=12500.0, deg_out=5, deg_in=4, mode=8 | 3)),
 ]
@@ -116,7 +123,7 @@ def main() -> None:
             continue
         raw = synth.config_signal(sig_name, nchunks)
         cfg = po.Config(**kw)
-        out = R.run(raw, cfg)
+        out = (po.port() if ((cfg.mode >> 2) & 3) == 1 else R).run(raw, cfg)
         outb = run_binary(raw, flags)
         nb = min(outb.size, out.size)
         assert nb >= out.size, (name, outb.size, out.size)

@@ -13,7 +13,7 @@ B = synth.CHUNK_BYTES
 TOL = 1e-4  # north-star tolerance: max-abs 1e-4 against the reference's CPU output
 
 GOLDEN_CASES = ["cfg1", "cfg2", "cfg3", "default", "d5_L", "m3_L", "m1_d4", "m1_e5_nan", "D7_d4_L", "q3", "q3_L",
-                "q2", "q2_L", "q2_d5_D4_L_m3"]
+                "q2", "q2_L", "q2_d5_D4_L_m3", "q1", "q1_L", "q1_cfg3"]
 
 
 def load_golden(name: str):

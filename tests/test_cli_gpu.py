@@ -44,6 +44,8 @@ CASES = [
     ("cfg1", [], dict()),
     ("cfg2", ["-S96000", "-l6500", "-L12500", "-q3"], dict(fs=96000.0, fc_out=6500.0, fc_in=12500.0, mode=12)),
     ("cfg1", ["-S96000", "-l12500", "-q2"], dict(fs=96000.0, fc_out=12500.0, mode=8)),
+    ("cfg1", ["-S96000", "-l12500", "-q1"], dict(fs=96000.0, fc_out=12500.0, mode=4)),
+    ("cfg2", ["-S96000", "-l6500", "-L12500", "-q1"], dict(fs=96000.0, fc_out=6500.0, fc_in=12500.0, mode=4)),
 ]
 
 
@@ -108,8 +110,8 @@ def test_cli_rejects_undefined_configs(tmp_path):
     synth.config_signal("cfg1", 1).tofile(src)
     r = subprocess.run([CLI, "-i", str(src), "-o", str(tmp_path / "o"), "-D3"], capture_output=True, text=True)
     assert r.returncode != 0 and "-D without -L" in r.stderr
-    r = subprocess.run([CLI, "-i", str(src), "-o", str(tmp_path / "o"), "-q1"], capture_output=True, text=True)
-    assert r.returncode != 0 and "-q1" in r.stderr
+    r = subprocess.run([CLI, "-i", str(src), "-o", str(tmp_path / "o"), "-q2", "-b-6"], capture_output=True, text=True)
+    assert r.returncode != 0 and "-q2" in r.stderr
 
 
 @pytest.mark.skipif(not os.path.exists(SEAM), reason="seam binary (reference main + this backend) not prebuilt")

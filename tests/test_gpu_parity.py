@@ -174,9 +174,24 @@ def test_rejects_what_the_reference_leaves_undefined():
     with pytest.raises(fm.FmdError):
         fm.Demodulator(bufSize=6)
     with pytest.raises(fm.FmdError):
-        fm.Demodulator(mode=0x4)  # -q1
+        fm.Demodulator(mode=0x4, bufSize=262144 + 4)  # -q1 with a chunk its scan cannot tile
     with pytest.raises(fm.FmdError):
         fm.Demodulator(mode=0x8, bufSize=16384)  # -q2 with a scratch buffer small enough to be a recycled heap chunk
+
+
+def test_q1_offsets_live_on_across_calls(oracle_port):
+    """-q1 (correctIq): the running offsets are stream state -- calls of whole chunks continue it,
+    reset() starts over (the reference keeps them in a function-local static)"""
+    cfg = po.Config(fs=96000.0, fc_out=12500.0, mode=4)
+    raw = synth.config_signal("cfg1", 7)
+    want = oracle_port.run(raw, cfg)
+    with fm.Demodulator(**demod_kwargs(cfg)) as d:
+        for _ in range(2):
+            out = np.concatenate([d.process(raw[:B]), d.process(raw[B:4 * B]), d.process(raw[4 * B:])])
+            check_close(out, want, what="-q1 in three calls")
+            d.reset()
+        with pytest.raises(fm.FmdError, match="whole chunks"):
+            d.process(raw[:B + 1000])
 
 
 def test_atan2_special_values():
