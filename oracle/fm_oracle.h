@@ -1,5 +1,5 @@
 /*
- * oracle/fm_oracle.h -- CPU restatement of peads/demodulator's default FM path.
+ * oracle/fm_oracle.h -- CPU restatement of peads/demodulator's FM path (every -q conditioner).
  *
  * TEST INFRASTRUCTURE ONLY.  Nothing in the product (demodulator_b200/, the
  * C-ABI library, the CLI) may include, link or call this.  Callers allowed:
