@@ -115,6 +115,14 @@ def main() -> None:
                "max_abs_err_vs_gpu": err}
 
     peak, peak_src = bench.measured_peak_gbs()
+    traffic = None
+    try:  # dram bytes of the main kernel per launch from the committed ncu capture, scaled to this launch size
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            e = json.load(f).get(a.config)
+        if e:
+            traffic = float(e["dram_bytes_per_launch"]) * n / float(e["samples_per_launch"])
+    except Exception:
+        pass
     bps = 2.0 + 4.0 / decim
     k_avg = k_ms / max(k_n, 1)
     line = {
@@ -124,7 +132,8 @@ def main() -> None:
         "config": {"workload": case["what"], "name": a.config, "samples_per_step": n, "decimation": decim,
                    "l2": f"{2 * n >> 20} MiB of input per step vs 126 MB L2"},
         "roofline": {"bound": "hbm", "achieved": round(bps * n / (ms / a.steps * 1e-3) / 1e9, 1), "peak": peak,
-                     "unit": "GB/s", "frac": round(bps * n / (ms / a.steps * 1e-3) / 1e9 / peak, 4), "traffic": None,
+                     "unit": "GB/s", "frac": round(bps * n / (ms / a.steps * 1e-3) / 1e9 / peak, 4), "traffic": traffic,
+                     "algorithmic_bytes_per_launch": bps * n,
                      "algorithmic_bytes_per_sample": bps, "peak_source": peak_src,
                      "kernel": "fmq_main_kernel", "kernel_ms_avg": round(k_avg, 4),
                      "kernel_share_of_step": round(k_ms / max(ms, 1e-9), 4),
