@@ -12,7 +12,8 @@ for c in cfg1 cfg2 cfg3; do cp gpurun_out/bench_$c.json profiles/${R}_bench_$c.j
 [ -f gpurun_out/bench_ref.json ] && cp gpurun_out/bench_ref.json profiles/${R}_bench_reference_arm.json
 python - <<PY
 import csv,json,collections
-t={}
+import os
+t=json.load(open('profiles/traffic.json')) if os.path.exists('profiles/traffic.json') else {}  # keep the quality_* entries
 for c in ("cfg2","cfg1"):
     rows=list(csv.reader(open(f'profiles/${R}_fast_kernel_{c}_raw.csv')))
     h,u,r=rows[0],rows[1],rows[2]

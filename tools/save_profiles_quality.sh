@@ -51,3 +51,16 @@ for f in ("fmq_main_quality_cfg3", "fmq_main_quality_cfg2"):
     print('  stalls (warps per issue):', ', '.join(f'{n}={v:.2f}' for v, n in sorted(st, reverse=True)[:8]))
 PY
 cat profiles/${R}_quality_ncu_summary.txt
+python - <<PY
+import csv, json, os
+p = "profiles/traffic.json"
+t = json.load(open(p)) if os.path.exists(p) else {}
+for c in ("quality_cfg3", "quality_cfg2"):
+    f = f"profiles/${R}_fmq_main_{c}_raw.csv"
+    if not os.path.exists(f): continue
+    rows = list(csv.reader(open(f))); h, u, r = rows[0], rows[1], rows[2]
+    val = lambda k: float(r[h.index(k)]) * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1}[u[h.index(k)]]
+    t[c] = {"samples_per_launch": 268435456, "dram_bytes_per_launch": val('dram__bytes_read.sum') + val('dram__bytes_write.sum'),
+            "source": f"{f} (fmq_main_kernel: dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture)"}
+json.dump(t, open(p, "w"), indent=1)
+PY
