@@ -237,6 +237,38 @@ def test_random_filter_configurations(seed, oracle_port):
     check_close(out, want, tol=1e-4 + 3e-6 * scale, what=f"seed {seed}: {cfg} bs={bs} n={nbytes}")
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_random_conditioner_configurations(seed, oracle_port):
+    """the -q conditioners under random filters: -q1 (whole chunks, offsets carried from chunk to
+    chunk), -q2 (highpass sweep + its spill into the next stage; ragged tails) and -q3, with and
+    without the input filter, degrees 1..8, both families"""
+    rng = np.random.default_rng(5000 + seed)
+    q = int(1 + seed % 3)
+    deg_out = int(rng.integers(1, 9))
+    with_in = bool(rng.integers(0, 2))
+    deg_in = int(rng.integers(0, 9)) if with_in else 0
+    mode = (int(rng.integers(0, 4)) if with_in else int(rng.integers(0, 2))) | (q << 2)
+    fs = float(rng.choice([48000.0, 96000.0, 250000.0]))
+    fc_out = float(rng.uniform(0.04, 0.3) * fs)
+    fc_in = float(rng.uniform(0.05, 0.3) * fs) if with_in else 0.0
+    bs = int(rng.choice([65536, B, 2 * B]))
+    nbytes = int(rng.integers(1, 4)) * bs
+    if q != 1:
+        nbytes += int(rng.choice([0, 4 * int(rng.integers(64, bs // 8))]))
+    raw = np.resize(synth.config_signal("cfg2", 2, seed=seed), nbytes)
+    cfg = po.Config(fs=fs, fc_in=fc_in, fc_out=fc_out, eps=0.2, deg_in=deg_in, deg_out=deg_out, mode=mode)
+    whole = nbytes // bs * bs
+    want = [oracle_port.run(raw[:whole], cfg, chunk_bytes=bs)]
+    if nbytes > whole:
+        want.append(oracle_port.run(raw[whole:], cfg, chunk_bytes=nbytes - whole))
+    want = np.concatenate(want)
+    with fm.Demodulator(bufSize=bs, **demod_kwargs(cfg)) as d:
+        out = d.process(raw)
+    assert out.size == want.size
+    scale = float(np.abs(want[np.isfinite(want)]).max(initial=1.0))
+    check_close(out, want, tol=1e-4 + 3e-6 * scale, what=f"seed {seed}: {cfg} bs={bs} n={nbytes}")
+
+
 @pytest.mark.parametrize("nbytes,bs,with_in", [(3 * B, B, True), (B + 1000 * 4, B, True), (B + 516, B, False),
                                                (5 * 4096 + 260, 4096, True), (7 * 512, 512, False),
                                                (2 * B - 4, B, True), (640, 64, True)])
