@@ -218,6 +218,75 @@ fmd_exact_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const 
 }
 
 
+/*
+ * The same op-for-op evaluation for WHOLE chunks (FMD_FLAG_EXACT, -q1, a conditioner stacked under
+ * -L, chunk sizes the streaming kernel does not take), staged through shared memory.  A CTA owns
+ * FMD_XT consecutive outputs of one chunk: the conditioned lanes it needs are evaluated once into
+ * shared memory, then the input-filtered lanes from those, then the discriminator outputs, then
+ * the output sweep -- the very same cones (fmd_sweep_cone) with the very same operations, but each
+ * intermediate value is computed once per CTA instead of once per consumer per consumer per
+ * consumer.  Measured on B200: 4-8x the one-thread-per-output form above.
+ */
+#define FMD_XT 256                                           /* outputs per CTA                 */
+#define FMD_XX (FMD_XT + FMD_CONE_W + 1)                     /* discriminator outputs it needs  */
+#define FMD_XZ (2 * FMD_XX)                                  /* complex samples they come from  */
+#define FMD_XC (FMD_XZ + FMD_CONE_W + 1)                     /* conditioned samples under those */
+
+struct FmdStagedLane { /* lane values staged in shared memory, from complex index `base` on */
+    const float *buf;
+    long long base;
+    __device__ float operator()(long long c) const { return buf[c - base]; }
+};
+
+__global__ void __launch_bounds__(FMD_XT)
+fmd_exact_tiled_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const FmdGeom g,
+                       const FmdSections *__restrict__ sec) {
+    __shared__ float xl[2][FMD_XC]; /* conditioned lanes I, Q                 */
+    __shared__ float zl[2][FMD_XZ]; /* after the input filter                 */
+    __shared__ float xd[FMD_XX];    /* discriminator outputs                  */
+    const unsigned tiles_per_chunk = (g.chunk_out + FMD_XT - 1u) / FMD_XT;
+    const unsigned chunk = blockIdx.x / tiles_per_chunk;
+    const unsigned k0 = (blockIdx.x - chunk * tiles_per_chunk) * FMD_XT;
+    const uint8_t *cin = in + (unsigned long long) chunk * g.chunk_stride;
+    const long long n_out = g.chunk_out, nc = 2ll * g.chunk_out, c0 = 2ll * k0;
+    const bool filtered = sec->lin != 0;
+
+    for (unsigned i = threadIdx.x; i < 2u * FMD_XC; i += FMD_XT) {
+        const int q = (int) (i & 1u);
+        xl[q][i >> 1] = FmdConditionedLane{cin, nc, sec, q}(c0 + (long long) (i >> 1));
+    }
+    __syncthreads();
+    if (filtered) {
+        for (unsigned i = threadIdx.x; i < 2u * FMD_XZ; i += FMD_XT) {
+            const int q = (int) (i & 1u);
+            const FmdStagedLane sx{xl[q], c0};
+            zl[q][i >> 1] = fmd_sweep_cone(c0 + (long long) (i >> 1), nc, sec->lin, sec->in, q == 0, sx,
+                                           FmdConditionerSpill{FmdConditionedLane{cin, nc, sec, q}});
+        }
+        __syncthreads();
+    }
+    const float(*zz)[FMD_XZ] = zl;
+    for (unsigned i = threadIdx.x; i < FMD_XX; i += FMD_XT) {
+        const long long j = (long long) k0 + i;
+        float x = 0.0f; /* zero past the end of the chunk (demodRet slack, matrix.c:184) */
+        if (j < n_out) {
+            const float a = filtered ? zz[0][2 * i] : xl[0][2 * i], b = filtered ? zz[1][2 * i] : xl[1][2 * i];
+            const float c = filtered ? zz[0][2 * i + 1] : xl[0][2 * i + 1], d = filtered ? zz[1][2 * i + 1] : xl[1][2 * i + 1];
+            const float re = __fadd_rn(__fmul_rn(a, c), __fmul_rn(b, d));
+            const float im = __fadd_rn(__fmul_rn(-a, d), __fmul_rn(b, c));
+            x = fmd_atan2(im, re);
+        }
+        xd[i] = x;
+    }
+    __syncthreads();
+    const unsigned k = k0 + threadIdx.x;
+    if (k < g.chunk_out) {
+        const FmdStagedLane sx{xd, (long long) k0};
+        out[(unsigned long long) chunk * g.chunk_out + k] =
+            fmd_sweep_cone((long long) k, n_out, sec->lout, sec->out, true, sx, FmdSpillInit{cin, nc, sec});
+    }
+}
+
 /* --------------------------------------------------------------- fast kernel */
 
 #define FMD_FILL 0x7f7f7f7fu /* four bytes that shift to 0.0: the zero extension past a chunk */

@@ -412,16 +412,15 @@ static fast_fn pick_fast(unsigned nti, unsigned nto, unsigned at, unsigned condi
     return at <= 6 ? pick_in<6>(nti, nto) : pick_in<8>(nti, nto);
 }
 
-/* every output of every chunk through the op-for-op path */
+/* every output of every chunk through the op-for-op path (staged through shared memory) */
 static int launch_exact(fmd_ctx *c, const uint8_t *d_in, float *d_out, FmdGeom g, cudaStream_t s) {
     if (!g.chunk_out || !g.nchunks) return FMD_OK;
     g.head = g.chunk_out;
     g.fast_out = g.chunk_out;
-    const unsigned long long total = (unsigned long long) g.nchunks * g.chunk_out;
-    const unsigned long long blocks = (total + FMD_BLOCK - 1) / FMD_BLOCK;
+    const unsigned long long blocks = (unsigned long long) g.nchunks * ((g.chunk_out + FMD_XT - 1u) / FMD_XT);
     if (blocks > 0x7fffffffull) return fmd_set_error(FMD_EINVAL, "exact kernel grid too large");
     g.exact_blocks = (unsigned) blocks;
-    fmd_exact_kernel<<<(unsigned) blocks, FMD_BLOCK, 0, s>>>(d_in, d_out, g, c->d_sec);
+    fmd_exact_tiled_kernel<<<(unsigned) blocks, FMD_XT, 0, s>>>(d_in, d_out, g, c->d_sec);
     FMD_CUDA(cudaGetLastError());
     c->launches++;
     return FMD_OK;
