@@ -77,17 +77,25 @@ fmd_correctiq_kernel(const uint8_t *__restrict__ in, float *__restrict__ sbuf, c
     }
     /* the reference's loop body, operation for operation (matrix.c:129-138) */
     float off0 = v[0][0], off1 = v[1][0];
-    float2 *__restrict__ sf = reinterpret_cast<float2 *>(sbuf + chunk * g.chunk_bytes) + k0;
-    float2 *__restrict__ sb = reinterpret_cast<float2 *>(sbuf + chunk * g.chunk_bytes) + (nc - 1u - k0);
+    /* FMQ_T divides the steps of a chunk, so cnt is 0 or FMQ_T: steps go in pairs, 16 bytes per store */
+    float4 *__restrict__ sf = reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(sbuf + chunk * g.chunk_bytes) + k0);
+    float4 *__restrict__ sb =
+        reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(sbuf + chunk * g.chunk_bytes) + (nc - 2u - k0));
 #pragma unroll 4
-    for (unsigned k = 0; k < cnt; ++k) {
-        const unsigned f = front[k], b = back[-(int) k];
-        const float fi = __fsub_rn((float) (f & 0xffu), off0), bi = __fsub_rn((float) (b & 0xffu), off0);
-        const float fq = __fsub_rn((float) (f >> 8), off1), bq = __fsub_rn((float) (b >> 8), off1);
-        sf[k] = make_float2(fi, fq);
-        sb[-(int) k] = make_float2(bi, bq);
-        off0 = __fadd_rn(off0, __fmul_rn(__fadd_rn(fi, bi), g.esr));
-        off1 = __fadd_rn(off1, __fmul_rn(__fadd_rn(fq, bq), g.esr));
+    for (unsigned k = 0; k + 1 < cnt; k += 2) {
+        float fi[2], fq[2], bi[2], bq[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const unsigned f = front[k + j], b = back[-(int) (k + j)];
+            fi[j] = __fsub_rn((float) (f & 0xffu), off0);
+            bi[j] = __fsub_rn((float) (b & 0xffu), off0);
+            fq[j] = __fsub_rn((float) (f >> 8), off1);
+            bq[j] = __fsub_rn((float) (b >> 8), off1);
+            off0 = __fadd_rn(off0, __fmul_rn(__fadd_rn(fi[j], bi[j]), g.esr));
+            off1 = __fadd_rn(off1, __fmul_rn(__fadd_rn(fq[j], bq[j]), g.esr));
+        }
+        sf[k >> 1] = make_float4(fi[0], fq[0], fi[1], fq[1]);
+        sb[-(int) (k >> 1)] = make_float4(bi[1], bq[1], bi[0], bq[0]); /* complex nc-2-k0-k, then nc-1-k0-k */
     }
 }
 

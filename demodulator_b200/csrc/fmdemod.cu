@@ -417,6 +417,17 @@ static int launch_exact(fmd_ctx *c, const uint8_t *d_in, float *d_out, FmdGeom g
     if (!g.chunk_out || !g.nchunks) return FMD_OK;
     g.head = g.chunk_out;
     g.fast_out = g.chunk_out;
+    if (g.chunk_out < FMD_XT) {
+        /* chunks shorter than a tile (-b down to 4 bytes): one thread per output, no staging */
+        const unsigned long long total = (unsigned long long) g.nchunks * g.chunk_out;
+        const unsigned long long nb = (total + FMD_BLOCK - 1) / FMD_BLOCK;
+        if (nb > 0x7fffffffull) return fmd_set_error(FMD_EINVAL, "exact kernel grid too large");
+        g.exact_blocks = (unsigned) nb;
+        fmd_exact_kernel<<<(unsigned) nb, FMD_BLOCK, 0, s>>>(d_in, d_out, g, c->d_sec);
+        FMD_CUDA(cudaGetLastError());
+        c->launches++;
+        return FMD_OK;
+    }
     const unsigned long long blocks = (unsigned long long) g.nchunks * ((g.chunk_out + FMD_XT - 1u) / FMD_XT);
     if (blocks > 0x7fffffffull) return fmd_set_error(FMD_EINVAL, "exact kernel grid too large");
     g.exact_blocks = (unsigned) blocks;
