@@ -20,6 +20,7 @@ MAX_SECTIONS = 8
 MAX_TAPS = 6
 FLAG_EXACT = 1
 FLAG_QUALITY = 2
+FLAG_S16 = 4
 
 
 class FmdError(RuntimeError):
@@ -126,13 +127,14 @@ class Demodulator:
     def __init__(self, sampleRate: float = 125000.0, lowpassIn: float = 0.0, lowpassOut: float = 12500.0,
                  epsilon: float = 0.3, inFilterDegree: int = 0, outFilterDegree: int = 3, mode: int = 0,
                  bufSize: int = DEFAULT_CHUNK_BYTES, device: int = 0, exact: bool = False,
-                 quality: bool = False, inputRate: float = 0.0) -> None:
+                 quality: bool = False, inputRate: float = 0.0, s16: bool = False) -> None:
         """quality=True selects the opt-in stream pipeline (FMD_FLAG_QUALITY: recursive filters with
-        carried state, adjacent-sample discriminator, decimation by inputRate / sampleRate)."""
+        carried state, adjacent-sample discriminator, decimation by inputRate / sampleRate); s16=True
+        (with quality) makes the outputs signed 16-bit samples (FMD_FLAG_S16: 1.0 = 32768, clipped)."""
         self._L = load_library()
         self._ctx = C.c_void_p()
         cfg = _Config(sampleRate, lowpassIn, lowpassOut, epsilon, inFilterDegree, outFilterDegree,
-                      (mode & 0x3f) | 0x10, (FLAG_EXACT if exact else 0) | (FLAG_QUALITY if quality else 0),
+                      (mode & 0x3f) | 0x10, (FLAG_EXACT if exact else 0) | (FLAG_QUALITY if quality else 0) | (FLAG_S16 if s16 else 0),
                       bufSize, inputRate)
         _check(self._L.fmd_create(C.byref(cfg), device, C.byref(self._ctx)))
         eff = _Config()
@@ -141,6 +143,7 @@ class Demodulator:
         self.inFilterDegree = int(eff.in_degree)
         self.outFilterDegree = int(eff.out_degree)
         self.device = device
+        self.out_dtype = np.int16 if s16 else np.float32
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self) -> None:
@@ -188,8 +191,8 @@ class Demodulator:
                                    np.uint8)
         n = self.out_count(raw.size)
         if out is None:
-            out = np.empty(n, np.float32)
-        assert out.dtype == np.float32 and out.size >= n and out.flags.c_contiguous
+            out = np.empty(n, self.out_dtype)
+        assert out.dtype == self.out_dtype and out.size >= n and out.flags.c_contiguous
         got = C.c_size_t(0)
         _check(self._L.fmd_demod_host(self._ctx, raw.ctypes.data, raw.size, out.ctypes.data, C.byref(got)))
         return out[:got.value]

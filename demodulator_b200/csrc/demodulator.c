@@ -5,7 +5,7 @@
  *
  *   demodulator -i <file|-> -o <file|-> [-L fcIn] [-l fcOut] [-S fs] [-d degOut] [-D degIn]
  *               [-m bits] [-e eps] [-b shift] [-q n] [-c n] [-r x] [-n x]
- *               [-Q -r inputRate]      (extension: the opt-in quality pipeline, FMD_FLAG_QUALITY --
+ *               [-Q -r inputRate [-F s16]]  (extension: the opt-in quality pipeline, FMD_FLAG_QUALITY --
  *                                       recursive filters with carried state, adjacent-sample
  *                                       discriminator, output decimated to -S; one GPU, one stream)
  *
@@ -63,6 +63,7 @@ typedef struct {
     int in_regular, out_regular; /* regular files: positioned I/O, several threads */
     unsigned long long in_size;  /* bytes, when in_regular */
     size_t chunk, slot_bytes;
+    size_t out_elem; /* bytes per output sample: 4, or 2 with -F s16 */
     unsigned nslots;
     slot_t *slots;
     fmd_ctx *ctx[MAX_DEV];
@@ -182,7 +183,7 @@ static void *writer_main(void *arg) {
             const size_t nf = s->nout;
             /* reference-compatible mode: a slot yields as many output bytes as it had input bytes,
              * so slot n lands at n*slot_bytes (positioned writes are off in quality mode) */
-            if (!h->error && write_all(h->out_fd, s->out, nf * sizeof(float), h->out_regular,
+            if (!h->error && write_all(h->out_fd, s->out, nf * h->out_elem, h->out_regular,
                                        (off_t) (n * (unsigned long long) h->slot_bytes))) {
                 perror("demodulator: write");
                 h->error = -4;
@@ -230,7 +231,7 @@ int main(int argc, char **argv) {
 
     if (argc < 3) return -1; /* src/main.c:122-123 */
 
-    while ((opt = getopt(argc, argv, "i:o:r:L:l:S:D:d:e:m:b:c:q:n:Q")) != -1) {
+    while ((opt = getopt(argc, argv, "i:o:r:L:l:S:D:d:e:m:b:c:q:n:QF:")) != -1) {
         switch (opt) {
             case 'i': /* any argument containing '-' means stdin (src/main.c:128) */
                 h.in_fd = strstr(optarg, "-") ? STDIN_FILENO : open(optarg, O_RDONLY);
@@ -260,6 +261,12 @@ int main(int argc, char **argv) {
              * rate -r to the output rate -S.  Without -Q, -r is parsed and ignored like the
              * reference does (src/main.c:180). */
             case 'Q': cfg.flags |= FMD_FLAG_QUALITY; break;
+            /* -F s16 (with -Q): signed 16-bit output, what the sox stage of the reference's pipelines
+             * would make of the floats -- `... -Q -r2400000 -S48000 -F s16 | dsd -i - ...` */
+            case 'F':
+                if (!strcmp(optarg, "s16")) cfg.flags |= FMD_FLAG_S16;
+                else if (strcmp(optarg, "f32")) { fprintf(stderr, "demodulator: -F takes f32 or s16\n"); ret += 1; }
+                break;
             case 'r': cfg.input_rate = (double) strtold(optarg, NULL); break;
             default: break; /* -n: accepted and ignored, like the reference */
         }
@@ -313,6 +320,7 @@ int main(int argc, char **argv) {
         if (fmd_create(&cfg, devs[d], &h.ctx[d])) die("fmd_create");
 
     h.chunk = (size_t) cfg.chunk_bytes;
+    h.out_elem = (cfg.flags & FMD_FLAG_S16) ? sizeof(int16_t) : sizeof(float);
     {
         size_t mb = (e = getenv("FMD_SLOT_MB")) ? (size_t) atol(e) : 32;
         unsigned depth = (e = getenv("FMD_SLOTS")) ? (unsigned) atoi(e) : 3;

@@ -831,4 +831,19 @@ fmq_scan_tiles_kernel(const float *__restrict__ E, float *__restrict__ Q, float 
     }
 }
 
+/* ------------------------------------------------------------- egress: float32 -> signed 16 bit */
+
+/*
+ * FMD_FLAG_S16: what the `sox ... -e signed-integer -b16` stage of the reference's pipelines does to
+ * the float stream (README.md:22,29) -- full scale 1.0 = 32768, round to nearest, clip -- applied to
+ * the decimated outputs, so that `demodulator -Q ... -S48000` feeds dsd / multimon-ng directly.
+ */
+__global__ void __launch_bounds__(256)
+fmq_to_s16_kernel(const float *__restrict__ y, short *__restrict__ o, const unsigned n) {
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= n) return;
+    const float v = fminf(fmaxf(rintf(y[i] * 32768.0f), -32768.0f), 32767.0f);
+    o[i] = (short) (int) v;
+}
+
 #endif /* FMD_QUALITY_CUH */

@@ -36,6 +36,8 @@ struct fmq_ctx {
     FmqState *d_state = nullptr;
     float *d_ein = nullptr, *d_qin = nullptr, *d_eout = nullptr, *d_qout = nullptr; /* per-tile scratch */
     unsigned *d_lb = nullptr; /* look-back ticket + per-tile flags */
+    float *d_y = nullptr;     /* FMD_FLAG_S16: the float outputs of a launch, before the conversion */
+    size_t y_cap = 0;
     unsigned tile_cap = 0;
     bool smem_opted_in = false;
     unsigned long long pos = 0; /* stream position: global index of the next input sample */
@@ -95,6 +97,7 @@ void fmq_free(fmd_ctx *c) {
     if (q->d_eout) cudaFree(q->d_eout);
     if (q->d_qout) cudaFree(q->d_qout);
     if (q->d_lb) cudaFree(q->d_lb);
+    if (q->d_y) cudaFree(q->d_y);
     delete q;
     c->q = nullptr;
 }
@@ -186,6 +189,22 @@ static int quality_launch(fmd_ctx *c, const uint8_t *d_in, unsigned n, float *d_
         memcpy(wtile_in.m, q->fin.c_tile.warp, sizeof wtile_in.m); /* A^(32 TILE): one look-back round */
     }
 
+    /* FMD_FLAG_S16: the kernels write floats into a scratch of the context; the caller's buffer
+     * receives the converted samples at the end */
+    const bool s16 = (c->cfg.flags & FMD_FLAG_S16) != 0;
+    float *const user_out = d_out;
+    if (s16) {
+        if (g.n_out > q->y_cap) {
+            if (q->d_y) cudaFree(q->d_y);
+            q->d_y = nullptr;
+            q->y_cap = 0;
+            const size_t cap = g.n_out < (1u << 20) ? (1u << 20) : g.n_out;
+            FMD_CUDA(cudaMalloc(&q->d_y, cap * sizeof(float)));
+            q->y_cap = cap;
+        }
+        d_out = q->d_y;
+    }
+
     fmq_main_fn fn = quality_pick_main(q->lin ? c->cfg.in_degree : 0u, c->cfg.out_degree);
     if (!fn) return fmd_set_error(FMD_EINVAL, "no quality kernel for degrees %u/%u", c->cfg.in_degree, c->cfg.out_degree);
     /* shared memory for the kept samples of one tile */
@@ -229,6 +248,10 @@ static int quality_launch(fmd_ctx *c, const uint8_t *d_in, unsigned n, float *d_
             if (g.n_out) fmq_zir_kernel<6><<<zgrid, 256, 0, s>>>(d_out, g, zl, q->fout.ckn(), q->d_qout);
             break;
     }
+    if (s16 && g.n_out) {
+        fmq_to_s16_kernel<<<(g.n_out + 255u) / 256u, 256, 0, s>>>(d_out, reinterpret_cast<short *>(user_out), g.n_out);
+        c->launches++;
+    }
     FMD_CUDA(cudaGetLastError());
     c->launches += g.n_out ? 3 : 2;
     q->pos += n;
@@ -237,8 +260,8 @@ static int quality_launch(fmd_ctx *c, const uint8_t *d_in, unsigned n, float *d_
 
 int fmq_demod_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, float *d_out, cudaStream_t s) {
     if (nbytes & 1u) return fmd_set_error(FMD_EINVAL, "quality mode takes whole IQ samples (an even number of bytes)");
-    if (((uintptr_t) d_in % 16) || ((uintptr_t) d_out % 4))
-        return fmd_set_error(FMD_EINVAL, "quality mode needs a 16-byte aligned input and a 4-byte aligned output");
+    if (((uintptr_t) d_in % 16) || ((uintptr_t) d_out % ((c->cfg.flags & FMD_FLAG_S16) ? 2 : 4)))
+        return fmd_set_error(FMD_EINVAL, "quality mode needs a 16-byte aligned input and an aligned output");
     size_t left = nbytes / 2;
     const size_t step = (size_t) 1 << 30; /* a multiple of the tile: later groups stay 16-byte aligned */
     while (left) {
@@ -247,7 +270,8 @@ int fmq_demod_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, float *d_ou
         int rc = quality_launch(c, d_in, n, d_out, s, &nout);
         if (rc) return rc;
         d_in += 2ull * n;
-        d_out += nout;
+        if (c->cfg.flags & FMD_FLAG_S16) d_out = reinterpret_cast<float *>(reinterpret_cast<short *>(d_out) + nout);
+        else d_out += nout;
         left -= n;
     }
     return FMD_OK;

@@ -126,6 +126,8 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
                              (unsigned long long) cfg.chunk_bytes, cfg.in_degree);
     const unsigned conditioner = (cfg.mode >> 2) & 3u;
     const bool quality = (cfg.flags & FMD_FLAG_QUALITY) != 0;
+    if ((cfg.flags & FMD_FLAG_S16) && !quality)
+        return fmd_set_error(FMD_EINVAL, "FMD_FLAG_S16 is an egress of the quality pipeline (FMD_FLAG_QUALITY) only");
     unsigned q_decim = 1;
     if (quality) {
         if (cfg.flags & FMD_FLAG_EXACT)
@@ -616,7 +618,8 @@ extern "C" int fmd_submit(fmd_ctx *c, unsigned slot, const uint8_t *in, size_t n
     if (rc) return rc;
     FMD_CUDA(cudaEventRecord(s.ev_k, c->s_k));
     FMD_CUDA(cudaStreamWaitEvent(c->s_out, s.ev_k, 0));
-    FMD_CUDA(cudaMemcpyAsync(out, s.d_out, nout * sizeof(float), cudaMemcpyDeviceToHost, c->s_out));
+    const size_t out_elem = (c->cfg.flags & FMD_FLAG_S16) ? sizeof(short) : sizeof(float);
+    FMD_CUDA(cudaMemcpyAsync(out, s.d_out, nout * out_elem, cudaMemcpyDeviceToHost, c->s_out));
     FMD_CUDA(cudaEventRecord(s.ev_out, c->s_out));
     s.busy = true;
     return FMD_OK;
@@ -658,7 +661,9 @@ extern "C" int fmd_demod_host(fmd_ctx *c, const uint8_t *in, size_t nbytes, floa
         const size_t len = nbytes - off < c->slot_bytes ? nbytes - off : c->slot_bytes;
         int rc = fmd_wait(c, slot);
         const size_t produced = fmd_out_count(c, len); /* before the submit moves the stream on */
-        if (!rc) rc = fmd_submit(c, slot, in + off, len, out + out_off);
+        float *dst = (c->cfg.flags & FMD_FLAG_S16) ? reinterpret_cast<float *>(reinterpret_cast<short *>(out) + out_off)
+                                                   : out + out_off;
+        if (!rc) rc = fmd_submit(c, slot, in + off, len, dst);
         if (rc) return rc;
         off += len;
         out_off += produced;

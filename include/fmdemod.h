@@ -58,7 +58,15 @@ enum {
      * order on one stream), fmd_reset starts a new one.  Needs input_rate / sample_rate to be an
      * integer >= 1, degrees <= 6, -q0, and cut-offs of at least input_rate / 1000 (float32 state).
      */
-    FMD_FLAG_QUALITY = 2u
+    FMD_FLAG_QUALITY = 2u,
+    /*
+     * Egress adapter of the quality pipeline (with FMD_FLAG_QUALITY only): the decimated outputs
+     * leave as signed 16-bit samples -- full scale 1.0 = 32768, round to nearest, clip -- i.e. what
+     * the `sox -e signed-integer -b16` stage of the reference's pipelines (README.md:22,29) does to
+     * the float stream.  Every `float *out` argument then points at int16_t storage (cast it);
+     * fmd_out_count still counts samples.
+     */
+    FMD_FLAG_S16 = 4u
 };
 
 /*

@@ -167,6 +167,31 @@ def test_quality_constant_tone_property():
     assert float(settled.std()) < 2e-3  # 8-bit quantisation noise through a 15 kHz lowpass
 
 
+def test_quality_s16_egress(tmp_path_nodash, oracle_port):
+    """FMD_FLAG_S16 / -F s16: the decimated outputs as signed 16-bit samples (1.0 = 32768, round to
+    nearest, clip) -- the oracle's floats quantised the same way, give or take one step where the GPU's
+    float sits on the other side of a rounding boundary"""
+    g, cfg, raw, rate = load_quality("quality_cfg3")
+    y = oracle_port.quality(cfg, rate).run(raw).astype(np.float64)
+    want = np.clip(np.rint(y * 32768.0), -32768, 32767).astype(np.int16)
+    with fm.Demodulator(s16=True, **quality_kwargs(cfg, rate)) as d:
+        out = np.concatenate([d.process(raw[: 2 * 150001]), d.process(raw[2 * 150001:])])
+    assert out.dtype == np.int16 and out.size == want.size
+    diff = np.abs(out.astype(np.int32) - want.astype(np.int32))
+    assert diff.max() <= 1 and (diff != 0).mean() < 0.05, (int(diff.max()), float((diff != 0).mean()))
+    # clipping: a gain-free 0.2 rad signal never clips, so drive the clip path through the CLI on a loud one
+    src, dst = tmp_path_nodash / "in.u8", tmp_path_nodash / "out.s16"
+    raw.tofile(src)
+    r = subprocess.run([CLI, "-i", str(src), "-o", str(dst), "-Q", "-r2400000", "-S48000", "-l15000", "-F", "s16"],
+                       capture_output=True, text=True, env=dict(os.environ, FMD_SLOT_MB="1"))
+    assert r.returncode == 0, r.stderr
+    cli = np.fromfile(dst, np.int16)
+    want_cli = want[: oracle_port.quality(cfg, rate).run(raw[: raw.size & ~3]).size]
+    assert cli.size == want_cli.size and np.abs(cli.astype(np.int32) - want_cli.astype(np.int32)).max() <= 1
+    with pytest.raises(fm.FmdError, match="FMD_FLAG_S16"):
+        fm.Demodulator(s16=True)
+
+
 def test_quality_cli(tmp_path_nodash, oracle_port):
     g, cfg, raw, rate = load_quality("quality_cfg3")
     src, dst = tmp_path_nodash / "in.u8", tmp_path_nodash / "out.f32"
