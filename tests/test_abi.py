@@ -87,3 +87,33 @@ def test_cli_fails_loudly_without_gpu(tmp_path):
     src.write_bytes(bytes(1024))
     r = subprocess.run([CLI, "-i", str(src), "-o", str(tmp_path / "out.f32")], capture_output=True, text=True)
     assert r.returncode != 0 and "no CUDA device" in r.stderr
+
+
+def test_cli_reports_configuration_errors_before_it_needs_a_gpu(tmp_path):
+    """the C host validates through fmd_create: argument errors come out as such (exit 2, message on
+    stderr) on any machine; with valid arguments and no GPU it says that there is no CPU path"""
+    import subprocess
+    cli = os.path.join(ROOT, "demodulator_b200", "bin", "demodulator")
+    if not os.path.exists(cli):
+        pytest.skip("CLI not built")
+    src = tmp_path / "in.u8"
+    src.write_bytes(b"\x80\x7f" * 64)
+    d = str(tmp_path).replace("-", "_")  # an -i/-o argument with a '-' means stdin/stdout (src/main.c:128)
+    os.makedirs(d, exist_ok=True)
+    inp, outp = os.path.join(d, "in.u8"), os.path.join(d, "out.f32")
+    with open(inp, "wb") as f:
+        f.write(src.read_bytes())
+
+    def run(*flags):
+        r = subprocess.run([cli, "-i", inp, "-o", outp, *flags], capture_output=True, text=True)
+        return r.returncode, r.stderr
+    assert "FMD_FLAG_S16" in run("-F", "s16")[1]
+    assert "not an integer" in run("-Q", "-r100000", "-S48000")[1]
+    assert "-q2" in run("-q2", "-b-6")[1]
+    assert "-D without -L" in run("-D3")[1]
+    rc, err = run("-F", "wav")
+    assert rc == 1 and "f32 or s16" in err
+    rc, err = run("-S96000", "-l12500")
+    import torch
+    if not torch.cuda.is_available():
+        assert rc == 2 and "no CPU path" in err
