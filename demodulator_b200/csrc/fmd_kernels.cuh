@@ -12,7 +12,9 @@
  *      exchanged through memory and there is no block-level barrier.
  *      Computes, per chunk-local output k:
  *          s[c]  = (int8)(u8 - 127)                        shiftOrigin        matrix.c:82-98
+ *                  (-q3: u * (2/255) - 1, normalizeInput, matrix.c:100-118)
  *          z[c]  = dc + sum_t tin[t]  * s[c+t]   (-L only)  applyComplexFilter filter.c:233-259
+ *                  (without -L, -q2's highpass sweep, matrix.c:142-157, takes this place)
  *                  (evaluated as z/tin[0]: the common factor cancels in the atan2 below)
  *          x[k]  = atan2(Im, Re)(z[2k] * conj(z[2k+1]))    fmDemod            matrix.c:159-176
  *          y[k]  = dco + sum_t tout[t] * x[k+t]            applyFilter        filter.c:212-231
@@ -25,6 +27,9 @@
  *      outputs of every chunk when -L is on).  They produce the first few outputs of every
  *      chunk (where the sweep is not in steady state), ragged remainders, chunk sizes the
  *      streaming part does not take, and everything under FMD_FLAG_EXACT (audits).
+ *
+ *  fmd_exact_tiled_kernel -- the same cones for WHOLE chunks, staged through shared memory (audits,
+ *      -q1 after fmd_correctiq.cuh has conditioned the samples, -q2 / -q3 stacked under -L).
  */
 #ifndef FMD_KERNELS_CUH
 #define FMD_KERNELS_CUH
