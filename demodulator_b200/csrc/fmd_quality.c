@@ -104,38 +104,40 @@ void fmq_matpow_f(const fmq_design *d, unsigned long long k, float *out) {
     to_float(m, d->D * d->D, out);
 }
 
-void fmq_build_consts(const fmq_design *d, unsigned unit, fmq_consts *c) {
+void fmq_build_consts(const fmq_design *d, unsigned unit, unsigned tile, fmq_consts *c) {
     memset(c, 0, sizeof *c);
     c->L = d->L;
     c->D = d->D;
     memcpy(c->sos, d->sos, sizeof c->sos);
     for (int j = 0; j < 5; ++j) fmq_matpow_f(d, (unsigned long long) unit << j, c->lvl[j]);
     fmq_matpow_f(d, 32ull * unit, c->warp);
-    fmq_matpow_f(d, (unsigned long long) FMQ_TILE, c->tile);
+    fmq_matpow_f(d, (unsigned long long) tile, c->tile);
 }
 
-void fmq_table_layout(const fmq_design *d, fmq_table_sizes *sz) {
+void fmq_table_layout(const fmq_design *d, unsigned T, fmq_table_sizes *sz) {
     const unsigned D = (unsigned) d->D;
     sz->lane = 32u * D * D;
-    sz->apow = (FMQ_T + 1u) * D * D;
-    sz->ck = FMQ_T * D;
-    sz->ckn = FMQ_TILE * D;
+    sz->apow = (T + 1u) * D * D;
+    sz->ck = T * D;
+    sz->ckn = T * FMQ_THREADS * D;
     sz->lane_tile = 32u * D * D;
 }
 
-unsigned fmq_build_tables(const fmq_design *d, float *lane, float *apow, float *ck, float *ckn, float *lane_tile) {
+unsigned fmq_build_tables(const fmq_design *d, unsigned T, float *lane, float *apow, float *ck, float *ckn,
+                          float *lane_tile) {
     const int D = d->D;
+    const unsigned TILE = T * FMQ_THREADS;
     ld a[FMQ_MAXD * FMQ_MAXD], pt[FMQ_MAXD * FMQ_MAXD], cur[FMQ_MAXD * FMQ_MAXD], tmp[FMQ_MAXD * FMQ_MAXD];
     unsigned zir_len = 1;
     mat_pack(d, a);
-    fmq_matpow(d, FMQ_T, pt);
+    fmq_matpow(d, T, pt);
     mat_identity(D, cur);
     for (int l = 0; l < 32; ++l) { /* (A^T)^l */
         to_float(cur, D * D, lane + l * D * D);
         mat_mul(D, pt, cur, tmp);
         memcpy(cur, tmp, sizeof tmp);
     }
-    fmq_matpow(d, FMQ_TILE, pt);
+    fmq_matpow(d, TILE, pt);
     mat_identity(D, cur);
     for (int l = 0; l < 32; ++l) { /* (A^TILE)^l */
         to_float(cur, D * D, lane_tile + l * D * D);
@@ -143,7 +145,7 @@ unsigned fmq_build_tables(const fmq_design *d, float *lane, float *apow, float *
         memcpy(cur, tmp, sizeof tmp);
     }
     mat_identity(D, cur);
-    for (int k = 0; k <= FMQ_T; ++k) { /* A^k */
+    for (unsigned k = 0; k <= T; ++k) { /* A^k */
         to_float(cur, D * D, apow + k * D * D);
         mat_mul(D, a, cur, tmp);
         memcpy(cur, tmp, sizeof tmp);
@@ -151,10 +153,10 @@ unsigned fmq_build_tables(const fmq_design *d, float *lane, float *apow, float *
     /* row vector C A^k, k = 0 .. TILE-1 (the first T of them are the thread-level table) */
     ld row[FMQ_MAXD], nxt[FMQ_MAXD];
     for (int j = 0; j < D; ++j) row[j] = d->C[j];
-    for (int k = 0; k < FMQ_TILE; ++k) {
+    for (unsigned k = 0; k < TILE; ++k) {
         for (int j = 0; j < D; ++j) {
             ckn[k * D + j] = (float) row[j];
-            if (k < FMQ_T) ck[k * D + j] = (float) row[j];
+            if (k < T) ck[k * D + j] = (float) row[j];
             if (row[j] >= FMQ_ZIR_EPS || row[j] <= -FMQ_ZIR_EPS || row[j] != row[j]) zir_len = (unsigned) k + 1u;
         }
         for (int j = 0; j < D; ++j) {
@@ -170,13 +172,13 @@ unsigned fmq_build_tables(const fmq_design *d, float *lane, float *apow, float *
 /* ---- flat exports for the CPU-side test of the scan algebra (tests/test_quality_tables.py);
  *      not part of include/fmdemod.h ---- */
 
-int fmq_test_sizes(unsigned sections, unsigned *consts_bytes, unsigned sizes[5]) {
+int fmq_test_sizes(unsigned sections, unsigned T, unsigned *consts_bytes, unsigned sizes[5]) {
     fmq_design d;
     memset(&d, 0, sizeof d);
     d.L = (int) sections;
     d.D = 2 * (int) sections;
     fmq_table_sizes sz;
-    fmq_table_layout(&d, &sz);
+    fmq_table_layout(&d, T, &sz);
     *consts_bytes = (unsigned) sizeof(fmq_consts);
     sizes[0] = sz.lane;
     sizes[1] = sz.apow;
@@ -186,14 +188,14 @@ int fmq_test_sizes(unsigned sections, unsigned *consts_bytes, unsigned sizes[5])
     return FMD_OK;
 }
 
-int fmq_test_build(const float *sos6, unsigned sections, fmq_consts *c, fmq_consts *c_tile, float *lane, float *apow,
+int fmq_test_build(const float *sos6, unsigned sections, unsigned T, fmq_consts *c, fmq_consts *c_tile, float *lane, float *apow,
                    float *ck, float *ckn, float *lane_tile, double *abcd /* D*D + D + D + 1 */, unsigned *zir_len) {
     fmq_design d;
     int rc = fmq_design_from_sos(sos6, sections, &d);
     if (rc) return rc;
-    fmq_build_consts(&d, FMQ_T, c);
-    fmq_build_consts(&d, FMQ_TILE, c_tile);
-    *zir_len = fmq_build_tables(&d, lane, apow, ck, ckn, lane_tile);
+    fmq_build_consts(&d, T, T * FMQ_THREADS, c);
+    fmq_build_consts(&d, T * FMQ_THREADS, T * FMQ_THREADS, c_tile);
+    *zir_len = fmq_build_tables(&d, T, lane, apow, ck, ckn, lane_tile);
     int p = 0;
     for (int i = 0; i < d.D; ++i)
         for (int j = 0; j < d.D; ++j) abcd[p++] = (double) d.A[i][j];

@@ -9,7 +9,7 @@
  *
  * The recursions run as a three-level scan with an explicit state carry (fmd_quality.h):
  *
- *   thread  FMQ_T = 64 consecutive samples, serially, from a ZERO state
+ *   thread  T = 64 (or 128, large decimation factors) consecutive samples, serially, from a ZERO state
  *   CTA     affine scan over its 256 threads (warp shuffles with the matrices A^(T*2^j), then a
  *           short serial pass over the 8 warp totals): state at the start of every thread's span
  *   launch  fmq_scan_tiles_kernel scans the per-tile end states of all CTAs (and takes the carry
@@ -199,13 +199,9 @@ __device__ __forceinline__ void fmq_span_end(const float *__restrict__ apow, uns
     }
 }
 
-/* Full spans are walked in FMQ_T / 8 groups of 8 samples (one 16-byte load each); only the body of
+/* Full spans are walked in T / 8 groups of 8 samples (one 16-byte load each); only the body of
  * a group is unrolled, so the instruction footprint stays a quarter of the fully unrolled span
  * (the fully unrolled <2,2> kernel stalled mostly on instruction fetch: ncu `no_instruction`). */
-#define FMQ_GROUPS (FMQ_T / 8)
-#ifndef FMQ_UNR0
-#define FMQ_UNR0 FMQ_GROUPS /* groups unrolled in the main loop when there is no input cascade */
-#endif
 
 __device__ __forceinline__ uint4 fmq_load_group(const uint8_t *__restrict__ in, unsigned F, int grp) {
     return __ldg(reinterpret_cast<const uint4 *>(in + 2ull * F) + grp);
@@ -220,25 +216,25 @@ __device__ __forceinline__ uint4 fmq_load_group(const uint8_t *__restrict__ in, 
  * Input cascade from a zero state over the thread's SHIFTED span: the halo sample (F-1), then
  * samples F .. F+cnt-2.  cnt = number of samples of the x span (0 for a thread past the end).
  */
-template <int LIN, bool FOI>
+template <int LIN, bool FOI, int T>
 __device__ __forceinline__ void fmq_in_zero_state(const fmq_consts &cin, const uint8_t *__restrict__ in, unsigned F,
                                                   unsigned cnt, float hi, float hq, float (&e)[2][2 * LIN]) {
 #pragma unroll
     for (int i = 0; i < 2 * LIN; ++i) e[0][i] = e[1][i] = 0.0f;
-    if (cnt == FMQ_T) {
+    if (cnt == T) {
         fmq_step<LIN, FOI>(cin, e[0], hi);
         fmq_step<LIN, FOI>(cin, e[1], hq);
         uint4 nx = fmq_load_group(in, F, 0);
 #pragma unroll 1
-        for (int grp = 0; grp < FMQ_GROUPS; ++grp) {
+        for (int grp = 0; grp < (T / 8); ++grp) {
             const uint4 v = nx;
-            if (grp + 1 < FMQ_GROUPS) nx = fmq_load_group(in, F, grp + 1);
+            if (grp + 1 < (T / 8)) nx = fmq_load_group(in, F, grp + 1);
 #pragma unroll
             for (int i = 0; i < 7; ++i) {
                 fmq_step<LIN, FOI>(cin, e[0], FMQ_SI(v, i));
                 fmq_step<LIN, FOI>(cin, e[1], FMQ_SQ(v, i));
             }
-            if (grp + 1 < FMQ_GROUPS) { /* the span's very last sample belongs to the next thread's span */
+            if (grp + 1 < (T / 8)) { /* the span's very last sample belongs to the next thread's span */
                 fmq_step<LIN, FOI>(cin, e[0], FMQ_SI(v, 7));
                 fmq_step<LIN, FOI>(cin, e[1], FMQ_SQ(v, 7));
             }
@@ -262,12 +258,13 @@ struct FmqSpan {
     bool last;          /* this thread's span reaches the end of the tile's valid samples          */
 };
 
+template <int T>
 __device__ __forceinline__ FmqSpan fmq_span(const FmqGeom &g, const unsigned tile) {
     FmqSpan s;
-    s.S = tile * (unsigned) FMQ_TILE;
-    s.F = s.S + threadIdx.x * (unsigned) FMQ_T;
-    s.cnt = s.F >= g.n ? 0u : min((unsigned) FMQ_T, g.n - s.F);
-    s.last = s.cnt != 0u && (threadIdx.x == FMQ_THREADS - 1 || s.F + FMQ_T >= g.n);
+    s.S = tile * (unsigned) (T * FMQ_THREADS);
+    s.F = s.S + threadIdx.x * (unsigned) T;
+    s.cnt = s.F >= g.n ? 0u : min((unsigned) T, g.n - s.F);
+    s.last = s.cnt != 0u && (threadIdx.x == FMQ_THREADS - 1 || s.F + T >= g.n);
     return s;
 }
 
@@ -416,7 +413,7 @@ __device__ __forceinline__ void fmq_discriminate2(float pr, float pi, float z0r,
 #define FMQ_MINB (1024 / FMQ_THREADS) /* resident CTAs per SM the register budget of the main kernel is cut for: 32 warps */
 #endif
 
-template <int NIN, int NOUT> /* degrees of the input (0 = none) and output cascades */
+template <int NIN, int NOUT, int T> /* degrees of the input (0 = none) and output cascades; samples per thread */
 __global__ void __launch_bounds__(FMQ_THREADS, FMQ_MINB)
 fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const FmqGeom g, const fmq_consts cin,
                 const fmq_consts cout, const float *__restrict__ lane_in, const float *__restrict__ lane_out,
@@ -429,9 +426,10 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     constexpr bool FOI = (NIN & 1) != 0, FOO = (NOUT & 1) != 0;
     constexpr int DI = 2 * LI1;
     constexpr int DO = 2 * LOUT;
+    constexpr int TILE = T * FMQ_THREADS, GROUPS = T / 8;
     extern __shared__ float ybuf[];                    /* kept v of this tile, zero state at the tile start */
     __shared__ float qs[FMQ_THREADS * DO];             /* output-cascade state at the start of every thread */
-    __shared__ float ck[FMQ_T * DO];
+    __shared__ float ck[T * DO];
     __shared__ float tot_in[FMQ_WARPS * 2 * DI];
     __shared__ float tot_out[FMQ_WARPS * DO];
 
@@ -439,12 +437,12 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     __shared__ float carry_s[2 * DI];
     /* tiles in ticket order: a tile's predecessors have all started (the look-back relies on it) */
     if (threadIdx.x == 0) tile_s = LIN > 0 ? atomicAdd(lb.ticket, 1u) : blockIdx.x;
-    for (unsigned i = threadIdx.x; i < FMQ_T * DO; i += FMQ_THREADS) ck[i] = __ldg(ck_out + i);
+    for (unsigned i = threadIdx.x; i < T * DO; i += FMQ_THREADS) ck[i] = __ldg(ck_out + i);
     __syncthreads();
     const unsigned tile = tile_s;
-    const FmqSpan sp = fmq_span(g, tile);
+    const FmqSpan sp = fmq_span<T>(g, tile);
 
-    const bool full = sp.cnt == FMQ_T;
+    const bool full = sp.cnt == T;
     float hi, hq;
     fmq_halo(in, st, sp.F, sp.cnt, hi, hq);
 
@@ -452,7 +450,7 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     float qi[2][DI];
     if (LIN > 0) {
         float e[2][DI], zero[2][DI];
-        fmq_in_zero_state<LI1, FOI>(cin, in, sp.F, sp.cnt, hi, hq, e);
+        fmq_in_zero_state<LI1, FOI, T>(cin, in, sp.F, sp.cnt, hi, hq, e);
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -465,8 +463,8 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
         /* ... which gives the tile's end state from a zero state (E, held by the last thread with
          * samples).  Its warp publishes E, finds the true state at the tile start by look-back,
          * publishes the true end state S. */
-        const unsigned tile_samples = min((unsigned) FMQ_TILE, g.n - sp.S);
-        const unsigned last_t = (tile_samples + FMQ_T - 1u) / FMQ_T - 1u;
+        const unsigned tile_samples = min((unsigned) TILE, g.n - sp.S);
+        const unsigned last_t = (tile_samples + T - 1u) / T - 1u;
         if ((threadIdx.x >> 5) == (last_t >> 5)) {
             const unsigned lane = threadIdx.x & 31u, src_lane = last_t & 31u;
             float E[2][DI], q0[2][DI];
@@ -562,7 +560,7 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     {
         const unsigned o_first = fmq_kept_below(sp.F, g.r0, g.decim);
         const unsigned long long kfirst = (unsigned long long) g.r0 + (unsigned long long) o_first * g.decim;
-        next = kfirst - sp.F >= (unsigned long long) FMQ_T ? 0xffffffffu : (unsigned) (kfirst - sp.F);
+        next = kfirst - sp.F >= (unsigned long long) T ? 0xffffffffu : (unsigned) (kfirst - sp.F);
         yp = ybuf + (o_first - o_tile) + threadIdx.x;
     }
 
@@ -582,12 +580,12 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     if (full) {
         /* measured on B200: without the input cascade the fully unrolled span is 8 % faster (more
          * freedom for the scheduler); with it the rolled form is 4 % faster (instruction fetch) */
-        constexpr int UNR = LIN > 0 ? 1 : FMQ_UNR0;
+        constexpr int UNR = LIN > 0 ? 1 : GROUPS;
         uint4 nx = fmq_load_group(in, sp.F, 0);
 #pragma unroll(UNR)
-        for (int grp = 0; grp < FMQ_GROUPS; ++grp) {
+        for (int grp = 0; grp < GROUPS; ++grp) {
             const uint4 v = nx;
-            if (grp + 1 < FMQ_GROUPS) nx = fmq_load_group(in, sp.F, grp + 1);
+            if (grp + 1 < GROUPS) nx = fmq_load_group(in, sp.F, grp + 1);
             const unsigned i0 = 8u * (unsigned) grp;
 #pragma unroll
             for (int i = 0; i < 8; i += 2) {
@@ -648,11 +646,11 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     __syncthreads();
 
     /* kept samples: add the thread-level zero-input response, store coalesced */
-    const unsigned tile_end = min(sp.S + (unsigned) FMQ_TILE, g.n);
+    const unsigned tile_end = min(sp.S + (unsigned) TILE, g.n);
     const unsigned count = fmq_kept_below(tile_end, g.r0, g.decim) - o_tile;
     for (unsigned o = threadIdx.x; o < count; o += FMQ_THREADS) {
         const unsigned ks = (unsigned) ((unsigned long long) g.r0 + (unsigned long long) (o_tile + o) * g.decim - sp.S);
-        const unsigned owner = ks / FMQ_T, k = ks % FMQ_T;
+        const unsigned owner = ks / T, k = ks % T;
         float y = ybuf[o + owner];
 #pragma unroll
         for (int i = 0; i < DO; ++i) y = fmaf(ck[k * DO + i], qs[owner * DO + i], y);
@@ -669,13 +667,13 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
  */
 template <int DO>
 __global__ void __launch_bounds__(256)
-fmq_zir_kernel(float *__restrict__ out, const FmqGeom g, const unsigned zir_len,
+fmq_zir_kernel(float *__restrict__ out, const FmqGeom g, const unsigned zir_len, const unsigned tile_samples,
                const float *__restrict__ ckn /* [TILE][DO] */, const float *__restrict__ q_tile /* [ntiles][DO] */) {
-    const unsigned tile = blockIdx.x, S = tile * (unsigned) FMQ_TILE;
+    const unsigned tile = blockIdx.x, S = tile * tile_samples;
     const unsigned o = fmq_kept_below(S, g.r0, g.decim) + blockIdx.y * 256u + threadIdx.x;
     if (o >= g.n_out) return;
     const unsigned long long ks = (unsigned long long) g.r0 + (unsigned long long) o * g.decim;
-    if (ks >= (unsigned long long) S + zir_len || ks >= (unsigned long long) S + FMQ_TILE) return;
+    if (ks >= (unsigned long long) S + zir_len || ks >= (unsigned long long) S + tile_samples) return;
     const unsigned k = (unsigned) (ks - S);
     const float *__restrict__ c = ckn + (size_t) k * DO;
     const float *__restrict__ q = q_tile + (size_t) tile * DO;

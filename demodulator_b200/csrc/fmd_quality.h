@@ -32,6 +32,10 @@ extern "C" {
 #ifndef FMQ_THREADS
 #define FMQ_THREADS 256                   /* threads per CTA                                  */
 #endif
+#define FMQ_T_BIG 128                     /* thread span the quality pipeline picks when the
+                                             decimation factor is large (measured: +11 % at M = 50,
+                                             -25 % at M = 1, where a tile's kept samples then take
+                                             128 KiB of shared memory)                          */
 #define FMQ_WARPS (FMQ_THREADS / 32)
 #define FMQ_TILE (FMQ_T * FMQ_THREADS)    /* samples per CTA: 16384 (32 KiB of input)         */
 #define FMQ_MAXL 3                        /* sections per cascade: degree <= 6                */
@@ -70,13 +74,15 @@ typedef struct fmq_design {
 int fmq_design_from_sos(const float *sos6, unsigned sections, fmq_design *d);
 /* out = A^k, packed row-major D x D */
 void fmq_matpow(const fmq_design *d, unsigned long long k, long double *out);
-/* unit = FMQ_T for the scan over threads, FMQ_TILE for the scan over tiles */
-void fmq_build_consts(const fmq_design *d, unsigned unit, fmq_consts *c);
-void fmq_table_layout(const fmq_design *d, fmq_table_sizes *sz);
+/* unit = T for the scan over threads, T * FMQ_THREADS for the scan over tiles; `tile` = samples per tile */
+void fmq_build_consts(const fmq_design *d, unsigned unit, unsigned tile, fmq_consts *c);
+/* T = samples per thread (FMQ_T or FMQ_T_BIG); a tile is T * FMQ_THREADS samples */
+void fmq_table_layout(const fmq_design *d, unsigned T, fmq_table_sizes *sz);
 /* fills the tables (sizes from fmq_table_layout); returns the number of leading rows of ckn that
  * are not negligible (|C A^k| >= FMQ_ZIR_EPS somewhere in the row): the tile-level zero-input
  * response is applied to those offsets only */
-unsigned fmq_build_tables(const fmq_design *d, float *lane, float *apow, float *ck, float *ckn, float *lane_tile);
+unsigned fmq_build_tables(const fmq_design *d, unsigned T, float *lane, float *apow, float *ck, float *ckn,
+                          float *lane_tile);
 /* float copy of A^k for the launch-dependent transition of a ragged last tile */
 void fmq_matpow_f(const fmq_design *d, unsigned long long k, float *out);
 

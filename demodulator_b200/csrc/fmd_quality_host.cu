@@ -19,7 +19,7 @@ struct fmq_filter {
     fmq_consts c;      /* scan over the threads of a CTA (unit T)   */
     fmq_consts c_tile; /* scan over the tiles of a launch (unit TILE) */
     fmq_table_sizes sz;
-    unsigned zir_len = FMQ_TILE; /* tile offsets whose zero-input response is not negligible */
+    unsigned zir_len = 0; /* tile offsets whose zero-input response is not negligible */
     float *d_tab = nullptr; /* lane | apow | ck | ckn | lane_tile */
     const float *lane() const { return d_tab; }
     const float *apow() const { return d_tab + sz.lane; }
@@ -31,6 +31,7 @@ struct fmq_filter {
 /* FMD_FLAG_QUALITY state of a context (fmd_quality.cuh) */
 struct fmq_ctx {
     unsigned decim = 1;
+    unsigned T = FMQ_T, tile = FMQ_TILE; /* samples per thread / per CTA: FMQ_T_BIG for large decimation factors */
     unsigned lin = 0, lout = 0; /* sections */
     fmq_filter fin, fout;
     FmqState *d_state = nullptr;
@@ -49,16 +50,16 @@ static size_t quality_out_count(unsigned long long pos, size_t nsamp, unsigned M
     return nsamp > r0 ? (size_t) ((nsamp - r0 + M - 1) / M) : 0;
 }
 
-static int quality_upload_filter(fmq_filter &f, const float *sos6, unsigned sections) {
+static int quality_upload_filter(fmq_filter &f, const float *sos6, unsigned sections, unsigned T) {
     int rc = fmq_design_from_sos(sos6, sections, &f.des);
     if (rc) return rc;
-    fmq_build_consts(&f.des, FMQ_T, &f.c);
-    fmq_build_consts(&f.des, FMQ_TILE, &f.c_tile);
-    fmq_table_layout(&f.des, &f.sz);
+    fmq_build_consts(&f.des, T, T * FMQ_THREADS, &f.c);
+    fmq_build_consts(&f.des, T * FMQ_THREADS, T * FMQ_THREADS, &f.c_tile);
+    fmq_table_layout(&f.des, T, &f.sz);
     const size_t n = (size_t) f.sz.lane + f.sz.apow + f.sz.ck + f.sz.ckn + f.sz.lane_tile;
     float *h = (float *) malloc(n * sizeof(float));
     if (!h) return fmd_set_error(FMD_ENOMEM, "out of host memory");
-    f.zir_len = fmq_build_tables(&f.des, h, h + f.sz.lane, h + f.sz.lane + f.sz.apow, h + f.sz.lane + f.sz.apow + f.sz.ck,
+    f.zir_len = fmq_build_tables(&f.des, T, h, h + f.sz.lane, h + f.sz.lane + f.sz.apow, h + f.sz.lane + f.sz.apow + f.sz.ck,
                                  h + f.sz.lane + f.sz.apow + f.sz.ck + f.sz.ckn);
     cudaError_t e = cudaMalloc(&f.d_tab, n * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(f.d_tab, h, n * sizeof(float), cudaMemcpyHostToDevice);
@@ -74,8 +75,16 @@ int fmq_setup(fmd_ctx *c, unsigned decim) {
     q->decim = decim;
     q->lout = c->lout;
     q->lin = c->lin;
-    int rc = quality_upload_filter(q->fout, &c->sec.out[0][0], q->lout);
-    if (!rc && q->lin) rc = quality_upload_filter(q->fin, &c->sec.in[0][0], q->lin);
+    /* measured on B200: 128 samples per thread is +11 % at M = 50 and -25 % at M = 1 (shared memory
+     * for the kept samples of a tile); 64 is the better span up to M = 4 */
+    q->T = decim >= 8 ? FMQ_T_BIG : FMQ_T;
+    if (const char *e = getenv("FMD_QUALITY_T")) { /* tuning experiments only */
+        const int t = atoi(e);
+        if (t == FMQ_T || t == FMQ_T_BIG) q->T = (unsigned) t;
+    }
+    q->tile = q->T * FMQ_THREADS;
+    int rc = quality_upload_filter(q->fout, &c->sec.out[0][0], q->lout, q->T);
+    if (!rc && q->lin) rc = quality_upload_filter(q->fin, &c->sec.in[0][0], q->lin, q->T);
     if (rc) return rc;
     /* the kernels for odd degrees skip the second state of the last (first-order) section */
     if (((c->cfg.out_degree & 1u) && (c->sec.out[q->lout - 1][2] != 0.0f || c->sec.out[q->lout - 1][5] != 0.0f)) ||
@@ -128,31 +137,36 @@ typedef void (*fmq_main_fn)(const uint8_t *, float *, const FmqGeom, const fmq_c
                             const float *, const float *, const float *, const float *, const float *,
                             const FmqLookback, const FmqMat, const FmqMat, float *, FmqState *);
 
-template <int NIN>
+template <int NIN, int T>
 static fmq_main_fn quality_pick_out(unsigned nout) {
     switch (nout) {
-        case 1: return fmq_main_kernel<NIN, 1>;
-        case 2: return fmq_main_kernel<NIN, 2>;
-        case 3: return fmq_main_kernel<NIN, 3>;
-        case 4: return fmq_main_kernel<NIN, 4>;
-        case 5: return fmq_main_kernel<NIN, 5>;
-        case 6: return fmq_main_kernel<NIN, 6>;
+        case 1: return fmq_main_kernel<NIN, 1, T>;
+        case 2: return fmq_main_kernel<NIN, 2, T>;
+        case 3: return fmq_main_kernel<NIN, 3, T>;
+        case 4: return fmq_main_kernel<NIN, 4, T>;
+        case 5: return fmq_main_kernel<NIN, 5, T>;
+        case 6: return fmq_main_kernel<NIN, 6, T>;
         default: return nullptr;
     }
 }
 
 /* by filter DEGREE: an odd degree ends in a first-order section, which the kernels exploit */
-static fmq_main_fn quality_pick_main(unsigned nin, unsigned nout) {
+template <int T>
+static fmq_main_fn quality_pick_in(unsigned nin, unsigned nout) {
     switch (nin) {
-        case 0: return quality_pick_out<0>(nout);
-        case 1: return quality_pick_out<1>(nout);
-        case 2: return quality_pick_out<2>(nout);
-        case 3: return quality_pick_out<3>(nout);
-        case 4: return quality_pick_out<4>(nout);
-        case 5: return quality_pick_out<5>(nout);
-        case 6: return quality_pick_out<6>(nout);
+        case 0: return quality_pick_out<0, T>(nout);
+        case 1: return quality_pick_out<1, T>(nout);
+        case 2: return quality_pick_out<2, T>(nout);
+        case 3: return quality_pick_out<3, T>(nout);
+        case 4: return quality_pick_out<4, T>(nout);
+        case 5: return quality_pick_out<5, T>(nout);
+        case 6: return quality_pick_out<6, T>(nout);
         default: return nullptr;
     }
+}
+
+static fmq_main_fn quality_pick_main(unsigned nin, unsigned nout, unsigned T) {
+    return T == FMQ_T_BIG ? quality_pick_in<FMQ_T_BIG>(nin, nout) : quality_pick_in<FMQ_T>(nin, nout);
 }
 
 /* one launch group: `n` samples (< 2^31) that continue the stream; *nout = floats written */
@@ -160,14 +174,14 @@ static int quality_launch(fmd_ctx *c, const uint8_t *d_in, unsigned n, float *d_
     fmq_ctx *q = c->q;
     FmqGeom g;
     g.n = n;
-    g.ntiles = (n + FMQ_TILE - 1) / FMQ_TILE;
+    g.ntiles = (n + q->tile - 1) / q->tile;
     g.decim = q->decim;
     g.r0 = (unsigned) ((q->decim - q->pos % q->decim) % q->decim);
     g.n_out = (unsigned) quality_out_count(q->pos, n, q->decim);
     *nout = g.n_out;
     int rc = quality_reserve_tiles(q, g.ntiles);
     if (rc) return rc;
-    const unsigned len_last = n - (g.ntiles - 1u) * FMQ_TILE;
+    const unsigned len_last = n - (g.ntiles - 1u) * q->tile;
     /* the scan over tiles: 32 warps, each a run of `runlen` tiles (a multiple of 32) */
     const unsigned nwarps = FMQ_SCAN_THREADS / 32;
     const unsigned runlen = ((g.ntiles + nwarps - 1u) / nwarps + 31u) & ~31u;
@@ -205,11 +219,11 @@ static int quality_launch(fmd_ctx *c, const uint8_t *d_in, unsigned n, float *d_
         d_out = q->d_y;
     }
 
-    fmq_main_fn fn = quality_pick_main(q->lin ? c->cfg.in_degree : 0u, c->cfg.out_degree);
+    fmq_main_fn fn = quality_pick_main(q->lin ? c->cfg.in_degree : 0u, c->cfg.out_degree, q->T);
     if (!fn) return fmd_set_error(FMD_EINVAL, "no quality kernel for degrees %u/%u", c->cfg.in_degree, c->cfg.out_degree);
     /* shared memory for the kept samples of one tile */
-    const unsigned keep_cap = FMQ_TILE / q->decim + 2u;
-    const unsigned keep = keep_cap < FMQ_TILE ? keep_cap : FMQ_TILE;
+    const unsigned keep_cap = q->tile / q->decim + 2u;
+    const unsigned keep = keep_cap < q->tile ? keep_cap : q->tile;
     const size_t smem = (size_t) (keep + FMQ_THREADS) * sizeof(float); /* one pad word per owning thread */
     cudaEvent_t *pe = nullptr;
     rc = fmd_prof_events(c, &pe);
@@ -228,24 +242,24 @@ static int quality_launch(fmd_ctx *c, const uint8_t *d_in, unsigned n, float *d_
 
     memset(&prun, 0, sizeof prun);
     memset(&pl, 0, sizeof pl);
-    fmq_matpow_f(&q->fout.des, (unsigned long long) FMQ_TILE * runlen, prun.m);
+    fmq_matpow_f(&q->fout.des, (unsigned long long) q->tile * runlen, prun.m);
     fmq_matpow_f(&q->fout.des, len_last, pl.m);
     const uint8_t *last = d_in + 2ull * (n - 1u);
     /* zero-input response of the tile carry: only the leading zir_len offsets of every tile */
-    const unsigned zl = q->fout.zir_len < FMQ_TILE ? q->fout.zir_len : FMQ_TILE;
+    const unsigned zl = q->fout.zir_len < q->tile ? q->fout.zir_len : q->tile;
     const dim3 zgrid(g.ntiles, (zl / q->decim + 1u + 255u) / 256u);
     switch (q->lout) {
         case 1:
             fmq_scan_tiles_kernel<2, 1><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_eout, q->d_qout, q->d_state->out_q, q->fout.c_tile, q->fout.lane_tile(), prun, pl, g.ntiles, runlen, last, q->d_state->s_prev);
-            if (g.n_out) fmq_zir_kernel<2><<<zgrid, 256, 0, s>>>(d_out, g, zl, q->fout.ckn(), q->d_qout);
+            if (g.n_out) fmq_zir_kernel<2><<<zgrid, 256, 0, s>>>(d_out, g, zl, q->tile, q->fout.ckn(), q->d_qout);
             break;
         case 2:
             fmq_scan_tiles_kernel<4, 1><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_eout, q->d_qout, q->d_state->out_q, q->fout.c_tile, q->fout.lane_tile(), prun, pl, g.ntiles, runlen, last, q->d_state->s_prev);
-            if (g.n_out) fmq_zir_kernel<4><<<zgrid, 256, 0, s>>>(d_out, g, zl, q->fout.ckn(), q->d_qout);
+            if (g.n_out) fmq_zir_kernel<4><<<zgrid, 256, 0, s>>>(d_out, g, zl, q->tile, q->fout.ckn(), q->d_qout);
             break;
         default:
             fmq_scan_tiles_kernel<6, 1><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_eout, q->d_qout, q->d_state->out_q, q->fout.c_tile, q->fout.lane_tile(), prun, pl, g.ntiles, runlen, last, q->d_state->s_prev);
-            if (g.n_out) fmq_zir_kernel<6><<<zgrid, 256, 0, s>>>(d_out, g, zl, q->fout.ckn(), q->d_qout);
+            if (g.n_out) fmq_zir_kernel<6><<<zgrid, 256, 0, s>>>(d_out, g, zl, q->tile, q->fout.ckn(), q->d_qout);
             break;
     }
     if (s16 && g.n_out) {
@@ -324,13 +338,13 @@ int fmq1_setup(fmd_ctx *c) {
     q->des.D = 1;
     q->des.A[0][0] = (long double) a;
     q->des.C[0] = 1.0L;
-    fmq_build_consts(&q->des, FMQ_T, &q->c);
-    fmq_build_consts(&q->des, FMQ_TILE, &q->c_tile);
-    fmq_table_layout(&q->des, &q->sz);
+    fmq_build_consts(&q->des, FMQ_T, FMQ_TILE, &q->c);
+    fmq_build_consts(&q->des, FMQ_TILE, FMQ_TILE, &q->c_tile);
+    fmq_table_layout(&q->des, FMQ_T, &q->sz);
     const size_t n = (size_t) q->sz.lane + q->sz.apow + q->sz.ck + q->sz.ckn + q->sz.lane_tile;
     float *h = (float *) malloc(n * sizeof(float));
     if (!h) return fmd_set_error(FMD_ENOMEM, "out of host memory");
-    fmq_build_tables(&q->des, h, h + q->sz.lane, h + q->sz.lane + q->sz.apow, h + q->sz.lane + q->sz.apow + q->sz.ck,
+    fmq_build_tables(&q->des, FMQ_T, h, h + q->sz.lane, h + q->sz.lane + q->sz.apow, h + q->sz.lane + q->sz.apow + q->sz.ck,
                      h + q->sz.lane + q->sz.apow + q->sz.ck + q->sz.ckn);
     cudaError_t e = cudaMalloc(&q->d_tab, n * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(q->d_tab, h, n * sizeof(float), cudaMemcpyHostToDevice);

@@ -13,7 +13,6 @@ import ctypes as C
 import numpy as np
 
 THREADS, MAXD = 256, 6
-T, TILE = 64, 64 * THREADS  # FMQ_T, FMQ_TILE of the library (checked against its table sizes below)
 
 
 class _Consts(C.Structure):
@@ -22,18 +21,21 @@ class _Consts(C.Structure):
 
 
 class Filter:
-    def __init__(self, lib, sos: np.ndarray) -> None:
+    def __init__(self, lib, sos: np.ndarray, T: int) -> None:
+        """T = samples per thread (64, or 128 when the decimation factor is large); tile = 256 T"""
+        self.T, self.TILE = T, T * THREADS
+        TILE = self.TILE
         sos = np.ascontiguousarray(sos, np.float32)
         L = sos.shape[0]
         D = 2 * L
         nbytes = C.c_uint(0)
         sizes = (C.c_uint * 5)()
-        lib.fmq_test_sizes.argtypes = [C.c_uint, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
-        lib.fmq_test_build.argtypes = ([C.c_void_p, C.c_uint, C.POINTER(_Consts), C.POINTER(_Consts)] +
+        lib.fmq_test_sizes.argtypes = [C.c_uint, C.c_uint, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+        lib.fmq_test_build.argtypes = ([C.c_void_p, C.c_uint, C.c_uint, C.POINTER(_Consts), C.POINTER(_Consts)] +
                                        [C.c_void_p] * 6 + [C.POINTER(C.c_uint)])
-        lib.fmq_test_sizes(L, C.byref(nbytes), sizes)
+        lib.fmq_test_sizes(L, T, C.byref(nbytes), sizes)
         assert nbytes.value == C.sizeof(_Consts), (nbytes.value, C.sizeof(_Consts))
-        assert sizes[2] == T * D and sizes[3] == TILE * D, "quality_model.T does not match the library's FMQ_T"
+        assert sizes[2] == T * D and sizes[3] == TILE * D
         self.c, self.ct = _Consts(), _Consts()
         lane = np.zeros(sizes[0], np.float32)
         apow = np.zeros(sizes[1], np.float32)
@@ -42,7 +44,7 @@ class Filter:
         lane_tile = np.zeros(sizes[4], np.float32)
         abcd = np.zeros(D * D + 2 * D + 1, np.float64)
         zl = C.c_uint(0)
-        rc = lib.fmq_test_build(sos.ctypes.data, L, C.byref(self.c), C.byref(self.ct), lane.ctypes.data,
+        rc = lib.fmq_test_build(sos.ctypes.data, L, T, C.byref(self.c), C.byref(self.ct), lane.ctypes.data,
                                 apow.ctypes.data, ck.ctypes.data, ckn.ctypes.data, lane_tile.ctypes.data,
                                 abcd.ctypes.data, C.byref(zl))
         assert rc == 0
@@ -75,7 +77,7 @@ class Filter:
         return np.linalg.matrix_power(self.A, k)
 
 
-def block_scan(f: Filter, e: np.ndarray, carry: np.ndarray) -> np.ndarray:
+def block_scan(f: "Filter", e: np.ndarray, carry: np.ndarray) -> np.ndarray:
     """e: [ntiles, 256, D] zero-state end states; carry: [ntiles, D] -> state at each thread's start"""
     nt = e.shape[0]
     v = e.reshape(nt, 8, 32, f.D).copy()
@@ -115,6 +117,7 @@ def scan_tiles(f: "Filter", E: np.ndarray, carry: np.ndarray, len_last: int):
     """fmq_scan_tiles_kernel: 32 warps, each a run of `runlen` tiles walked 32 tiles at a time with
     the tile-level tables; returns (state at the start of every tile, carry out)"""
     nt, D = E.shape
+    TILE = f.TILE
     nwarps = 32
     runlen = ((nt + nwarps - 1) // nwarps + 31) & ~31
     prun = f.matpow(TILE * runlen)
@@ -158,9 +161,11 @@ def kept_below(pos, r0, M):
 class Stream:
     """the host side of one quality context (fmdemod.cu: quality_launch) over the model kernels"""
 
-    def __init__(self, lib, sos_in, sos_out, decim: int) -> None:
-        self.fin = Filter(lib, sos_in) if sos_in is not None and len(sos_in) else None
-        self.fout = Filter(lib, sos_out)
+    def __init__(self, lib, sos_in, sos_out, decim: int, T: int | None = None) -> None:
+        T = T or (128 if decim >= 8 else 64)  # fmq_setup's choice
+        self.T, self.TILE = T, T * THREADS
+        self.fin = Filter(lib, sos_in, T) if sos_in is not None and len(sos_in) else None
+        self.fout = Filter(lib, sos_out, T)
         self.M = decim
         self.pos = 0
         self.in_q = np.zeros((2, self.fin.D)) if self.fin else None
@@ -170,6 +175,7 @@ class Stream:
     def run(self, raw: np.ndarray) -> np.ndarray:
         n = raw.size // 2
         M = self.M
+        T, TILE = self.T, self.TILE
         ntiles = (n + TILE - 1) // TILE
         r0 = (M - self.pos % M) % M
         n_out = int(kept_below(n, r0, M))

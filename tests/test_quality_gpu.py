@@ -71,23 +71,25 @@ def test_quality_stream_continues_across_calls(name, sizes, oracle_port):
 
 
 def test_quality_every_degree_combination(oracle_port):
-    """one kernel instantiation per (input degree 0..6, output degree 1..6): all of them, Butterworth
-    and Chebyshev, against the oracle, in two calls that split a tile"""
-    rate, fs = 192e3, 48000.0
+    """one kernel instantiation per (input degree 0..6, output degree 1..6), in both thread spans
+    between them: Butterworth and Chebyshev, against the oracle, in two calls that split a tile"""
+    rate = 192e3
     c = synth.CONFIGS["cfg2"]
-    raw = synth.fm_iq_u8(40000, c["fs_sig"], c["df"], c["fm"], 21)
+    raw = synth.fm_iq_u8(80000, c["fs_sig"], c["df"], c["fm"], 21)
     worst = 0.0
     for deg_in in range(0, 7):
         for deg_out in range(1, 7):
+            # M = 4 runs the 64-samples-per-thread kernels, M = 8 the 128-samples-per-thread ones
+            fs = 48000.0 if (deg_in + deg_out) % 2 == 0 else 24000.0
             mode = 3 if (deg_in + deg_out) % 3 == 0 else 0
             cfg = po.Config(fs=fs, fc_out=9000.0 + 500.0 * deg_out, fc_in=30000.0 if deg_in else 0.0,
                             deg_in=deg_in, deg_out=deg_out, mode=mode, eps=0.1)
             want = oracle_port.quality(cfg, rate).run(raw)
             with fm.Demodulator(**quality_kwargs(cfg, rate)) as d:
-                out = np.concatenate([d.process(raw[:2 * 17001]), d.process(raw[2 * 17001:])])
+                out = np.concatenate([d.process(raw[:2 * 37001]), d.process(raw[2 * 37001:])])
             err = max_err(out, want)
             worst = max(worst, err)
-            assert err <= TOL, (deg_in, deg_out, mode, err)
+            assert err <= TOL, (deg_in, deg_out, mode, fs, err)
     print(f"42 degree combinations: worst max-abs {worst:.2e}")
 
 

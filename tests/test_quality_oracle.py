@@ -88,13 +88,15 @@ def product_lib():
     return C.CDLL(fm.lib_path())
 
 
-@pytest.mark.parametrize("name,sizes", [
-    ("quality_cfg2", (20000, 8192, 33, 1, 50001)),
-    ("quality_cfg3", (8192 * 3, 31, 32, 8191, 40000)),
-    ("quality_d5_M1", (10000, 7, 16384)),
-    ("quality_m3_d6", (70000,)),
+@pytest.mark.parametrize("name,sizes,T", [
+    ("quality_cfg2", (20000, 8192, 33, 1, 50001), 64),
+    ("quality_cfg3", (8192 * 3, 31, 32, 8191, 40000), 128),
+    ("quality_cfg3", (16384 * 2, 63, 64, 16383, 30000), 64),
+    ("quality_d5_M1", (10000, 7, 16384), 64),
+    ("quality_d5_M1", (32768, 127, 128, 5), 128),
+    ("quality_m3_d6", (70000,), 64),
 ])
-def test_scan_algebra_and_tables_match_oracle(name, sizes, oracle_port, product_lib):
+def test_scan_algebra_and_tables_match_oracle(name, sizes, T, oracle_port, product_lib):
     """the three-level scan with the host-built power tables reproduces the serial recursion,
     across calls of awkward lengths (tile = 8192 samples, thread = 32)"""
     g, cfg, raw, rate = load_quality(name)
@@ -102,7 +104,7 @@ def test_scan_algebra_and_tables_match_oracle(name, sizes, oracle_port, product_
     sos_out = oracle_port.design(cfg.mode & 1, cfg.deg_out, cfg.fc_out, rate, cfg.eps)
     deg_in = cfg.deg_in or cfg.deg_out
     sos_in = oracle_port.design((cfg.mode >> 1) & 1, deg_in, cfg.fc_in, rate, cfg.eps) if cfg.fc_in else None
-    st = qm.Stream(product_lib, sos_in, sos_out, q.decim)
+    st = qm.Stream(product_lib, sos_in, sos_out, q.decim, T)
     off = 0
     for n in sizes:
         seg = raw[2 * off:2 * (off + n)]
