@@ -580,7 +580,10 @@ fmq_main_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     if (full) {
         /* measured on B200: without the input cascade the fully unrolled span is 8 % faster (more
          * freedom for the scheduler); with it the rolled form is 4 % faster (instruction fetch) */
-        constexpr int UNR = LIN > 0 ? 1 : GROUPS;
+#ifndef FMQ_UNR_MAX
+#define FMQ_UNR_MAX 4 /* groups unrolled without the input cascade: 4 measured best for both spans (616 vs 602 GS/s at T = 128) */
+#endif
+        constexpr int UNR = LIN > 0 ? 1 : (GROUPS > FMQ_UNR_MAX ? FMQ_UNR_MAX : GROUPS);
         uint4 nx = fmq_load_group(in, sp.F, 0);
 #pragma unroll(UNR)
         for (int grp = 0; grp < GROUPS; ++grp) {
