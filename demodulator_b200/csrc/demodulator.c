@@ -15,7 +15,8 @@
  * Where the reference hands ONE 256 KiB buffer from its reader to its worker under a mutex
  * (src/main.c:72-91, src/matrix.c:238-242), this host keeps a ring of pinned slots, each
  * holding many chunks: reader threads fill slots, the main thread submits them (H2D / kernels /
- * D2H on three streams inside the library), writer threads drain them.  A stream (pipe, tty,
+ * D2H on three streams inside the library), writer threads drain them; a slot passes from hand to
+ * hand by an explicit per-slot turn counter (slot_acquire / slot_release).  A stream (pipe, tty,
  * socket) has one reader and one writer, and its slots are cut short when the producer stalls,
  * so a live source sees one-chunk latency like the reference; regular files are read and written
  * with positioned I/O by several threads, because one thread copies only ~5 GB/s out of the page
@@ -34,7 +35,6 @@
 #include <fcntl.h>
 #include <poll.h>
 #include <pthread.h>
-#include <semaphore.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -55,7 +55,12 @@ typedef struct {
     int last;      /* nothing follows this slot */
     int dev;       /* which context owns it */
     unsigned ring; /* slot index inside that context's ring */
-    sem_t free_, filled, inflight; /* reader -> main -> writer -> reader */
+    /* Whose turn it is: slot number n (n % nslots == this slot, generation g = n / nslots) may be
+     * filled when stage == 3g, submitted when stage == 3g + 1, drained when stage == 3g + 2; the
+     * writer then sets 3(g + 1).  A thread waits for the stage of ITS slot number, so slot numbers
+     * n and n + nslots can never be confused however the threads are scheduled (a binary
+     * semaphore per phase would let the reader of n + nslots overtake the reader of n). */
+    unsigned long long stage;
 } slot_t;
 
 typedef struct {
@@ -69,9 +74,15 @@ typedef struct {
     fmd_ctx *ctx[MAX_DEV];
     int ndev;
     unsigned n_readers, n_writers;
+    off_t in_base, out_base;     /* where the descriptors stood when we got them (inherited stdin / stdout) */
     volatile int error;
     unsigned long long bytes_in, floats_out;
     pthread_mutex_t stat_lock;
+    /* one lock + one condition for all slot hand-offs: an event per 32 MiB slot, no contention */
+    pthread_mutex_t turn_lock;
+    pthread_cond_t turn_cond;
+    int finished;                 /* the stream has ended ... */
+    unsigned long long last_n;    /* ... with this slot number */
 } host_t;
 
 typedef struct { host_t *h; unsigned id; } io_arg_t;
@@ -79,6 +90,43 @@ typedef struct { host_t *h; unsigned id; } io_arg_t;
 static void die(const char *what) {
     fprintf(stderr, "demodulator: %s: %s\n", what, fmd_last_error());
     exit(2);
+}
+
+enum { PH_FREE = 0, PH_FILLED = 1, PH_INFLIGHT = 2 };
+
+/* Block until slot number n reaches `phase`.  Returns 0 when the stream ended before slot number n
+ * (the caller has nothing left to do), 1 when the slot is the caller's. */
+static int slot_acquire(host_t *h, unsigned long long n, int phase) {
+    slot_t *s = &h->slots[n % h->nslots];
+    const unsigned long long want = 3ull * (n / h->nslots) + (unsigned) phase;
+    int mine = 1;
+    pthread_mutex_lock(&h->turn_lock);
+    while (s->stage != want) {
+        if (h->finished && n > h->last_n) {
+            mine = 0;
+            break;
+        }
+        pthread_cond_wait(&h->turn_cond, &h->turn_lock);
+    }
+    pthread_mutex_unlock(&h->turn_lock);
+    return mine;
+}
+
+/* hand slot number n on to the next phase (PH_FREE = to the reader of slot number n + nslots) */
+static void slot_release(host_t *h, unsigned long long n, int next_phase) {
+    slot_t *s = &h->slots[n % h->nslots];
+    pthread_mutex_lock(&h->turn_lock);
+    s->stage = next_phase == PH_FREE ? 3ull * (n / h->nslots + 1ull) : 3ull * (n / h->nslots) + (unsigned) next_phase;
+    pthread_cond_broadcast(&h->turn_cond);
+    pthread_mutex_unlock(&h->turn_lock);
+}
+
+static void stream_finished(host_t *h, unsigned long long last_n) {
+    pthread_mutex_lock(&h->turn_lock);
+    h->finished = 1;
+    h->last_n = last_n;
+    pthread_cond_broadcast(&h->turn_cond);
+    pthread_mutex_unlock(&h->turn_lock);
 }
 
 /* stream input: read until `want` bytes, EOF, or -- once at least one whole chunk is in -- the
@@ -116,7 +164,7 @@ static size_t fill_slot_file(host_t *h, uint8_t *dst, unsigned long long n, int 
     else if (h->in_size - off < want) want = (size_t) (h->in_size - off);
     *eof = off + want >= h->in_size;
     while (got < want) {
-        ssize_t r = pread(h->in_fd, dst + got, want - got, (off_t) (off + got));
+        ssize_t r = pread(h->in_fd, dst + got, want - got, h->in_base + (off_t) (off + got));
         if (r < 0) {
             if (errno == EINTR) continue;
             perror("demodulator: pread");
@@ -140,14 +188,14 @@ static void *reader_main(void *arg) {
         /* file input: slot numbers past the end of the file are never produced (slot 0 always is) */
         if (h->in_regular && n > 0 && n * (unsigned long long) h->slot_bytes >= h->in_size) break;
         slot_t *s = &h->slots[n % h->nslots];
-        sem_wait(&s->free_);
+        if (!slot_acquire(h, n, PH_FREE)) break;
         int eof;
         s->nbytes = h->in_regular ? fill_slot_file(h, s->in, n, &eof) : fill_slot_stream(h, s->in, h->slot_bytes, &eof);
         s->last = eof;
         pthread_mutex_lock(&h->stat_lock);
         h->bytes_in += s->nbytes;
         pthread_mutex_unlock(&h->stat_lock);
-        sem_post(&s->filled);
+        slot_release(h, n, PH_FILLED);
         if (eof) break;
     }
     return NULL;
@@ -174,17 +222,14 @@ static void *writer_main(void *arg) {
     host_t *h = ((io_arg_t *) arg)->h;
     for (unsigned long long n = ((io_arg_t *) arg)->id;; n += h->n_writers) {
         slot_t *s = &h->slots[n % h->nslots];
-        sem_wait(&s->inflight);
-        if (s->nbytes == (size_t) -1) { /* poison: the stream ended before this slot number */
-            break;
-        }
+        if (!slot_acquire(h, n, PH_INFLIGHT)) break; /* the stream ended before this slot number */
         if (s->nbytes) {
             if (fmd_wait(h->ctx[s->dev], s->ring)) die("fmd_wait");
             const size_t nf = s->nout;
             /* reference-compatible mode: a slot yields as many output bytes as it had input bytes,
              * so slot n lands at n*slot_bytes (positioned writes are off in quality mode) */
             if (!h->error && write_all(h->out_fd, s->out, nf * h->out_elem, h->out_regular,
-                                       (off_t) (n * (unsigned long long) h->slot_bytes))) {
+                                       h->out_base + (off_t) (n * (unsigned long long) h->slot_bytes))) {
                 perror("demodulator: write");
                 h->error = -4;
             }
@@ -193,7 +238,7 @@ static void *writer_main(void *arg) {
             pthread_mutex_unlock(&h->stat_lock);
         }
         const int last = s->last;
-        sem_post(&s->free_);
+        slot_release(h, n, PH_FREE);
         if (last) break;
     }
     return NULL;
@@ -289,11 +334,28 @@ int main(int argc, char **argv) {
 
     {
         struct stat sb;
+        /* Regular files get positioned I/O from several threads.  A descriptor we inherited
+         * (`-i -` / `-o -` with a redirection) may already stand past byte 0, and may be shared with
+         * other writers: offsets are taken relative to where it stands now, and the descriptor is
+         * moved past what was consumed / produced at exit, so `{ echo hdr; demodulator -o -; } > f`
+         * behaves like the reference's sequential fread / fwrite.  With O_APPEND pwrite ignores
+         * its offset (Linux), so such an output is written sequentially by one thread. */
         if (!fstat(h.in_fd, &sb) && S_ISREG(sb.st_mode)) {
-            h.in_regular = 1;
-            h.in_size = (unsigned long long) sb.st_size;
+            const off_t base = lseek(h.in_fd, 0, SEEK_CUR);
+            if (base >= 0) {
+                h.in_regular = 1;
+                h.in_base = base;
+                h.in_size = sb.st_size > base ? (unsigned long long) (sb.st_size - base) : 0ull;
+            }
         }
-        if (!fstat(h.out_fd, &sb) && S_ISREG(sb.st_mode)) h.out_regular = 1;
+        if (!fstat(h.out_fd, &sb) && S_ISREG(sb.st_mode)) {
+            const off_t base = lseek(h.out_fd, 0, SEEK_CUR);
+            const int fl = fcntl(h.out_fd, F_GETFL);
+            if (base >= 0 && fl >= 0 && !(fl & O_APPEND)) {
+                h.out_regular = 1;
+                h.out_base = base;
+            }
+        }
         unsigned want = (e = getenv("FMD_IO_THREADS")) ? (unsigned) atoi(e) : 4;
         if (want < 1) want = 1;
         if (want > MAX_IO_THREADS) want = MAX_IO_THREADS;
@@ -347,11 +409,8 @@ int main(int argc, char **argv) {
                 die("fmd_host_alloc");
         }
     }
-    for (unsigned i = 0; i < h.nslots; ++i) {
-        sem_init(&h.slots[i].free_, 0, 1);
-        sem_init(&h.slots[i].filled, 0, 0);
-        sem_init(&h.slots[i].inflight, 0, 0);
-    }
+    pthread_mutex_init(&h.turn_lock, NULL);
+    pthread_cond_init(&h.turn_cond, NULL);
 
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
@@ -368,23 +427,18 @@ int main(int argc, char **argv) {
     unsigned long long n = 0;
     for (;; ++n) {
         slot_t *s = &h.slots[n % h.nslots];
-        sem_wait(&s->filled);
+        slot_acquire(&h, n, PH_FILLED);
         /* tail policy: a final partial chunk of r bytes is a chunk of r&~3 bytes */
         s->nbytes &= ~(size_t) 3;
         if (((cfg.mode >> 2) & 3u) == 1u) s->nbytes -= s->nbytes % h.chunk; /* -q1 works on whole chunks only */
         s->nout = fmd_out_count(h.ctx[s->dev], s->nbytes); /* before the submit moves a -Q stream on */
         if (s->nbytes && fmd_submit(h.ctx[s->dev], s->ring, s->in, s->nbytes, s->out)) die("fmd_submit");
         const int last = s->last;
-        sem_post(&s->inflight);
+        slot_release(&h, n, PH_INFLIGHT);
         if (last) break;
     }
-    /* writers whose next slot number lies past the end of the stream get a poison slot */
-    for (unsigned k = 1; k < h.n_writers; ++k) {
-        slot_t *s = &h.slots[(n + k) % h.nslots];
-        sem_wait(&s->free_);
-        s->nbytes = (size_t) -1;
-        sem_post(&s->inflight);
-    }
+    /* readers and writers whose next slot number lies past the end of the stream stop waiting */
+    stream_finished(&h, n);
     for (unsigned i = 0; i < h.n_readers; ++i) pthread_join(rd[i], NULL);
     for (unsigned i = 0; i < h.n_writers; ++i) pthread_join(wr[i], NULL);
     clock_gettime(CLOCK_MONOTONIC, &t1);
@@ -394,6 +448,9 @@ int main(int argc, char **argv) {
         fprintf(stderr, "demodulator: %llu bytes in, %llu floats out, %.3f s, %.1f MS/s, %d GPU(s)\n", h.bytes_in,
                 h.floats_out, sec, (double) h.bytes_in / 2e6 / sec, h.ndev);
     }
+    /* leave inherited descriptors where sequential I/O would have left them */
+    if (h.in_regular) lseek(h.in_fd, h.in_base + (off_t) h.bytes_in, SEEK_SET);
+    if (h.out_regular) lseek(h.out_fd, h.out_base + (off_t) (h.floats_out * h.out_elem), SEEK_SET);
     for (int d = 0; d < h.ndev; ++d) fmd_destroy(h.ctx[d]);
     for (unsigned i = 0; i < h.nslots; ++i) {
         fmd_host_free(h.slots[i].in);

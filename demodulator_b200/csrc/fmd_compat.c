@@ -10,7 +10,7 @@
  * and chooses the implementation at link time (src/matrix.c:178,282 or cuda/matrix.cu:63,106).
  * This file is a third implementation: build the reference's own, unmodified src/main.c with
  * -DIS_NVIDIA and link it against libfmd_compat.so + libfmdemod.so (recipe in INTEGRATION.md;
- * tests/test_compat_seam.py does it on the GPU box's prebuilt objects).
+ * tests/test_cli_gpu.py::test_reference_main_over_this_backend runs the prebuilt binary on the GPU box).
  *
  * The struct below restates the reference's consumerArgs field for field
  * (include/matrix.h:43-57; x86-64 offsets in SURVEY.md section 8b) -- it is the ABI of the seam.
@@ -109,6 +109,7 @@ void *processMatrix(void *ctx) {
     fmd_get_config(fm, &cfg);
     args->inFilterDegree = cfg.in_degree;
 
+    int failed = 0;
     for (;;) {
         if (!take_full(args)) break;
         const unsigned s = n & 1u;
@@ -119,26 +120,39 @@ void *processMatrix(void *ctx) {
         pthread_mutex_unlock(&args->mutex);
         sem_post(args->empty);
 
+        /* After a failure the hand-offs are still taken (and dropped): the reference's reader
+         * (src/main.c:72-91) blocks in sem_wait(empty) until the worker takes its buffer and
+         * overwrites exitFlag with ferror() on every turn, so the only way not to hang it is to
+         * keep the protocol going until it sees the end of its input. */
+        if (failed) continue;
         len &= ~(size_t) 3;
         if (len) {
             if (fmd_submit(fm, s, in[s], len, out[s])) {
-                fprintf(stderr, "processMatrix: %s\n", fmd_last_error());
-                break;
+                failed = 1;
+                fprintf(stderr, "processMatrix: %s (dropping the rest of the stream)\n", fmd_last_error());
+                continue;
             }
             pending[s] = len >> 2;
         }
         /* while this chunk is in flight, write the previous one */
         if (pending[s ^ 1u]) {
-            fmd_wait(fm, s ^ 1u);
+            if (fmd_wait(fm, s ^ 1u)) {
+                failed = 1;
+                fprintf(stderr, "processMatrix: %s (dropping the rest of the stream)\n", fmd_last_error());
+                continue;
+            }
             fwrite(out[s ^ 1u], sizeof(float), pending[s ^ 1u], args->outFile);
             pending[s ^ 1u] = 0;
         }
         if (len) ++n;
     }
-    for (unsigned k = 0; k < 2; ++k) {
+    for (unsigned k = 0; k < 2 && !failed; ++k) {
         const unsigned s = (n + k) & 1u; /* oldest first */
         if (pending[s]) {
-            fmd_wait(fm, s);
+            if (fmd_wait(fm, s)) {
+                fprintf(stderr, "processMatrix: %s\n", fmd_last_error());
+                break;
+            }
             fwrite(out[s], sizeof(float), pending[s], args->outFile);
             pending[s] = 0;
         }

@@ -3,8 +3,8 @@
  * long double, and folding of the designed sections into the finite stencil the
  * reference's section sweep actually computes.
  *
- * Replaces (same results, float-for-float -- tests/test_design.py checks the
- * table generated from the reference):
+ * Replaces (same results, float-for-float -- tests/test_oracle_golden.py::test_design_table_port_and_product
+ * checks the 288-design table generated from the reference):
  *   processFilterOption                 /root/reference/src/matrix.c:25-80
  *   warpButter.. / warpCheby1..         /root/reference/src/filter.c:22-101
  *   zp2Sos                              /root/reference/src/filter.c:104-140

@@ -305,9 +305,19 @@ size_t fmq_max_out_count(const fmd_ctx *c, size_t nsamp) { return quality_out_co
 
 int fmq_check_error(fmd_ctx *c) {
     if (!c->q->lin) return FMD_OK; /* only the input cascade's look-back can raise it */
+    /* the calling thread's current device may be another one (multi-GPU hosts) */
+    int prev = -1;
+    FMD_CUDA(cudaGetDevice(&prev));
+    if (prev != c->device) FMD_CUDA(cudaSetDevice(c->device));
     unsigned err = 0;
-    FMD_CUDA(cudaMemcpy(&err, &c->q->d_state->error, sizeof err, cudaMemcpyDeviceToHost));
-    if (err) return fmd_set_error(FMD_ECUDA, "quality pipeline: a tile gave up waiting for its predecessor's carry");
+    cudaError_t e = cudaMemcpy(&err, &c->q->d_state->error, sizeof err, cudaMemcpyDeviceToHost);
+    /* report once: the flag is cleared so that the calls after an fmd_reset (or a retry) start clean */
+    if (e == cudaSuccess && err) e = cudaMemset(&c->q->d_state->error, 0, sizeof err);
+    if (prev != c->device && prev >= 0) cudaSetDevice(prev);
+    if (e != cudaSuccess) return fmd_set_error(FMD_ECUDA, "quality pipeline: reading the error flag failed: %s", cudaGetErrorString(e));
+    if (err)
+        return fmd_set_error(FMD_ECUDA, "quality pipeline: a tile gave up waiting for its predecessor's carry "
+                                        "(the outputs of that call are invalid; fmd_reset and resubmit)");
     return FMD_OK;
 }
 

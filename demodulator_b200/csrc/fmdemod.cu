@@ -98,6 +98,43 @@ extern "C" void fmd_config_default(fmd_config *cfg) {
     cfg->chunk_bytes = FMD_DEFAULT_CHUNK_BYTES;
 }
 
+/* FMD_VERBOSE=1: what the reference prints to stderr when built with -DIS_VERBOSE (filter
+ * parameters and section rows, src/matrix.c:39-46, src/filter.c:193-204), plus the folded stencils
+ * the streaming kernel runs */
+static void fmd_dump_design(const fmd_ctx *c, unsigned conditioner) {
+    const fmd_config &g = c->cfg;
+    const bool quality = (g.flags & FMD_FLAG_QUALITY) != 0;
+    const double fs = quality ? g.input_rate : g.sample_rate;
+    auto rows = [](const char *what, const float (*sos)[6], unsigned n) {
+        for (unsigned i = 0; i < n; ++i)
+            fprintf(stderr, "  %s sos[%u] = {%.9g, %.9g, %.9g, %.9g, %.9g, %.9g}\n", what, i, sos[i][0], sos[i][1],
+                    sos[i][2], sos[i][3], sos[i][4], sos[i][5]);
+    };
+    auto taps = [](const char *what, const float *t, unsigned n, float dc) {
+        fprintf(stderr, "  %s stencil:", what);
+        for (unsigned i = 0; i < n; ++i) fprintf(stderr, " %.9g", t[i]);
+        fprintf(stderr, "  dc %.9g\n", dc);
+    };
+    fprintf(stderr, "fmdemod: design rate %.1f Hz, chunk %llu bytes, conditioner -q%u%s\n", fs,
+            (unsigned long long) g.chunk_bytes, conditioner, quality ? ", quality pipeline" : "");
+    fprintf(stderr, " output lowpass: %s, cutoff %.1f Hz, w = %.6f, degree %u (%u sections)\n",
+            (g.mode & 1u) ? "Chebyshev type 1" : "Butterworth", g.lowpass_out, M_PI * g.lowpass_out / fs, g.out_degree,
+            c->lout);
+    if (g.mode & 1u) fprintf(stderr, "  ripple parameter %.3f\n", g.epsilon);
+    rows("out", c->sec.out, c->lout);
+    if (!quality) taps("out", c->st.tout, c->nto, c->st.dco);
+    if (c->lin) {
+        fprintf(stderr, " input lowpass: %s, cutoff %.1f Hz, w = %.6f, degree %u (%u sections)\n",
+                (g.mode & 2u) ? "Chebyshev type 1" : "Butterworth", g.lowpass_in, M_PI * g.lowpass_in / fs, g.in_degree,
+                c->lin);
+        rows("in ", c->sec.in, c->lin);
+        if (!quality)
+            taps(c->fast_in_ok ? "in  (divided by its first tap; dc is the Q lane's)" : "in  (op-for-op path only)",
+                 c->st.tin, c->nti, c->st.dcq);
+    }
+    if (conditioner == 2u) rows("-q2 highpass", c->sec.hp, 2);
+}
+
 extern "C" int fmd_device_count(void) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -248,6 +285,9 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
         for (unsigned t = 0; t < c->nto; ++t) gain += fabs((double) c->st.tout[t]);
         c->atan_terms = (gain * 1.75e-6 <= 2.0e-5) ? 6u : 8u;
         if (const char *e = getenv("FMD_ATAN_TERMS")) c->atan_terms = (unsigned) atoi(e); /* audits */
+    }
+    if (const char *e = getenv("FMD_VERBOSE")) {
+        if (atoi(e)) fmd_dump_design(c, conditioner);
     }
     c->head = 2 * c->lout - 1;
     if (c->lin && 4 * c->lin - 2 > c->head) c->head = 4 * c->lin - 2;
@@ -559,19 +599,23 @@ extern "C" int fmd_time_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, f
                                int reps, float *ms) {
     if (!c || !ms || reps <= 0) return fmd_set_error(FMD_EINVAL, "bad argument");
     cudaStream_t s = (cudaStream_t) stream;
-    cudaEvent_t a, b;
-    FMD_CUDA(cudaEventCreate(&a));
-    FMD_CUDA(cudaEventCreate(&b));
-    FMD_CUDA(cudaEventRecord(a, s));
+    /* events belong to a device: record them on the context's, whatever the caller's current one is */
+    int prev = -1;
+    FMD_CUDA(cudaGetDevice(&prev));
+    if (prev != c->device) FMD_CUDA(cudaSetDevice(c->device));
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaError_t e = cudaEventCreate(&a);
+    if (e == cudaSuccess) e = cudaEventCreate(&b);
+    if (e == cudaSuccess) e = cudaEventRecord(a, s);
     int rc = FMD_OK;
-    for (int i = 0; i < reps && !rc; ++i) rc = fmd_demod_device(c, d_in, nbytes, d_out, s);
-    if (!rc) {
-        FMD_CUDA(cudaEventRecord(b, s));
-        FMD_CUDA(cudaEventSynchronize(b));
-        FMD_CUDA(cudaEventElapsedTime(ms, a, b));
-    }
-    cudaEventDestroy(a);
-    cudaEventDestroy(b);
+    for (int i = 0; i < reps && !rc && e == cudaSuccess; ++i) rc = fmd_demod_device(c, d_in, nbytes, d_out, s);
+    if (!rc && e == cudaSuccess) e = cudaEventRecord(b, s);
+    if (!rc && e == cudaSuccess) e = cudaEventSynchronize(b);
+    if (!rc && e == cudaSuccess) e = cudaEventElapsedTime(ms, a, b);
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+    if (prev != c->device && prev >= 0) cudaSetDevice(prev);
+    if (!rc && e != cudaSuccess) rc = fmd_set_error(FMD_ECUDA, "fmd_time_device: %s", cudaGetErrorString(e));
     return rc;
 }
 
@@ -633,6 +677,17 @@ extern "C" int fmd_wait(fmd_ctx *c, unsigned slot) {
     s.busy = false;
     if (c->q) return fmq_check_error(c); /* a look-back that gave up waiting raises a device-side flag */
     return FMD_OK;
+}
+
+extern "C" int fmd_check(fmd_ctx *c, void *stream) {
+    if (!c) return fmd_set_error(FMD_EINVAL, "null argument");
+    int prev = -1;
+    FMD_CUDA(cudaGetDevice(&prev));
+    if (prev != c->device) FMD_CUDA(cudaSetDevice(c->device));
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t) stream);
+    if (prev != c->device && prev >= 0) cudaSetDevice(prev);
+    if (e != cudaSuccess) return fmd_set_error(FMD_ECUDA, "fmd_check: %s", cudaGetErrorString(e));
+    return c->q ? fmq_check_error(c) : FMD_OK;
 }
 
 /* ------------------------------------------------------- host-buffer wrapper */

@@ -158,6 +158,10 @@ int fmd_reset(fmd_ctx *ctx);
 
 /* device-resident buffers; asynchronous on `stream` */
 int fmd_demod_device(fmd_ctx *ctx, const uint8_t *d_in, size_t nbytes, float *d_out, void *stream);
+/* Synchronise `stream` and report what only the device can know: in the quality pipeline a tile
+ * whose look-back gave up waiting raises a flag (its outputs are then invalid).  fmd_wait does this
+ * for ring slots; callers of fmd_demod_device use this.  The flag is cleared once reported. */
+int fmd_check(fmd_ctx *ctx, void *stream);
 
 /* host buffers; copies in, computes, copies out, returns when `out` is complete.
  * Pageable memory works; pinned memory (fmd_host_alloc) gets full copy/compute overlap. */
