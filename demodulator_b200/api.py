@@ -75,6 +75,8 @@ def load_library() -> C.CDLL:
     L.fmd_reset.argtypes = [vp]
     L.fmd_demod_device.argtypes = [vp, u8p, C.c_size_t, f32p, vp]
     L.fmd_demod_host.argtypes = [vp, u8p, C.c_size_t, f32p, C.POINTER(C.c_size_t)]
+    L.fmd_copy_host.argtypes = [vp, u8p, C.c_size_t, f32p]
+    L.fmd_check.argtypes = [vp, vp]
     L.fmd_ring_create.argtypes = [vp, C.c_uint, C.c_size_t]
     L.fmd_submit.argtypes = [vp, C.c_uint, u8p, C.c_size_t, f32p]
     L.fmd_wait.argtypes = [vp, C.c_uint]
@@ -202,6 +204,14 @@ class Demodulator:
         got = C.c_size_t(0)
         _check(self._L.fmd_demod_host(self._ctx, in_ptr, nbytes, out_ptr, C.byref(got)))
         return int(got.value)
+
+    def copy_ptr(self, in_ptr: int, nbytes: int, out_ptr: int) -> None:
+        """fmd_copy_host: the copies of process_ptr without the kernels (the e2e ceiling of the box)."""
+        _check(self._L.fmd_copy_host(self._ctx, in_ptr, nbytes, out_ptr))
+
+    def check(self, stream: int = 0) -> None:
+        """fmd_check: synchronise `stream` and raise if the device flagged an error."""
+        _check(self._L.fmd_check(self._ctx, stream))
 
     def process_device(self, d_in: int, nbytes: int, d_out: int, stream: int = 0) -> None:
         """Device pointers; asynchronous on `stream` (a cudaStream_t as int, 0 = the default stream)."""

@@ -305,14 +305,29 @@ fmd_exact_tiled_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, 
  * 8 bytes of the lane's raw input of the following pass: lane 0's copy is what lane 31 needs
  * as its input-filter halo.  LITE: only outputs 0 and 2 are computed (the drain pass).
  */
+#ifndef FMD_HALO_CARRY
+#define FMD_HALO_CARRY 1 /* 0: re-bias the shuffled raw halo word every pass (round-1 form) */
+#endif
+
+/* Does the pass keep the biased first word of the NEXT pass (`w0c`) from pass to pass?  The input
+ * filter's halo is the next lane's first word -- for lane 31 lane 0's first word of the next pass.
+ * That word is biased (3 instructions) anyway when its pass comes; biasing it one pass early and
+ * handing it on lets the halo be a shuffle of ALREADY biased words: 3 instructions per pass less
+ * than shuffling the raw word and biasing the result. */
+template <int NTI, int COND>
+struct FmdCarry {
+    static constexpr bool value = FMD_HALO_CARRY && COND == 0 && (NTI == 2 || NTI == 3);
+};
+
 template <int NTI, int NTO, int AT, bool LITE = false, int COND = 0>
 __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, const float (&xprev)[4],
                                          float (&xcur)[4], const bool zero_x, float *__restrict__ dst,
                                          const bool do_store, const unsigned lane, const unsigned nxt_lane,
-                                         const FmdStencil &st) {
+                                         const FmdStencil &st, uint32_t &w0c) {
     constexpr int HC = NTI > 1 ? NTI - 1 : 0; /* complex samples needed from the next lane */
     constexpr int HW = (HC + 1) / 2;          /* ... as 4-byte words (2 complex each)      */
     constexpr int NB = NTO - 1;               /* discriminator outputs needed from the next lane */
+    constexpr bool CARRY = FmdCarry<NTI, COND>::value;
 
     /* biased words: own four, then the halo from the next lane (lane 31: lane 0's next pass) */
     static_assert(COND == 0 || (COND == 3 && NTI == 0), "-q3 streams only without the input filter");
@@ -320,14 +335,19 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, con
     if (COND == 3) { /* normalizeInput works on the raw bytes */
         w[0] = cur.x; w[1] = cur.y; w[2] = cur.z; w[3] = cur.w;
     } else {
-        w[0] = fmd_bias_bytes(cur.x);
+        w[0] = CARRY ? w0c : fmd_bias_bytes(cur.x);
         w[1] = fmd_bias_bytes(cur.y);
         w[2] = fmd_bias_bytes(cur.z);
         w[3] = fmd_bias_bytes(cur.w);
     }
     w[4] = w[5] = 0u;
-    if (HW >= 1) w[4] = fmd_bias_bytes(__shfl_sync(0xffffffffu, lane == 0 ? nxt.x : cur.x, nxt_lane));
-    if (HW >= 2) w[5] = fmd_bias_bytes(__shfl_sync(0xffffffffu, lane == 0 ? nxt.y : cur.y, nxt_lane));
+    if (CARRY) {
+        w0c = fmd_bias_bytes(nxt.x); /* this lane's first word of the next pass */
+        w[4] = __shfl_sync(0xffffffffu, lane == 0 ? w0c : w[0], nxt_lane);
+    } else {
+        if (HW >= 1) w[4] = fmd_bias_bytes(__shfl_sync(0xffffffffu, lane == 0 ? nxt.x : cur.x, nxt_lane));
+        if (HW >= 2) w[5] = fmd_bias_bytes(__shfl_sync(0xffffffffu, lane == 0 ? nxt.y : cur.y, nxt_lane));
+    }
 
     /* vi[k] = (I_k, I_{k+4}), vq[k] = (Q_k, Q_{k+4}): complex samples k and k+4 of this lane feed
      * outputs j and j+2, so every later step runs two outputs per instruction (FADD2/FFMA2) */
@@ -414,6 +434,11 @@ __device__ __forceinline__ uint4 fmd_lds128(uint32_t a) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
+__device__ __forceinline__ uint32_t fmd_lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ uint2 fmd_lds64(uint32_t a) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
@@ -422,6 +447,9 @@ __device__ __forceinline__ uint2 fmd_lds64(uint32_t a) {
 
 #ifndef FMD_MINB
 #define FMD_MINB(NTI) 4 /* resident CTAs per SM the register budget is cut for */
+#endif
+#ifndef FMD_OVERREAD
+#define FMD_OVERREAD 0 /* 1 = EXPERIMENT ONLY: unpredicated prefetch (reads up to 3.5 KB past a segment) */
 #endif
 #ifndef FMD_STAGES
 #define FMD_STAGES 8 /* ring depth per lane (4 or 8): 16 B x FMD_STAGES in flight or landed */
@@ -485,6 +513,13 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
 
     float x0[4], x1[4] = {0.f, 0.f, 0.f, 0.f};
     const uint2 fill2 = make_uint2(FMD_FILL, FMD_FILL);
+    constexpr bool CARRY = FmdCarry<NTI, COND>::value;
+    constexpr int HWORDS = NTI > 1 ? NTI / 2 : 0; /* halo words: (NTI - 1 + 1) / 2 */
+    uint32_t w0c = 0u;
+    if (CARRY) { /* the first pass takes its biased first word from here, every later one from its predecessor */
+        fmd_cp_wait<S - 2>();
+        w0c = fmd_bias_bytes(fmd_lds32(sbase));
+    }
     /* the chunk head [0, head) belongs to the exact path: those lanes of the very first store
      * of a chunk's first segment keep quiet */
     const bool head_keep = !(it0 == 0 && k0 < g.head);
@@ -495,15 +530,16 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
      * immediates because the loop is unrolled by the ring depth. */
 #define FMD_STEP(U, XPREV, XCUR, STP)                                                                   \
     {                                                                                                   \
-        if (base + (U) + S - 1 < n_ld)                                                                  \
+        if (FMD_OVERREAD || base + (U) + S - 1 < n_ld)                                                  \
             fmd_cp_async16(sbase + (((U) + S - 1) & (S - 1)) * SLOT, src + 512 * ((U) + S - 1));        \
         fmd_cp_commit();                                                                                \
         fmd_cp_wait<PENDING>();                                                                         \
         const uint4 cur = fmd_lds128(sbase + (U) * SLOT);                                               \
         uint2 nx = fill2;                                                                               \
-        if (HALO) nx = fmd_lds64(sbase + (((U) + 1) & (S - 1)) * SLOT);                                 \
+        if (HALO && HWORDS >= 2) nx = fmd_lds64(sbase + (((U) + 1) & (S - 1)) * SLOT);                  \
+        if (HALO && HWORDS < 2) nx.x = fmd_lds32(sbase + (((U) + 1) & (S - 1)) * SLOT);                 \
         if (HALO && (U) == S - 1 && base + S >= n_ld) nx = fill2;                                       \
-        fmd_pass<NTI, NTO, AT, false, COND>(cur, nx, XPREV, XCUR, false, dst + 128 * ((U) - 1), STP, lane, nxt_lane, st); \
+        fmd_pass<NTI, NTO, AT, false, COND>(cur, nx, XPREV, XCUR, false, dst + 128 * ((U) - 1), STP, lane, nxt_lane, st, w0c); \
     }
 
     unsigned base = 0;
@@ -535,7 +571,7 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
         uint2 nx = fill2;
         if (HALO && p + 1 < n_ld) nx = fmd_lds64(sbase + ((u + 1) & (S - 1)) * SLOT);
         fmd_pass<NTI, NTO, AT, false, COND>(cur, nx, x1, x0, false, dst + 128 * ((int) u - 1), p >= 2 || (p == 1 && head_keep),
-                                     lane, nxt_lane, st);
+                                     lane, nxt_lane, st, w0c);
         x1[0] = x0[0]; x1[1] = x0[1]; x1[2] = x0[2]; x1[3] = x0[3];
     }
     /* the drain pass (position n_it): only lane 0's first NTO-1 outputs of it are consumed (by lane
@@ -547,7 +583,7 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
         uint4 cur = fill;
         if (p < n_ld) cur = fmd_lds128(sbase + (u & (S - 1)) * SLOT);
         fmd_pass<NTI, NTO, AT, (NTO <= 2), COND>(cur, fill2, x1, x0, end_zero, dst + 128 * ((int) u - 1),
-                                                 p >= 2 || (p == 1 && head_keep), lane, nxt_lane, st);
+                                                 p >= 2 || (p == 1 && head_keep), lane, nxt_lane, st, w0c);
     }
 
     fmd_cp_wait<0>();

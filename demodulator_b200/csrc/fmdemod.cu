@@ -647,7 +647,9 @@ extern "C" int fmd_ring_create(fmd_ctx *c, unsigned slots, size_t slot_bytes) {
     return FMD_OK;
 }
 
-extern "C" int fmd_submit(fmd_ctx *c, unsigned slot, const uint8_t *in, size_t nbytes, float *out) {
+/* `run_kernel` = false: the same copies in the same order without the compute in between (the
+ * copy ceiling of the host side, fmd_copy_host) */
+static int submit_slot(fmd_ctx *c, unsigned slot, const uint8_t *in, size_t nbytes, float *out, bool run_kernel) {
     if (!c || slot >= c->nslots || !in || !out) return fmd_set_error(FMD_EINVAL, "bad slot or null buffer");
     if (nbytes > c->slot_bytes) return fmd_set_error(FMD_EINVAL, "nbytes exceeds slot_bytes");
     fmd_slot &s = c->slots[slot];
@@ -658,7 +660,7 @@ extern "C" int fmd_submit(fmd_ctx *c, unsigned slot, const uint8_t *in, size_t n
     FMD_CUDA(cudaMemcpyAsync(s.d_in, in, nbytes, cudaMemcpyHostToDevice, c->s_in));
     FMD_CUDA(cudaEventRecord(s.ev_in, c->s_in));
     FMD_CUDA(cudaStreamWaitEvent(c->s_k, s.ev_in, 0));
-    int rc = fmd_demod_device(c, s.d_in, nbytes, s.d_out, c->s_k);
+    int rc = run_kernel ? fmd_demod_device(c, s.d_in, nbytes, s.d_out, c->s_k) : FMD_OK;
     if (rc) return rc;
     FMD_CUDA(cudaEventRecord(s.ev_k, c->s_k));
     FMD_CUDA(cudaStreamWaitEvent(c->s_out, s.ev_k, 0));
@@ -667,6 +669,10 @@ extern "C" int fmd_submit(fmd_ctx *c, unsigned slot, const uint8_t *in, size_t n
     FMD_CUDA(cudaEventRecord(s.ev_out, c->s_out));
     s.busy = true;
     return FMD_OK;
+}
+
+extern "C" int fmd_submit(fmd_ctx *c, unsigned slot, const uint8_t *in, size_t nbytes, float *out) {
+    return submit_slot(c, slot, in, nbytes, out, true);
 }
 
 extern "C" int fmd_wait(fmd_ctx *c, unsigned slot) {
@@ -692,7 +698,18 @@ extern "C" int fmd_check(fmd_ctx *c, void *stream) {
 
 /* ------------------------------------------------------- host-buffer wrapper */
 
+static int host_pipeline(fmd_ctx *c, const uint8_t *in, size_t nbytes, float *out, size_t *nout, bool run_kernel);
+
 extern "C" int fmd_demod_host(fmd_ctx *c, const uint8_t *in, size_t nbytes, float *out, size_t *nout) {
+    return host_pipeline(c, in, nbytes, out, nout, true);
+}
+
+extern "C" int fmd_copy_host(fmd_ctx *c, const uint8_t *in, size_t nbytes, float *out) {
+    if (c && c->q) return fmd_set_error(FMD_EINVAL, "fmd_copy_host measures the reference-compatible pipeline's copies");
+    return host_pipeline(c, in, nbytes, out, nullptr, false);
+}
+
+static int host_pipeline(fmd_ctx *c, const uint8_t *in, size_t nbytes, float *out, size_t *nout, bool run_kernel) {
     if (!c || (!in && nbytes) || (!out && nbytes)) return fmd_set_error(FMD_EINVAL, "null argument");
     if (nout) *nout = 0;
     const size_t B = c->cfg.chunk_bytes;
@@ -718,7 +735,7 @@ extern "C" int fmd_demod_host(fmd_ctx *c, const uint8_t *in, size_t nbytes, floa
         const size_t produced = fmd_out_count(c, len); /* before the submit moves the stream on */
         float *dst = (c->cfg.flags & FMD_FLAG_S16) ? reinterpret_cast<float *>(reinterpret_cast<short *>(out) + out_off)
                                                    : out + out_off;
-        if (!rc) rc = fmd_submit(c, slot, in + off, len, dst);
+        if (!rc) rc = submit_slot(c, slot, in + off, len, dst, run_kernel);
         if (rc) return rc;
         off += len;
         out_off += produced;

@@ -187,6 +187,10 @@ uint64_t fmd_launch_count(const fmd_ctx *ctx);
  * accumulated milliseconds and launch count since the last call, and resets both. */
 int fmd_profile_kernels(fmd_ctx *ctx, int enable);
 int fmd_kernel_time(fmd_ctx *ctx, double *ms, uint64_t *launches);
+/* The copies of fmd_demod_host without the kernels between them (same slices, same streams, same
+ * event chain; `out` receives whatever the device buffers hold): what the host side of the box
+ * can move for this call pattern, i.e. the ceiling of the end-to-end number. */
+int fmd_copy_host(fmd_ctx *ctx, const uint8_t *in, size_t nbytes, float *out);
 /* time the device leg only: `reps` back-to-back fmd_demod_device calls bracketed by CUDA
  * events on the launching stream; returns total milliseconds in *ms */
 int fmd_time_device(fmd_ctx *ctx, const uint8_t *d_in, size_t nbytes, float *d_out,
