@@ -80,6 +80,11 @@ def load_library() -> C.CDLL:
     L.fmd_ring_create.argtypes = [vp, C.c_uint, C.c_size_t]
     L.fmd_submit.argtypes = [vp, C.c_uint, u8p, C.c_size_t, f32p]
     L.fmd_wait.argtypes = [vp, C.c_uint]
+    L.fmd_warmup_samples.argtypes = [vp]
+    L.fmd_warmup_samples.restype = C.c_uint64
+    L.fmd_segment_out_count.argtypes = [vp, C.c_uint64, C.c_size_t]
+    L.fmd_segment_out_count.restype = C.c_size_t
+    L.fmd_submit_segment.argtypes = [vp, C.c_uint, u8p, C.c_size_t, C.c_size_t, C.c_uint64, f32p]
     L.fmd_launch_count.argtypes = [vp]
     L.fmd_launch_count.restype = C.c_uint64
     L.fmd_profile_kernels.argtypes = [vp, C.c_int]
@@ -240,6 +245,16 @@ class Demodulator:
 
     def wait(self, slot: int) -> None:
         _check(self._L.fmd_wait(self._ctx, slot))
+
+    # -- quality pipeline, one stream over several contexts / GPUs --------------------------
+    def warmup_samples(self) -> int:
+        return int(self._L.fmd_warmup_samples(self._ctx))
+
+    def segment_out_count(self, first_sample: int, nsamples: int) -> int:
+        return int(self._L.fmd_segment_out_count(self._ctx, first_sample, nsamples))
+
+    def submit_segment(self, slot: int, in_ptr: int, warm_bytes: int, nbytes: int, first_sample: int, out_ptr: int) -> None:
+        _check(self._L.fmd_submit_segment(self._ctx, slot, in_ptr, warm_bytes, nbytes, first_sample, out_ptr))
 
 
 class PinnedBuffer:

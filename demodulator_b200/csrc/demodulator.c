@@ -7,7 +7,8 @@
  *               [-m bits] [-e eps] [-b shift] [-q n] [-c n] [-r x] [-n x]
  *               [-Q -r inputRate [-F s16]]  (extension: the opt-in quality pipeline, FMD_FLAG_QUALITY --
  *                                       recursive filters with carried state, adjacent-sample
- *                                       discriminator, output decimated to -S; one GPU, one stream)
+ *                                       discriminator, output decimated to -S; over several GPUs the
+ *                                       stream is cut into segments with a warm-up prefix)
  *
  * in : raw unsigned 8-bit interleaved I,Q      out: raw native-endian float32,
  *      exactly bufSize/4 floats per bufSize input bytes, in order.
@@ -26,7 +27,9 @@
  *   FMD_DEVICES   comma list of GPU ordinals or "all" (default "0"): slots round-robin
  *   FMD_SLOT_MB   slot size in MiB (default 32), rounded to whole chunks
  *   FMD_SLOTS     ring depth per GPU (default 3)
- *   FMD_IO_THREADS reader / writer threads when the input / output is a regular file (default 4)
+ *   FMD_IO_THREADS reader / writer threads when the input / output is a regular file (default: a quarter
+ *                 of the cores, 4..16)
+ *   FMD_NO_MMAP   1 = write a regular output file with pwrite instead of through a shared mapping
  *   FMD_EXACT     1 = op-for-op audit kernel for every output
  *   FMD_STATS     1 = print throughput to stderr at exit
  */
@@ -38,6 +41,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <time.h>
 #include <unistd.h>
@@ -45,7 +49,7 @@
 #include "fmdemod.h"
 
 #define MAX_DEV 16
-#define MAX_IO_THREADS 8
+#define MAX_IO_THREADS 16
 
 typedef struct {
     uint8_t *in;   /* pinned */
@@ -53,6 +57,8 @@ typedef struct {
     size_t nbytes; /* filled by the reader */
     size_t nout;   /* floats this slot yields (set at submit time) */
     int last;      /* nothing follows this slot */
+    size_t warm;   /* segmented -Q: bytes of warm-up prefix that sit right before the payload */
+    unsigned long long first_sample; /* segmented -Q: global index of the payload's first sample */
     int dev;       /* which context owns it */
     unsigned ring; /* slot index inside that context's ring */
     /* Whose turn it is: slot number n (n % nslots == this slot, generation g = n / nslots) may be
@@ -74,7 +80,19 @@ typedef struct {
     fmd_ctx *ctx[MAX_DEV];
     int ndev;
     unsigned n_readers, n_writers;
+    /* -Q over several GPUs: every slot is an independent segment that starts warm_cap bytes early
+     * (include/fmdemod.h, fmd_submit_segment); the payload of a slot sits at in + warm_cap */
+    int segmented;
+    size_t warm_cap;
+    uint8_t *hist;               /* stream input: the last warm_cap bytes read so far */
+    unsigned long long stream_bytes;
     off_t in_base, out_base;     /* where the descriptors stood when we got them (inherited stdin / stdout) */
+    /* file output through a shared mapping: writers memcpy into it instead of pwrite -- buffered
+     * writes to ONE inode serialise on its lock (measured: 4 pwrite threads into a tmpfs file move
+     * 3.1 GB/s together), page faults on a shared mapping do not */
+    uint8_t *out_map;
+    size_t out_map_len;          /* bytes mapped, from the page that holds out_base */
+    size_t out_map_skew;         /* out_base minus the start of that page */
     volatile int error;
     unsigned long long bytes_in, floats_out;
     pthread_mutex_t stat_lock;
@@ -156,6 +174,17 @@ static size_t fill_slot_stream(host_t *h, uint8_t *dst, size_t want, int *eof) {
     return got;
 }
 
+static int pread_all(host_t *h, uint8_t *dst, size_t want, unsigned long long off) {
+    size_t got = 0;
+    while (got < want) {
+        ssize_t r = pread(h->in_fd, dst + got, want - got, h->in_base + (off_t) (off + got));
+        if (r < 0 && errno == EINTR) continue;
+        if (r <= 0) return -1;
+        got += (size_t) r;
+    }
+    return 0;
+}
+
 /* file input: slot number n is bytes [n*slot_bytes, (n+1)*slot_bytes) of the file */
 static size_t fill_slot_file(host_t *h, uint8_t *dst, unsigned long long n, int *eof) {
     const unsigned long long off = n * (unsigned long long) h->slot_bytes;
@@ -190,7 +219,28 @@ static void *reader_main(void *arg) {
         slot_t *s = &h->slots[n % h->nslots];
         if (!slot_acquire(h, n, PH_FREE)) break;
         int eof;
-        s->nbytes = h->in_regular ? fill_slot_file(h, s->in, n, &eof) : fill_slot_stream(h, s->in, h->slot_bytes, &eof);
+        uint8_t *payload = s->in + h->warm_cap;
+        if (h->segmented) {
+            /* the bytes that precede this slot in the stream, as far back as the warm-up reaches */
+            const unsigned long long at = h->in_regular ? n * (unsigned long long) h->slot_bytes : h->stream_bytes;
+            s->warm = at < h->warm_cap ? (size_t) at : h->warm_cap;
+            s->first_sample = at / 2;
+            if (s->warm && h->in_regular && pread_all(h, payload - s->warm, s->warm, at - s->warm)) {
+                perror("demodulator: pread");
+                h->error = -2;
+            }
+            if (s->warm && !h->in_regular) memcpy(payload - s->warm, h->hist + h->warm_cap - s->warm, s->warm);
+        }
+        s->nbytes = h->in_regular ? fill_slot_file(h, payload, n, &eof) : fill_slot_stream(h, payload, h->slot_bytes, &eof);
+        if (h->segmented && !h->in_regular) { /* one reader: remember the end of the stream so far */
+            if (s->nbytes >= h->warm_cap) {
+                memcpy(h->hist, payload + s->nbytes - h->warm_cap, h->warm_cap);
+            } else if (s->nbytes) {
+                memmove(h->hist, h->hist + s->nbytes, h->warm_cap - s->nbytes);
+                memcpy(h->hist + h->warm_cap - s->nbytes, payload, s->nbytes);
+            }
+            h->stream_bytes += s->nbytes;
+        }
         s->last = eof;
         pthread_mutex_lock(&h->stat_lock);
         h->bytes_in += s->nbytes;
@@ -228,8 +278,11 @@ static void *writer_main(void *arg) {
             const size_t nf = s->nout;
             /* reference-compatible mode: a slot yields as many output bytes as it had input bytes,
              * so slot n lands at n*slot_bytes (positioned writes are off in quality mode) */
-            if (!h->error && write_all(h->out_fd, s->out, nf * h->out_elem, h->out_regular,
-                                       h->out_base + (off_t) (n * (unsigned long long) h->slot_bytes))) {
+            const unsigned long long at = n * (unsigned long long) h->slot_bytes;
+            if (h->out_map && at + nf * h->out_elem <= h->out_map_len - h->out_map_skew) {
+                if (!h->error) memcpy(h->out_map + h->out_map_skew + at, s->out, nf * h->out_elem);
+            } else if (!h->error && write_all(h->out_fd, s->out, nf * h->out_elem, h->out_regular,
+                                              h->out_base + (off_t) at)) {
                 perror("demodulator: write");
                 h->error = -4;
             }
@@ -356,7 +409,11 @@ int main(int argc, char **argv) {
                 h.out_base = base;
             }
         }
-        unsigned want = (e = getenv("FMD_IO_THREADS")) ? (unsigned) atoi(e) : 4;
+        /* one thread copies ~4 GB/s between the page cache and a pinned slot: a quarter of the
+         * cores (4..16) by default */
+        long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+        unsigned dflt = ncpu >= 64 ? 16u : (ncpu >= 16 ? (unsigned) ncpu / 4u : 4u);
+        unsigned want = (e = getenv("FMD_IO_THREADS")) ? (unsigned) atoi(e) : dflt;
         if (want < 1) want = 1;
         if (want > MAX_IO_THREADS) want = MAX_IO_THREADS;
         h.n_readers = h.in_regular ? want : 1;
@@ -370,12 +427,28 @@ int main(int argc, char **argv) {
             h.out_regular = 0;
         }
         pthread_mutex_init(&h.stat_lock, NULL);
+        /* reference-compatible mode writes exactly as many bytes as it reads (4 B per 4 B): with a
+         * regular input the size of the output is known, so it can be sized and mapped up front */
+        if (h.out_regular && h.in_regular && h.n_writers > 1 && !((e = getenv("FMD_NO_MMAP")) && atoi(e))) {
+            const unsigned long long total = h.in_size & ~3ull;
+            const long pg = sysconf(_SC_PAGESIZE);
+            const off_t map_from = h.out_base / pg * pg;
+            if (total && !ftruncate(h.out_fd, h.out_base + (off_t) total)) {
+                const size_t len = (size_t) (h.out_base - map_from) + (size_t) total;
+                void *m = mmap(NULL, len, PROT_READ | PROT_WRITE, MAP_SHARED, h.out_fd, map_from);
+                if (m != MAP_FAILED) {
+                    h.out_map = m;
+                    h.out_map_len = len;
+                    h.out_map_skew = (size_t) (h.out_base - map_from);
+                }
+            }
+        }
     }
 
     h.ndev = parse_devices(getenv("FMD_DEVICES"), devs);
     if (h.ndev <= 0) die("no CUDA device");
-    if (((cfg.flags & FMD_FLAG_QUALITY) || ((cfg.mode >> 2) & 3u) == 1u) && h.ndev > 1) {
-        fprintf(stderr, "demodulator: -Q / -q1 carry state through the stream: using device %d only\n", devs[0]);
+    if (((cfg.mode >> 2) & 3u) == 1u && h.ndev > 1) {
+        fprintf(stderr, "demodulator: -q1 carries its offsets through the stream: using device %d only\n", devs[0]);
         h.ndev = 1;
     }
     for (int d = 0; d < h.ndev; ++d)
@@ -383,6 +456,13 @@ int main(int argc, char **argv) {
 
     h.chunk = (size_t) cfg.chunk_bytes;
     h.out_elem = (cfg.flags & FMD_FLAG_S16) ? sizeof(int16_t) : sizeof(float);
+    if ((cfg.flags & FMD_FLAG_QUALITY) && h.ndev > 1) {
+        /* recursive filters carry state: a slot that goes to another GPU becomes a segment with a
+         * warm-up prefix (one GPU keeps the true carried state and needs none) */
+        h.segmented = 1;
+        h.warm_cap = (size_t) fmd_warmup_samples(h.ctx[0]) * 2u;
+        if (!h.in_regular) h.hist = calloc(1, h.warm_cap ? h.warm_cap : 1);
+    }
     {
         size_t mb = (e = getenv("FMD_SLOT_MB")) ? (size_t) atol(e) : 32;
         unsigned depth = (e = getenv("FMD_SLOTS")) ? (unsigned) atoi(e) : 3;
@@ -391,12 +471,13 @@ int main(int argc, char **argv) {
         if (depth > 16) depth = 16;
         h.slot_bytes = (mb << 20) / h.chunk * h.chunk;
         if (!h.slot_bytes) h.slot_bytes = h.chunk;
+        while (h.segmented && h.slot_bytes < 4 * h.warm_cap) h.slot_bytes += h.chunk; /* keep the overlap under 25 % */
         /* enough slots for every I/O thread to own one while the GPUs own theirs */
         while (depth * (unsigned) h.ndev < h.n_readers + h.n_writers + 1u && depth < 16) ++depth;
         h.nslots = depth * (unsigned) h.ndev;
         h.slots = calloc(h.nslots, sizeof *h.slots);
         for (int d = 0; d < h.ndev; ++d)
-            if (fmd_ring_create(h.ctx[d], depth, h.slot_bytes)) die("fmd_ring_create");
+            if (fmd_ring_create(h.ctx[d], depth, h.slot_bytes + (h.warm_cap + h.chunk - 1) / h.chunk * h.chunk)) die("fmd_ring_create");
         for (unsigned i = 0; i < h.nslots; ++i) {
             slot_t *s = &h.slots[i];
             s->dev = (int) (i % (unsigned) h.ndev);
@@ -405,7 +486,7 @@ int main(int argc, char **argv) {
              * allocateBuffer seam (src/main.c:65): pinned, so copies are true DMA */
             size_t out_bytes = fmd_max_out_count(h.ctx[s->dev], h.slot_bytes) * sizeof(float);
             if (out_bytes < h.slot_bytes) out_bytes = h.slot_bytes;
-            if (fmd_host_alloc((void **) &s->in, h.slot_bytes) || fmd_host_alloc((void **) &s->out, out_bytes))
+            if (fmd_host_alloc((void **) &s->in, h.warm_cap + h.slot_bytes) || fmd_host_alloc((void **) &s->out, out_bytes))
                 die("fmd_host_alloc");
         }
     }
@@ -431,8 +512,15 @@ int main(int argc, char **argv) {
         /* tail policy: a final partial chunk of r bytes is a chunk of r&~3 bytes */
         s->nbytes &= ~(size_t) 3;
         if (((cfg.mode >> 2) & 3u) == 1u) s->nbytes -= s->nbytes % h.chunk; /* -q1 works on whole chunks only */
-        s->nout = fmd_out_count(h.ctx[s->dev], s->nbytes); /* before the submit moves a -Q stream on */
-        if (s->nbytes && fmd_submit(h.ctx[s->dev], s->ring, s->in, s->nbytes, s->out)) die("fmd_submit");
+        if (h.segmented) {
+            s->nout = fmd_segment_out_count(h.ctx[s->dev], s->first_sample, s->nbytes / 2);
+            if (s->nbytes && fmd_submit_segment(h.ctx[s->dev], s->ring, s->in + h.warm_cap - s->warm, s->warm, s->nbytes,
+                                                s->first_sample, s->out))
+                die("fmd_submit_segment");
+        } else {
+            s->nout = fmd_out_count(h.ctx[s->dev], s->nbytes); /* before the submit moves a -Q stream on */
+            if (s->nbytes && fmd_submit(h.ctx[s->dev], s->ring, s->in, s->nbytes, s->out)) die("fmd_submit");
+        }
         const int last = s->last;
         slot_release(&h, n, PH_INFLIGHT);
         if (last) break;
@@ -448,6 +536,7 @@ int main(int argc, char **argv) {
         fprintf(stderr, "demodulator: %llu bytes in, %llu floats out, %.3f s, %.1f MS/s, %d GPU(s)\n", h.bytes_in,
                 h.floats_out, sec, (double) h.bytes_in / 2e6 / sec, h.ndev);
     }
+    if (h.out_map) munmap(h.out_map, h.out_map_len);
     /* leave inherited descriptors where sequential I/O would have left them */
     if (h.in_regular) lseek(h.in_fd, h.in_base + (off_t) h.bytes_in, SEEK_SET);
     if (h.out_regular) lseek(h.out_fd, h.out_base + (off_t) (h.floats_out * h.out_elem), SEEK_SET);

@@ -64,6 +64,13 @@ struct fmd_ctx {
  * dominant kernel of a launch, or nullptr when profiling is off */
 int fmd_prof_events(fmd_ctx *c, cudaEvent_t **pe);
 
+/* the streaming kernel's instantiations, compiled in groups (fmd_fast_inst.cu); a8 = 1: 8-term atan */
+typedef void (*fmd_fast_fn)(const uint8_t *, float *, const FmdGeom, const FmdStencil, const FmdSections *);
+fmd_fast_fn fmd_pick_n01(unsigned nti, unsigned nto, unsigned a8);
+fmd_fast_fn fmd_pick_n23(unsigned nti, unsigned nto, unsigned a8);
+fmd_fast_fn fmd_pick_n45(unsigned nti, unsigned nto, unsigned a8);
+fmd_fast_fn fmd_pick_q3(unsigned nti, unsigned nto, unsigned a8);
+
 /* ---- quality pipeline, fmd_quality_host.cu ---- */
 int fmq_setup(fmd_ctx *c, unsigned decim);
 void fmq_free(fmd_ctx *c);
@@ -73,6 +80,9 @@ int fmq_demod_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, float *d_ou
 int fmq_reset(fmd_ctx *c);
 /* 0, or FMD_ECUDA if a look-back gave up waiting (reads a device-side flag: synchronises) */
 int fmq_check_error(fmd_ctx *c);
+int fmq_seek(fmd_ctx *c, unsigned long long pos, cudaStream_t s);
+size_t fmq_out_count_at(const fmd_ctx *c, unsigned long long pos, size_t nsamp);
+unsigned long long fmq_warmup_samples(const fmd_ctx *c);
 
 /* ---- -q1 (correctIq): offsets that live on from chunk to chunk, as a scan; fmd_quality_host.cu ---- */
 int fmq1_setup(fmd_ctx *c);

@@ -190,7 +190,7 @@ struct FmdSpillInit {
 };
 
 /* output k of one chunk, op for op */
-__device__ __noinline__ float fmd_exact_output(const uint8_t *cin, unsigned chunk_out, const FmdSections *sec,
+static __device__ __noinline__ float fmd_exact_output(const uint8_t *cin, unsigned chunk_out, const FmdSections *sec,
                                                unsigned k) {
     const long long n_out = chunk_out, nc = 2ll * chunk_out;
     FmdDemodX dx{cin, nc, n_out, sec};
@@ -215,6 +215,7 @@ __device__ __forceinline__ void fmd_exact_thread(const uint8_t *__restrict__ in,
         fmd_exact_output(in + (unsigned long long) chunk * g.chunk_stride, g.chunk_out, sec, k);
 }
 
+#ifdef FMD_WITH_EXACT_KERNELS /* defined by the one translation unit that launches them (fmdemod.cu) */
 /* stand-alone exact kernel: every output of every chunk (geometry: head = chunk_out, fast_out = chunk_out) */
 __global__ void __launch_bounds__(FMD_BLOCK)
 fmd_exact_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const FmdGeom g,
@@ -292,6 +293,8 @@ fmd_exact_tiled_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, 
     }
 }
 
+#endif /* FMD_WITH_EXACT_KERNELS */
+
 /* --------------------------------------------------------------- fast kernel */
 
 #define FMD_FILL 0x7f7f7f7fu /* four bytes that shift to 0.0: the zero extension past a chunk */
@@ -316,21 +319,21 @@ fmd_exact_tiled_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, 
  * than shuffling the raw word and biasing the result. */
 template <int NTI, int COND>
 struct FmdCarry {
-    static constexpr bool value = FMD_HALO_CARRY && COND == 0 && (NTI == 2 || NTI == 3);
+    static constexpr bool value = FMD_HALO_CARRY && COND == 0 && NTI == 2; /* measured there; with 3 taps it costs a spilled register */
 };
 
 template <int NTI, int NTO, int AT, bool LITE = false, int COND = 0>
 __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, const float (&xprev)[4],
                                          float (&xcur)[4], const bool zero_x, float *__restrict__ dst,
                                          const bool do_store, const unsigned lane, const unsigned nxt_lane,
-                                         const FmdStencil &st, uint32_t &w0c) {
+                                         const FmdStencil &st, uint32_t &w0c, const bool hz = false) {
     constexpr int HC = NTI > 1 ? NTI - 1 : 0; /* complex samples needed from the next lane */
     constexpr int HW = (HC + 1) / 2;          /* ... as 4-byte words (2 complex each)      */
     constexpr int NB = NTO - 1;               /* discriminator outputs needed from the next lane */
     constexpr bool CARRY = FmdCarry<NTI, COND>::value;
 
     /* biased words: own four, then the halo from the next lane (lane 31: lane 0's next pass) */
-    static_assert(COND == 0 || (COND == 3 && NTI == 0), "-q3 streams only without the input filter");
+    static_assert(COND == 0 || COND == 3, "conditioners of the streaming kernel: shiftOrigin (and what folds into its stencil), normalizeInput");
     uint32_t w[6];
     if (COND == 3) { /* normalizeInput works on the raw bytes */
         w[0] = cur.x; w[1] = cur.y; w[2] = cur.z; w[3] = cur.w;
@@ -345,8 +348,12 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, con
         w0c = fmd_bias_bytes(nxt.x); /* this lane's first word of the next pass */
         w[4] = __shfl_sync(0xffffffffu, lane == 0 ? w0c : w[0], nxt_lane);
     } else {
-        if (HW >= 1) w[4] = fmd_bias_bytes(__shfl_sync(0xffffffffu, lane == 0 ? nxt.x : cur.x, nxt_lane));
-        if (HW >= 2) w[5] = fmd_bias_bytes(__shfl_sync(0xffffffffu, lane == 0 ? nxt.y : cur.y, nxt_lane));
+        if (HW >= 1) w[4] = __shfl_sync(0xffffffffu, lane == 0 ? nxt.x : cur.x, nxt_lane);
+        if (HW >= 2) w[5] = __shfl_sync(0xffffffffu, lane == 0 ? nxt.y : cur.y, nxt_lane);
+        if (COND != 3) { /* normalizeInput works on the raw bytes */
+            if (HW >= 1) w[4] = fmd_bias_bytes(w[4]);
+            if (HW >= 2) w[5] = fmd_bias_bytes(w[5]);
+        }
     }
 
     /* vi[k] = (I_k, I_{k+4}), vq[k] = (Q_k, Q_{k+4}): complex samples k and k+4 of this lane feed
@@ -366,6 +373,21 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, con
         } else {
             vi[k] = fmd_bytes_to_f2<0>(w[k >> 1], w[(k >> 1) + 2]);
             vq[k] = fmd_bytes_to_f2<1>(w[k >> 1], w[(k >> 1) + 2]);
+        }
+    }
+    if (COND == 3 && HC > 0) {
+        /* The zero extension past the end of a chunk is the FLOAT 0.0 (the reference's zeroed
+         * arena); with shiftOrigin the fill byte 0x7f shifts to exactly that, but no byte
+         * normalises to 0.0: where the halo is the zero extension (lane 31 of the chunk's last
+         * pass) its samples -- the high halves of entries 4.. -- are cleared after the conversion. */
+        const bool clear = hz && lane == 31u;
+#pragma unroll
+        for (int k = 4; k < NK; ++k) {
+            float lo, hi;
+            fmd_upk(vi[k], lo, hi);
+            vi[k] = fmd_pk(lo, clear ? 0.0f : hi);
+            fmd_upk(vq[k], lo, hi);
+            vq[k] = fmd_pk(lo, clear ? 0.0f : hi);
         }
     }
 
@@ -538,8 +560,9 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
         uint2 nx = fill2;                                                                               \
         if (HALO && HWORDS >= 2) nx = fmd_lds64(sbase + (((U) + 1) & (S - 1)) * SLOT);                  \
         if (HALO && HWORDS < 2) nx.x = fmd_lds32(sbase + (((U) + 1) & (S - 1)) * SLOT);                 \
-        if (HALO && (U) == S - 1 && base + S >= n_ld) nx = fill2;                                       \
-        fmd_pass<NTI, NTO, AT, false, COND>(cur, nx, XPREV, XCUR, false, dst + 128 * ((U) - 1), STP, lane, nxt_lane, st, w0c); \
+        const bool hz = HALO && (U) == S - 1 && base + S >= n_ld; /* what follows is the zero extension */ \
+        if (hz) nx = fill2;                                                                             \
+        fmd_pass<NTI, NTO, AT, false, COND>(cur, nx, XPREV, XCUR, false, dst + 128 * ((U) - 1), STP, lane, nxt_lane, st, w0c, hz); \
     }
 
     unsigned base = 0;
@@ -571,7 +594,7 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
         uint2 nx = fill2;
         if (HALO && p + 1 < n_ld) nx = fmd_lds64(sbase + ((u + 1) & (S - 1)) * SLOT);
         fmd_pass<NTI, NTO, AT, false, COND>(cur, nx, x1, x0, false, dst + 128 * ((int) u - 1), p >= 2 || (p == 1 && head_keep),
-                                     lane, nxt_lane, st, w0c);
+                                     lane, nxt_lane, st, w0c, HALO && !(p + 1 < n_ld));
         x1[0] = x0[0]; x1[1] = x0[1]; x1[2] = x0[2]; x1[3] = x0[3];
     }
     /* the drain pass (position n_it): only lane 0's first NTO-1 outputs of it are consumed (by lane

@@ -5,6 +5,8 @@
  */
 #include <cuda_runtime.h>
 
+#include <cmath>
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -297,6 +299,42 @@ int fmq_reset(fmd_ctx *c) {
     FMD_CUDA(cudaMemset(c->q->d_state, 0, sizeof(FmqState)));
     c->q->pos = 0;
     return FMD_OK;
+}
+
+/* ---- one stream over several GPUs: independent segments with a warm-up prefix ---- */
+
+/* Start a fresh segment at global sample index `pos`: zero filter state (asynchronously, on the
+ * stream the segment's kernels will run on), the decimation phase follows the global index. */
+int fmq_seek(fmd_ctx *c, unsigned long long pos, cudaStream_t s) {
+    FMD_CUDA(cudaMemsetAsync(c->q->d_state, 0, offsetof(FmqState, error), s));
+    c->q->pos = pos;
+    return FMD_OK;
+}
+
+size_t fmq_out_count_at(const fmd_ctx *c, unsigned long long pos, size_t nsamp) {
+    return quality_out_count(pos, nsamp, c->q->decim);
+}
+
+/* Samples after which a cascade started from a zero state agrees with the running stream to far
+ * below the 1e-5 the pipeline is held to: the slowest pole radius rho of each cascade gives a decay
+ * rho^n (times a polynomial in n for the cascade's nearly coinciding poles, hence the margin); the
+ * output cascade only starts converging once the input cascade has, so the two lengths add. */
+unsigned long long fmq_warmup_samples(const fmd_ctx *c) {
+    auto one = [](const float (*sos)[6], unsigned rows) -> double {
+        double rho = 0.0;
+        for (unsigned r = 0; r < rows; ++r) {
+            const double a1 = sos[r][4], a2 = sos[r][5];
+            const double rr = a2 != 0.0 ? sqrt(fabs(a2)) : fabs(a1);
+            if (rr > rho) rho = rr;
+        }
+        if (!(rho > 0.0)) return 64.0;
+        if (rho >= 0.99999) rho = 0.99999;
+        return 1.5 * (log(1e-9) / log(rho)) + 64.0 * rows;
+    };
+    double w = one(c->sec.out, c->lout);
+    if (c->lin) w += one(c->sec.in, c->lin);
+    unsigned long long n = (unsigned long long) ceil(w);
+    return (n + 7ull) & ~7ull; /* 16 bytes of IQ: the payload after it stays aligned */
 }
 
 size_t fmq_out_count(const fmd_ctx *c, size_t nsamp) { return quality_out_count(c->q->pos, nsamp, c->q->decim); }

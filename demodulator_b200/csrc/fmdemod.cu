@@ -18,6 +18,7 @@
 #include <cstring>
 #include <new>
 
+#define FMD_WITH_EXACT_KERNELS
 #include "fmd_ctx.h"
 #include "fmd_kernels.cuh"
 
@@ -219,13 +220,14 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
     c->sec.lin = (int) c->lin;
     c->sec.lout = (int) c->lout;
     c->sec.conditioner = (int) conditioner;
-    /* -q3 (normalizeInput) streams without the input filter; with it the zero extension past a
-     * chunk is not a byte value (no u8 normalises to 0.0), so that combination stays op-for-op */
-    if (conditioner == 3u && c->lin) c->fast_in_ok = false;
-    /* -q2 (highpassDc) is one more complex sweep: without -L it IS the input stencil of the streaming
-     * kernel (folded below); stacked under -L its spill reaches the last outputs of every chunk
-     * through the input filter's aliased reads, so that combination stays op-for-op */
-    if (conditioner == 2u && c->lin) c->fast_in_ok = false;
+    /* -q3 (normalizeInput) streams with or without the input filter (the kernel clears the halo
+     * samples where they are the zero extension past a chunk: no byte normalises to 0.0).
+     * -q2 (highpassDc) is one more complex sweep: without -L it IS the input stencil of the streaming
+     * kernel; under -L the two stencils are composed into one (below).  The highpass sweep writes
+     * three complex values past its output region, which the input filter then reads: the first two
+     * are fully swept -- exactly what the composed stencil gives on the zero extension -- and only
+     * the third is partial, so the composition is used while the input stencil has at most 3 taps
+     * (degree <= 8: it then never reaches the third); wider ones stay on the op-for-op path. */
     /* -q1 (correctIq): the samples are conditioned by a scan of their own (fmd_correctiq.cuh) and the
      * rest runs op for op on the conditioned floats */
     if (conditioner == 1u) c->fast_in_ok = false;
@@ -259,6 +261,35 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
     if (!rc && conditioner == 2u) {
         /* matrix.c:151: processFilterOption(2, 3, sos, 1., samplingRate, 0.) */
         rc = fmd_design_sos(FMD_BUTTER_HP, 3, 1.0, cfg.sample_rate, 0.0, &c->sec.hp[0][0]);
+        if (!rc && c->lin && c->fast_in_ok) {
+            /* highpass, then lowpass: z[c] = dL + sum_t L[t] x[c+t] with x[c] = dH + sum_u H[u] s[c+u]
+             * is one stencil with taps L*H and constant dL + dH sum L (per lane; both I-lane
+             * constants are 0).  c->st.tin / dcq hold the lowpass stencil divided by its first tap
+             * at this point; the highpass one is folded here the same way. */
+            float hp[FMD_MAX_TAPS], hq[FMD_MAX_TAPS], dhi = 0.f, dhq = 0.f;
+            unsigned nh = 0, nhq = 0;
+            rc = fmd_fold_taps(&c->sec.hp[0][0], 2, 1, hp, &dhi, &nh);
+            if (!rc) rc = fmd_fold_taps(&c->sec.hp[0][0], 2, 0, hq, &dhq, &nhq);
+            const unsigned nl = c->nti, ncomp = nl + nh - 1u;
+            if (!rc && nl <= 3u && ncomp <= 5u && std::isfinite(hp[0]) && hp[0] != 0.0f && dhi == 0.0f && std::isfinite(dhq)) {
+                double comp[2 * FMD_MAX_TAPS] = {0.0}, suml = 0.0;
+                for (unsigned t = 0; t < nl; ++t) {
+                    suml += (double) c->st.tin[t];
+                    for (unsigned u = 0; u < nh; ++u) comp[t + u] += (double) c->st.tin[t] * (double) hp[u];
+                }
+                const double dq = (double) c->st.dcq + (double) dhq * suml, c0 = comp[0];
+                for (unsigned t = 0; t < ncomp; ++t) c->st.tin[t] = (float) (comp[t] / c0);
+                for (unsigned t = ncomp; t < FMD_MAX_TAPS; ++t) c->st.tin[t] = 0.f;
+                c->st.dcq = (float) (dq / c0);
+                c->st.tin[0] = 1.0f;
+                c->nti = ncomp;
+                if (!(c0 > 0.0) && !(c0 < 0.0)) c->fast_in_ok = false;
+            } else if (!rc) {
+                c->fast_in_ok = false;
+            }
+        } else if (!rc && c->lin) {
+            c->fast_in_ok = false;
+        }
         if (!rc && !c->lin) {
             float dci = 0.f, taps_q[FMD_MAX_TAPS];
             unsigned nti_q = 0;
@@ -279,6 +310,7 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
         delete c;
         return rc;
     }
+    if (conditioner == 3u && c->nti > 3u) c->fast_in_ok = false; /* -q3 under -L streams up to 3 input taps (degree <= 8) */
     {
         /* the discriminator's error reaches the output multiplied by sum|tout|: keep it near 2e-5 */
         double gain = 0.0;
@@ -408,50 +440,15 @@ extern "C" size_t fmd_max_out_count(const fmd_ctx *c, size_t nbytes) {
     return nbytes >> 2;
 }
 
-typedef void (*fast_fn)(const uint8_t *, float *, const FmdGeom, const FmdStencil, const FmdSections *);
-
-template <int NTI, int AT>
-static fast_fn pick_out(unsigned nto) {
-    switch (nto) {
-        case 1: return fmd_fast_kernel<NTI, 1, AT>;
-        case 2: return fmd_fast_kernel<NTI, 2, AT>;
-        case 3: return fmd_fast_kernel<NTI, 3, AT>;
-        case 4: return fmd_fast_kernel<NTI, 4, AT>;
-        case 5: return fmd_fast_kernel<NTI, 5, AT>;
-        default: return nullptr;
-    }
-}
-
-template <int AT>
-static fast_fn pick_in(unsigned nti, unsigned nto) {
-    switch (nti) {
-        case 0: return pick_out<0, AT>(nto);
-        case 1: return pick_out<1, AT>(nto);
-        case 2: return pick_out<2, AT>(nto);
-        case 3: return pick_out<3, AT>(nto);
-        case 4: return pick_out<4, AT>(nto);
-        case 5: return pick_out<5, AT>(nto);
-        default: return nullptr;
-    }
-}
-
-/* -q3 (normalizeInput) streams when there is no input filter */
-template <int AT>
-static fast_fn pick_q3(unsigned nto) {
-    switch (nto) {
-        case 1: return fmd_fast_kernel<0, 1, AT, 3>;
-        case 2: return fmd_fast_kernel<0, 2, AT, 3>;
-        case 3: return fmd_fast_kernel<0, 3, AT, 3>;
-        case 4: return fmd_fast_kernel<0, 4, AT, 3>;
-        case 5: return fmd_fast_kernel<0, 5, AT, 3>;
-        default: return nullptr;
-    }
-}
-
-/* `at` = terms of the atan polynomial: 6 (1.75e-6) unless the output stencil amplifies too much */
-static fast_fn pick_fast(unsigned nti, unsigned nto, unsigned at, unsigned conditioner) {
-    if (conditioner == 3u) return nti ? nullptr : (at <= 6 ? pick_q3<6>(nto) : pick_q3<8>(nto));
-    return at <= 6 ? pick_in<6>(nti, nto) : pick_in<8>(nti, nto);
+/* the streaming kernel's instantiations are compiled in groups (fmd_fast_inst.cu, one object per
+ * group, so that the build runs in parallel); `at` = terms of the atan polynomial: 6 (1.75e-6)
+ * unless the output stencil amplifies too much */
+static fmd_fast_fn pick_fast(unsigned nti, unsigned nto, unsigned at, unsigned conditioner) {
+    const unsigned a8 = at <= 6 ? 0u : 1u;
+    if (conditioner == 3u) return fmd_pick_q3(nti, nto, a8);
+    if (nti <= 1) return fmd_pick_n01(nti, nto, a8);
+    if (nti <= 3) return fmd_pick_n23(nti, nto, a8);
+    return fmd_pick_n45(nti, nto, a8);
 }
 
 /* every output of every chunk through the op-for-op path (staged through shared memory) */
@@ -493,7 +490,7 @@ static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned
     g.head = 0;
     g.exact_blocks = 0;
 
-    fast_fn fn = pick_fast(c->nti, c->nto, c->atan_terms, (unsigned) c->sec.conditioner);
+    fmd_fast_fn fn = pick_fast(c->nti, c->nto, c->atan_terms, (unsigned) c->sec.conditioner);
     const bool aligned = ((uintptr_t) d_in % 16 == 0) && ((uintptr_t) d_out % 16 == 0) && (stride % 16 == 0) &&
                          (nchunks == 1 || chunk_out % 4 == 0);
     /* the fast kernel covers whole 128-output passes; if the chunk is not a multiple of 128
@@ -673,6 +670,47 @@ static int submit_slot(fmd_ctx *c, unsigned slot, const uint8_t *in, size_t nbyt
 
 extern "C" int fmd_submit(fmd_ctx *c, unsigned slot, const uint8_t *in, size_t nbytes, float *out) {
     return submit_slot(c, slot, in, nbytes, out, true);
+}
+
+/* ---- the quality pipeline's stream over several GPUs: segments with a warm-up prefix ---- */
+
+extern "C" uint64_t fmd_warmup_samples(const fmd_ctx *c) { return (c && c->q) ? fmq_warmup_samples(c) : 0; }
+
+extern "C" size_t fmd_segment_out_count(const fmd_ctx *c, uint64_t first_sample, size_t nsamples) {
+    if (c && c->q) return fmq_out_count_at(c, first_sample, nsamples);
+    return nsamples >> 1;
+}
+
+extern "C" int fmd_submit_segment(fmd_ctx *c, unsigned slot, const uint8_t *in, size_t warm_bytes, size_t nbytes,
+                                  uint64_t first_sample, float *out) {
+    if (!c || slot >= c->nslots || !in || !out) return fmd_set_error(FMD_EINVAL, "bad slot or null buffer");
+    if (!c->q)
+        return fmd_set_error(FMD_EINVAL, "segments belong to the quality pipeline; in reference-compatible mode chunks "
+                                         "are independent and fmd_submit needs no warm-up");
+    if ((warm_bytes & 15u) || (nbytes & 1u) || warm_bytes / 2 > first_sample)
+        return fmd_set_error(FMD_EINVAL, "warm-up must be a multiple of 16 bytes that does not reach before the stream start");
+    if (warm_bytes + nbytes > c->slot_bytes) return fmd_set_error(FMD_EINVAL, "warm-up + payload exceed slot_bytes");
+    fmd_slot &s = c->slots[slot];
+    if (s.busy) return fmd_set_error(FMD_EBUSY, "slot %u still in flight: call fmd_wait first", slot);
+    FMD_CUDA(cudaSetDevice(c->device));
+    const size_t out_elem = (c->cfg.flags & FMD_FLAG_S16) ? sizeof(short) : sizeof(float);
+    const uint64_t seg_start = first_sample - warm_bytes / 2;
+    const size_t n_warm = fmq_out_count_at(c, seg_start, warm_bytes / 2);
+    const size_t n_pay = fmq_out_count_at(c, first_sample, nbytes / 2);
+    FMD_CUDA(cudaMemcpyAsync(s.d_in, in, warm_bytes + nbytes, cudaMemcpyHostToDevice, c->s_in));
+    FMD_CUDA(cudaEventRecord(s.ev_in, c->s_in));
+    FMD_CUDA(cudaStreamWaitEvent(c->s_k, s.ev_in, 0));
+    int rc = fmq_seek(c, seg_start, c->s_k);
+    if (!rc) rc = fmd_demod_device(c, s.d_in, warm_bytes + nbytes, s.d_out, c->s_k);
+    if (rc) return rc;
+    FMD_CUDA(cudaEventRecord(s.ev_k, c->s_k));
+    FMD_CUDA(cudaStreamWaitEvent(c->s_out, s.ev_k, 0));
+    if (n_pay)
+        FMD_CUDA(cudaMemcpyAsync(out, reinterpret_cast<const char *>(s.d_out) + n_warm * out_elem, n_pay * out_elem,
+                                 cudaMemcpyDeviceToHost, c->s_out));
+    FMD_CUDA(cudaEventRecord(s.ev_out, c->s_out));
+    s.busy = true;
+    return FMD_OK;
 }
 
 extern "C" int fmd_wait(fmd_ctx *c, unsigned slot) {

@@ -178,6 +178,25 @@ int fmd_ring_create(fmd_ctx *ctx, unsigned slots, size_t slot_bytes);
 int fmd_submit(fmd_ctx *ctx, unsigned slot, const uint8_t *in, size_t nbytes, float *out);
 int fmd_wait(fmd_ctx *ctx, unsigned slot);
 
+/*
+ * ---- one quality-pipeline stream over several GPUs (BASELINE north star: "a single long stream is
+ *      split into overlapped chunks with warm-up state handoff").  The reference has nothing to
+ *      replace here: its sweep keeps no state (src/matrix.c:272), which is why the
+ *      reference-compatible path needs no overlap at all.  With FMD_FLAG_QUALITY the recursive
+ *      filters do carry state, so a segment handed to another GPU starts `fmd_warmup_samples`
+ *      samples early from a zero state and drops the outputs of that prefix: the state has then
+ *      converged to the running stream's to ~1e-9 (the length follows from the slowest pole). ----
+ */
+uint64_t fmd_warmup_samples(const fmd_ctx *ctx);
+/* outputs of `nsamples` samples whose first has global index `first_sample` (decimation keeps the
+ * samples whose GLOBAL index is a multiple of the factor) */
+size_t fmd_segment_out_count(const fmd_ctx *ctx, uint64_t first_sample, size_t nsamples);
+/* like fmd_submit, for a segment: `in` holds warm_bytes of the stream that precede the payload (a
+ * multiple of 16; 0 at the stream start) and then nbytes of payload whose first sample has global
+ * index first_sample; `out` receives fmd_segment_out_count(first_sample, nbytes / 2) outputs */
+int fmd_submit_segment(fmd_ctx *ctx, unsigned slot, const uint8_t *in, size_t warm_bytes, size_t nbytes,
+                       uint64_t first_sample, float *out);
+
 /* ---- introspection for benches/tests ---- */
 
 /* kernels launched by this context since creation (fast + exact) */

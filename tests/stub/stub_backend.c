@@ -66,6 +66,33 @@ int fmd_submit(fmd_ctx *c, unsigned slot, const uint8_t *in, size_t nbytes, floa
     return 0;
 }
 
+/* segmented quality mode: the stub checks what the host must get right -- the warm-up prefix is
+ * exactly the stream bytes that precede the payload (input word k holds k) -- and then behaves
+ * like fmd_submit on the payload */
+uint64_t fmd_warmup_samples(const fmd_ctx *c) { (void) c; return getenv("STUB_WARM") ? (uint64_t) atoll(getenv("STUB_WARM")) : 0; }
+size_t fmd_segment_out_count(const fmd_ctx *c, uint64_t first_sample, size_t nsamples) { (void) c; (void) first_sample; return nsamples >> 1; }
+int fmd_submit_segment(fmd_ctx *c, unsigned slot, const uint8_t *in, size_t warm_bytes, size_t nbytes, uint64_t first_sample,
+                       float *out) {
+    if ((warm_bytes & 15u) || warm_bytes / 2 > first_sample || ((uintptr_t) in & 15u)) {
+        snprintf(g_err, sizeof g_err, "stub: bad segment geometry (warm %zu first %llu)", warm_bytes, (unsigned long long) first_sample);
+        return -1;
+    }
+    const uint64_t w0 = (first_sample * 2 - warm_bytes) / 4; /* index of the first word of the prefix */
+    for (size_t k = 0; k < (warm_bytes + nbytes) / 4; ++k) {
+        uint32_t w;
+        memcpy(&w, in + 4 * k, 4);
+        if (w != (uint32_t) (w0 + k)) {
+            snprintf(g_err, sizeof g_err, "stub: segment word %zu holds %u, expected %u", k, w, (uint32_t) (w0 + k));
+            return -1;
+        }
+    }
+    const size_t keep = c->slot_bytes; /* the ring was sized for warm-up + payload */
+    c->slot_bytes = (size_t) -1;
+    int rc = fmd_submit(c, slot, in + warm_bytes, nbytes, out);
+    c->slot_bytes = keep;
+    return rc;
+}
+
 int fmd_wait(fmd_ctx *c, unsigned slot) {
     (void) slot;
     if (getenv("STUB_JITTER")) {

@@ -56,14 +56,15 @@ def run(exe, args, env_extra, **kw):
     return subprocess.run([exe] + args, env=env, timeout=120, **kw)
 
 
-@pytest.mark.parametrize("slots,threads,devices", [(2, 8, 1), (3, 4, 1), (2, 3, 2), (5, 7, 3), (3, 8, 4), (2, 1, 1)])
-def test_file_to_file_keeps_order(exe, tmp_path, slots, threads, devices):
+@pytest.mark.parametrize("slots,threads,devices,mmap_out", [(2, 8, 1, True), (3, 4, 1, False), (2, 3, 2, True), (5, 7, 3, False),
+                                                            (3, 16, 4, True), (2, 1, 1, True), (2, 8, 1, False)])
+def test_file_to_file_keeps_order(exe, tmp_path, slots, threads, devices, mmap_out):
     # 1 MiB slots, > 4 * nslots slots of data, ragged tail (not a multiple of the chunk or of 4)
     nbytes = 41 * (1 << 20) + 262144 * 2 + 1234 + 3
     src, dst = str(tmp_path / "in.u8"), str(tmp_path / "out.f32")
     want = make_input(src, nbytes)
     env = dict(FMD_SLOT_MB="1", FMD_SLOTS=str(slots), FMD_IO_THREADS=str(threads),
-               STUB_DEVICES=str(devices), FMD_DEVICES="all")
+               STUB_DEVICES=str(devices), FMD_DEVICES="all", FMD_NO_MMAP="0" if mmap_out else "1")
     for _ in range(3):
         r = run(exe, ["-i", src, "-o", dst], env)
         assert r.returncode == 0
@@ -125,3 +126,20 @@ def test_inherited_stdin_is_read_from_where_it_stands(exe, tmp_path):
     got = np.fromfile(dst, dtype=np.float32)
     assert np.array_equal(got, want[skip // 4:])
     assert int(r.stdout.split()[0]) == 0  # nothing left for the next reader of the descriptor
+
+
+@pytest.mark.parametrize("from_file", [True, False])
+def test_segmented_quality_stream_hands_every_gpu_its_warm_up_prefix(exe, tmp_path, from_file):
+    """-Q over several GPUs: every slot is a segment that starts `fmd_warmup_samples` early.  The
+    stand-in backend checks that the prefix it is handed is exactly the stream before the payload
+    (and fails the submit otherwise); the outputs must still come back in order."""
+    nbytes = 23 * (1 << 20) + 262144
+    src, dst = str(tmp_path / "in.u8"), str(tmp_path / "out.f32")
+    want = make_input(src, nbytes)
+    env = dict(os.environ, STUB_JITTER="1", FMD_SLOT_MB="1", FMD_SLOTS="2", FMD_IO_THREADS="4", STUB_DEVICES="3",
+               FMD_DEVICES="all", STUB_WARM="5000")
+    cmd = f"{exe} -i {src} -o {dst} -Q -r2400000 -S48000" if from_file else f"cat {src} | {exe} -i - -o {dst} -Q -r2400000 -S48000"
+    r = subprocess.run(cmd, shell=True, env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    got = np.fromfile(dst, dtype=np.float32)
+    assert got.size == nbytes // 4 and np.array_equal(got, want)

@@ -205,3 +205,49 @@ def test_quality_cli(tmp_path_nodash, oracle_port):
     # the CLI drops a ragged tail below 4 bytes (2 samples), like the reference-compatible mode
     want = oracle_port.quality(cfg, rate).run(raw[: raw.size & ~3])
     assert max_err(out, want) <= TOL
+
+
+@pytest.mark.parametrize("case", [dict(sig="cfg3", rate=2.4e6, fs=48000.0, fc_out=15000.0),
+                                  dict(sig="cfg2", rate=192e3, fs=96000.0, fc_out=6500.0, fc_in=12500.0),
+                                  dict(sig="cfg3", rate=2.4e6, fs=48000.0, fc_out=4000.0, fc_in=9000.0, deg_out=5, deg_in=4, mode=1)])
+def test_quality_segments_with_warm_up_match_the_stream(case, oracle_port):
+    """The multi-GPU form of the stream (fmd_submit_segment): independent segments that start
+    fmd_warmup_samples early from a ZERO state and drop the prefix's outputs must reproduce the one
+    carried-state stream.  Run here on one GPU with segments in scrambled order -- nothing may depend
+    on which context, or in which order, a segment is processed."""
+    from demodulator_b200.api import PinnedBuffer
+    case = dict(case)
+    sig, rate = case.pop("sig"), case.pop("rate")
+    cfg = po.Config(**case)
+    raw = synth.config_signal(sig, 40)
+    n = raw.size // 2
+    want = oracle_port.quality(cfg, rate).run(raw)
+    with fm.Demodulator(**quality_kwargs(cfg, rate)) as d:
+        W = d.warmup_samples()
+        assert W % 8 == 0 and 0 < W < n // 8
+        seg = (n // 5 + 12345) // 8 * 8  # ragged against tiles, decimation and chunks; multiple of 8 samples
+        d.ring_create(2, 2 * (seg + W) // 262144 * 262144 + 262144)
+        pin = PinnedBuffer(raw.size)
+        pin.u8[:] = raw
+        outs = PinnedBuffer(4 * (n + 8))
+        starts = list(range(0, n, seg))
+        offs, counts, o = {}, {}, 0
+        for g0 in starts:
+            ns = min(seg, n - g0)
+            counts[g0] = d.segment_out_count(g0, ns)
+            offs[g0] = o
+            o += counts[g0]
+        assert o == want.size
+        order = starts[::-2] + starts[-2::-2] if len(starts) > 1 else starts
+        assert sorted(order) == starts
+        for i, g0 in enumerate(order):
+            ns = min(seg, n - g0)
+            warm = min(W, g0)
+            d.wait(i % 2)
+            d.submit_segment(i % 2, pin.ptr + 2 * (g0 - warm), 2 * warm, 2 * ns, g0, outs.ptr + 4 * offs[g0])
+        d.wait(0); d.wait(1)
+        got = outs.view(np.float32)[: want.size].copy()
+        pin.free(); outs.free()
+    err = max_err(got, want)
+    print(f"segments with warm-up {W}: max-abs {err:.2e}")
+    assert err <= 2e-5, err
