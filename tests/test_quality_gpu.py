@@ -209,7 +209,7 @@ def test_quality_cli(tmp_path_nodash, oracle_port):
 
 @pytest.mark.parametrize("case", [dict(sig="cfg3", rate=2.4e6, fs=48000.0, fc_out=15000.0),
                                   dict(sig="cfg2", rate=192e3, fs=96000.0, fc_out=6500.0, fc_in=12500.0),
-                                  dict(sig="cfg3", rate=2.4e6, fs=48000.0, fc_out=4000.0, fc_in=9000.0, deg_out=5, deg_in=4, mode=1)])
+                                  dict(sig="cfg3", rate=2.4e6, fs=48000.0, fc_out=14000.0, fc_in=30000.0, deg_out=5, deg_in=4, mode=1)])
 def test_quality_segments_with_warm_up_match_the_stream(case, oracle_port):
     """The multi-GPU form of the stream (fmd_submit_segment): independent segments that start
     fmd_warmup_samples early from a ZERO state and drop the prefix's outputs must reproduce the one
