@@ -467,6 +467,49 @@ __device__ __forceinline__ uint2 fmd_lds64(uint32_t a) {
     return v;
 }
 
+/* ---- 1-D TMA ring: one elected lane per warp moves the warp's 512 bytes of a pass with a single
+ * bulk copy (cp.async.bulk, SASS UBLKCP) that signals an mbarrier; the 32 lanes only test the
+ * barrier's phase.  Address, predicate, commit and wait bookkeeping of the per-lane cp.async ring
+ * leave 31 of the 32 lanes. ---- */
+__device__ __forceinline__ void fmd_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fmd_mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+/* arm the barrier with the byte count and start the copy (called by ONE lane) */
+__device__ __forceinline__ void fmd_bulk_fetch(uint32_t smem_dst, const void *gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+                 "l"(gsrc), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+/* wait until the barrier's phase with parity `parity` has completed; bounded: a copy that never
+ * lands traps (an error the host sees) instead of hanging the GPU */
+__device__ __forceinline__ void fmd_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0u;
+#pragma unroll 1
+    for (unsigned spin = 0; spin < (1u << 22); ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+/* one lane of the (converged) warp, chosen by the hardware: lets ptxas keep the copy's operands uniform */
+__device__ __forceinline__ bool fmd_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0u;
+}
+
+#ifndef FMD_TMA
+#define FMD_TMA 0 /* 1: bulk-copy (TMA) ring with mbarriers; 0: per-lane cp.async ring */
+#endif
 #ifndef FMD_MINB
 #define FMD_MINB(NTI) 4 /* resident CTAs per SM the register budget is cut for */
 #endif
@@ -502,11 +545,16 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     constexpr int S = FMD_STAGES;
     constexpr bool HALO = NTI > 1;               /* lane 31 needs lane 0's next pass */
     constexpr int PENDING = HALO ? S - 2 : S - 1; /* groups allowed in flight at the wait */
-    __shared__ uint4 ring[S * FMD_BLOCK];
+    constexpr bool TMA = FMD_TMA != 0;
+    __shared__ __align__(128) uint4 ring[S * FMD_BLOCK];
+    __shared__ __align__(8) unsigned long long bars[TMA ? S * FMD_WARPS : 1]; /* one mbarrier per warp and stage */
 
     const unsigned lane = threadIdx.x & 31u;
+    /* warp-uniform by construction (the shuffle tells ptxas so): segment, source and ring addresses
+     * of the warp can then live in uniform registers, which is what the bulk copy takes */
+    const unsigned warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     /* the host keeps nchunks * segs_per_chunk below 2^32 per launch */
-    const unsigned seg = (blockIdx.x - g.exact_blocks) * FMD_WARPS + (threadIdx.x >> 5);
+    const unsigned seg = (blockIdx.x - g.exact_blocks) * FMD_WARPS + warp;
     if (seg >= g.nchunks * g.segs_per_chunk) return;
     const unsigned chunk = seg / g.segs_per_chunk;
     const unsigned sic = seg - chunk * g.segs_per_chunk;
@@ -519,19 +567,40 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     const unsigned nxt_lane = (lane + 1u) & 31u;
     const unsigned k0 = it0 * FMD_PASS_OUT + lane * 4u;
 
-    const uint8_t *__restrict__ src = in + (unsigned long long) chunk * g.chunk_stride + 4ull * k0;
+    /* the warp's first byte (what the bulk copy reads from), then this lane's 16 bytes in it */
+    const uint8_t *__restrict__ src0 = in + (unsigned long long) chunk * g.chunk_stride + 4ull * (it0 * FMD_PASS_OUT);
+    const uint8_t *__restrict__ src = src0 + lane * 16u;
     float *__restrict__ dst = out + (unsigned long long) chunk * g.chunk_out + k0;
     const uint4 fill = make_uint4(FMD_FILL, FMD_FILL, FMD_FILL, FMD_FILL);
-    const uint32_t sbase = (uint32_t) __cvta_generic_to_shared(&ring[threadIdx.x]);
+    /* TMA ring: the warp's 512 bytes of slot q start at lane 0's entry; stage barriers of this warp */
+    const uint32_t wbase = (uint32_t) __cvta_generic_to_shared(&ring[0]) + warp * 512u;
+    const uint32_t sbase = wbase + lane * 16u;
     constexpr uint32_t SLOT = FMD_BLOCK * 16u;
     static_assert(S == 4 || S == 8, "the main loop is unrolled by the ring depth");
+    const uint32_t bbase = (uint32_t) __cvta_generic_to_shared(&bars[0]) + (TMA ? warp * (8u * S) : 0u);
+    if (TMA) {
+        if (lane == 0u) {
+#pragma unroll
+            for (int q = 0; q < S; ++q) fmd_mbar_init(bbase + 8u * q, 1u);
+            fmd_mbar_fence_init();
+        }
+        __syncwarp();
+    }
 
     /* position q of the segment lives in ring slot q % S; positions >= n_ld do not exist in memory */
 #pragma unroll
     for (int q = 0; q < S - 1; ++q) {
-        if ((unsigned) q < n_ld) fmd_cp_async16(sbase + q * SLOT, src + 512 * q);
-        fmd_cp_commit();
+        if (TMA) {
+            if ((unsigned) q < n_ld && fmd_elect_one()) fmd_bulk_fetch(wbase + q * SLOT, src0 + 512 * q, 512u, bbase + 8u * q);
+        } else {
+            if ((unsigned) q < n_ld) fmd_cp_async16(sbase + q * SLOT, src + 512 * q);
+            fmd_cp_commit();
+        }
     }
+    /* stage s holds position base + s during the trip that starts at `base`: its k-th fill, k = base / S,
+     * completes the barrier phase of parity k & 1 */
+    unsigned ph = 0u;
+    if (TMA && HALO) fmd_mbar_wait(bbase, 0u); /* position 0; every pass then waits for its successor's stage */
 
     float x0[4], x1[4] = {0.f, 0.f, 0.f, 0.f};
     const uint2 fill2 = make_uint2(FMD_FILL, FMD_FILL);
@@ -539,7 +608,7 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     constexpr int HWORDS = NTI > 1 ? NTI / 2 : 0; /* halo words: (NTI - 1 + 1) / 2 */
     uint32_t w0c = 0u;
     if (CARRY) { /* the first pass takes its biased first word from here, every later one from its predecessor */
-        fmd_cp_wait<S - 2>();
+        if (!TMA) fmd_cp_wait<S - 2>();
         w0c = fmd_bias_bytes(fmd_lds32(sbase));
     }
     /* the chunk head [0, head) belongs to the exact path: those lanes of the very first store
@@ -552,15 +621,25 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
      * immediates because the loop is unrolled by the ring depth. */
 #define FMD_STEP(U, XPREV, XCUR, STP)                                                                   \
     {                                                                                                   \
-        if (FMD_OVERREAD || base + (U) + S - 1 < n_ld)                                                  \
-            fmd_cp_async16(sbase + (((U) + S - 1) & (S - 1)) * SLOT, src + 512 * ((U) + S - 1));        \
-        fmd_cp_commit();                                                                                \
-        fmd_cp_wait<PENDING>();                                                                         \
+        const bool hz = HALO && (U) == S - 1 && base + S >= n_ld; /* what follows is the zero extension */ \
+        if (TMA) {                                                                                      \
+            /* the slot pass p - 1 read is free: every lane's LDS of it has been consumed */            \
+            __syncwarp();                                                                               \
+            if (base + (U) + S - 1 < n_ld && fmd_elect_one())                                           \
+                fmd_bulk_fetch(wbase + (((U) + S - 1) & (S - 1)) * SLOT, src0 + 512 * ((U) + S - 1), 512u, \
+                               bbase + 8u * (((U) + S - 1) & (S - 1)));                                 \
+            if (!HALO) fmd_mbar_wait(bbase + 8u * (U), ph);                                             \
+            else if (!hz) fmd_mbar_wait(bbase + 8u * (((U) + 1) & (S - 1)), (U) == S - 1 ? ph ^ 1u : ph); \
+        } else {                                                                                        \
+            if (FMD_OVERREAD || base + (U) + S - 1 < n_ld)                                              \
+                fmd_cp_async16(sbase + (((U) + S - 1) & (S - 1)) * SLOT, src + 512 * ((U) + S - 1));    \
+            fmd_cp_commit();                                                                            \
+            fmd_cp_wait<PENDING>();                                                                     \
+        }                                                                                               \
         const uint4 cur = fmd_lds128(sbase + (U) * SLOT);                                               \
         uint2 nx = fill2;                                                                               \
         if (HALO && HWORDS >= 2) nx = fmd_lds64(sbase + (((U) + 1) & (S - 1)) * SLOT);                  \
         if (HALO && HWORDS < 2) nx.x = fmd_lds32(sbase + (((U) + 1) & (S - 1)) * SLOT);                 \
-        const bool hz = HALO && (U) == S - 1 && base + S >= n_ld; /* what follows is the zero extension */ \
         if (hz) nx = fill2;                                                                             \
         fmd_pass<NTI, NTO, AT, false, COND>(cur, nx, XPREV, XCUR, false, dst + 128 * ((U) - 1), STP, lane, nxt_lane, st, w0c, hz); \
     }
@@ -579,7 +658,9 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
             FMD_STEP(7, x0, x1, true)
         }
         src += 512 * S;
+        src0 += 512 * S;
         dst += 128 * S;
+        ph ^= 1u;
     }
 #undef FMD_STEP
     /* n_it is not a multiple of the ring depth: up to S-1 more real passes, slots by arithmetic.
@@ -587,9 +668,19 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     unsigned p = base;
     for (; p < n_it; ++p) {
         const unsigned u = p - base;
-        if (p + S - 1 < n_ld) fmd_cp_async16(sbase + ((u + S - 1) & (S - 1)) * SLOT, src + 512 * (u + S - 1));
-        fmd_cp_commit();
-        fmd_cp_wait<PENDING>();
+        if (TMA) {
+            __syncwarp();
+            if (p + S - 1 < n_ld && fmd_elect_one())
+                fmd_bulk_fetch(wbase + ((u + S - 1) & (S - 1)) * SLOT, src0 + 512 * (u + S - 1), 512u,
+                               bbase + 8u * ((u + S - 1) & (S - 1)));
+            /* fewer than S passes are left: stages u and u + 1 still belong to this trip's phase */
+            if (!HALO) fmd_mbar_wait(bbase + 8u * u, ph);
+            else if (p + 1 < n_ld) fmd_mbar_wait(bbase + 8u * (u + 1u), ph);
+        } else {
+            if (p + S - 1 < n_ld) fmd_cp_async16(sbase + ((u + S - 1) & (S - 1)) * SLOT, src + 512 * (u + S - 1));
+            fmd_cp_commit();
+            fmd_cp_wait<PENDING>();
+        }
         const uint4 cur = fmd_lds128(sbase + (u & (S - 1)) * SLOT);
         uint2 nx = fill2;
         if (HALO && p + 1 < n_ld) nx = fmd_lds64(sbase + ((u + 1) & (S - 1)) * SLOT);
@@ -601,15 +692,19 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
      * 31, through the shuffle), so with a 2-tap output stencil half a pass is enough */
     {
         const unsigned u = p - base;
-        fmd_cp_commit();
-        fmd_cp_wait<PENDING>();
+        if (TMA) {
+            if (!HALO && p < n_ld) fmd_mbar_wait(bbase + 8u * u, ph); /* (with a halo the last pass waited for it) */
+        } else {
+            fmd_cp_commit();
+            fmd_cp_wait<PENDING>();
+        }
         uint4 cur = fill;
         if (p < n_ld) cur = fmd_lds128(sbase + (u & (S - 1)) * SLOT);
         fmd_pass<NTI, NTO, AT, (NTO <= 2), COND>(cur, fill2, x1, x0, end_zero, dst + 128 * ((int) u - 1),
                                                  p >= 2 || (p == 1 && head_keep), lane, nxt_lane, st, w0c);
     }
 
-    fmd_cp_wait<0>();
+    if (!TMA) fmd_cp_wait<0>();
 }
 
 #endif /* FMD_KERNELS_CUH */

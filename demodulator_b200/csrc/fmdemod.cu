@@ -338,6 +338,23 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
         return fmd_set_error(FMD_ECUDA, "coefficient upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     if (quality) {
+        /* The recursion state is float32: a pole at radius rho amplifies its rounding noise by
+         * roughly 1/(1-rho)^2.  Measured on B200 against the double-precision serial oracle:
+         * rho = 0.9806 (Butterworth 3, fc/rate 0.006) 3e-6, rho = 0.9987 1e-4 (the bar),
+         * rho = 0.9994 (Chebyshev 5, fc/rate 0.0017) 1.8e-2 -- profiles/r02_quality_narrow_diag.txt.
+         * Designs past 0.9985 are refused instead of answered wrongly. */
+        double rho = 0.0;
+        for (unsigned r = 0; r < c->lout + c->lin; ++r) {
+            const float *row = r < c->lout ? c->sec.out[r] : c->sec.in[r - c->lout];
+            const double rr = row[5] != 0.0f ? sqrt(fabs((double) row[5])) : fabs((double) row[4]);
+            if (rr > rho) rho = rr;
+        }
+        if (!(rho <= 0.9985)) {
+            fmd_destroy(c);
+            return fmd_set_error(FMD_EINVAL,
+                                 "quality mode keeps the filter state in float32: the slowest pole of this design has "
+                                 "radius %.5f (limit 0.9985) -- raise the cut-off or lower the degree", rho);
+        }
         rc = fmq_setup(c, q_decim);
         if (rc) {
             fmd_destroy(c);
