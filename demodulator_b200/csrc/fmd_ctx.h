@@ -70,6 +70,7 @@ fmd_fast_fn fmd_pick_n01(unsigned nti, unsigned nto, unsigned a8);
 fmd_fast_fn fmd_pick_n23(unsigned nti, unsigned nto, unsigned a8);
 fmd_fast_fn fmd_pick_n45(unsigned nti, unsigned nto, unsigned a8);
 fmd_fast_fn fmd_pick_q3(unsigned nti, unsigned nto, unsigned a8);
+fmd_fast_fn fmd_pick_float(unsigned nti, unsigned nto, unsigned a8); /* float-input kernel (-q1); takes const float* as its first argument */
 
 /* ---- quality pipeline, fmd_quality_host.cu ---- */
 int fmq_setup(fmd_ctx *c, unsigned decim);

@@ -300,6 +300,70 @@ fmd_exact_tiled_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, 
 #define FMD_FILL 0x7f7f7f7fu /* four bytes that shift to 0.0: the zero extension past a chunk */
 
 /*
+ * The arithmetic of one pass once the lane's samples are floats: vi[k] = (I_k, I_{k+4}),
+ * vq[k] = (Q_k, Q_{k+4}) for k = 0 .. 3 + (NTI > 1 ? NTI - 1 : 0) (entries from 4 on reach into the
+ * next lane's samples).  Input stencil, four discriminator outputs into xcur, output stencil over
+ * the PREVIOUS pass's xprev, one 16-byte store.  Shared by the byte-input kernel (fmd_pass unpacks
+ * into vi / vq) and the float-input one (-q1: the samples arrive conditioned).
+ */
+template <int NTI, int NTO, int AT, bool LITE, int NK>
+__device__ __forceinline__ void fmd_pass_core(const fmd_f2 (&vi)[NK], const fmd_f2 (&vq)[NK], const float (&xprev)[4],
+                                              float (&xcur)[4], const bool zero_x, float *__restrict__ dst,
+                                              const bool do_store, const unsigned lane, const unsigned nxt_lane,
+                                              const FmdStencil &st) {
+    constexpr int NB = NTO - 1; /* discriminator outputs needed from the next lane */
+#pragma unroll
+    for (int j = 0; j < (LITE ? 1 : 2); ++j) { /* outputs j and j+2 */
+        fmd_f2 a, b, c, d;
+        if (NTI == 0) {
+            a = vi[2 * j]; b = vq[2 * j]; c = vi[2 * j + 1]; d = vq[2 * j + 1];
+        } else {
+            /* The input stencil is applied up to its (positive) common factor tin[0]^2, which the
+             * atan2 of the product does not see: z'[c] = s[c] + sum_{t>=1} (tin[t]/tin[0]) s[c+t],
+             * plus dcq/tin[0] on the Q lane (the host normalises; dci is 0 for every design). */
+            const fmd_f2 dq = fmd_bc(st.dcq);
+            a = vi[2 * j];
+            b = fmd_add2(vq[2 * j], dq);
+            c = vi[2 * j + 1];
+            d = fmd_add2(vq[2 * j + 1], dq);
+#pragma unroll
+            for (int t = 1; t < NTI; ++t) {
+                const fmd_f2 tap = fmd_bc(st.tin[t]);
+                a = fmd_fma2(tap, vi[2 * j + t], a);
+                b = fmd_fma2(tap, vq[2 * j + t], b);
+                c = fmd_fma2(tap, vi[2 * j + 1 + t], c);
+                d = fmd_fma2(tap, vq[2 * j + 1 + t], d);
+            }
+        }
+        /* s0 * conj(s1).  The fused forms keep the reference's signed-zero results: a sum of
+         * two exact-zero products takes the same sign fused or not. */
+        const fmd_f2 re = fmd_fma2(a, c, fmd_mul2(b, d));
+        const fmd_f2 im = fmd_fma2(fmd_neg2(a), d, fmd_mul2(b, c));
+        fmd_atan2_x2<AT>(im, re, xcur[j], xcur[j + 2]);
+    }
+    if (LITE) xcur[1] = xcur[3] = 0.0f; /* drain pass: only lane 0's first output is ever read */
+    if (zero_x) { /* past the end of the chunk the discriminator output is exactly 0 */
+        xcur[0] = 0.0f; xcur[1] = 0.0f; xcur[2] = 0.0f; xcur[3] = 0.0f;
+    }
+
+    float xn[4 + (NB > 0 ? NB : 1)];
+    xn[0] = xprev[0]; xn[1] = xprev[1]; xn[2] = xprev[2]; xn[3] = xprev[3];
+#pragma unroll
+    for (int t = 0; t < NB; ++t)
+        xn[4 + t] = __shfl_sync(0xffffffffu, lane == 0 ? xcur[t] : xprev[t], nxt_lane);
+    float4 y;
+    float *yy = reinterpret_cast<float *>(&y);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float acc = st.dco;
+#pragma unroll
+        for (int t = 0; t < NTO; ++t) acc = fmaf(st.tout[t], xn[j + t], acc);
+        yy[j] = acc;
+    }
+    if (do_store) *reinterpret_cast<float4 *>(dst) = y;
+}
+
+/*
  * One pass of one lane: unpack `cur` (8 complex samples), input lowpass, four
  * discriminator outputs into xcur; then the output lowpass over the PREVIOUS
  * pass's xprev (neighbours: next lane's xprev, or lane 0's xcur for lane 31)
@@ -329,7 +393,6 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, con
                                          const FmdStencil &st, uint32_t &w0c, const bool hz = false) {
     constexpr int HC = NTI > 1 ? NTI - 1 : 0; /* complex samples needed from the next lane */
     constexpr int HW = (HC + 1) / 2;          /* ... as 4-byte words (2 complex each)      */
-    constexpr int NB = NTO - 1;               /* discriminator outputs needed from the next lane */
     constexpr bool CARRY = FmdCarry<NTI, COND>::value;
 
     /* biased words: own four, then the halo from the next lane (lane 31: lane 0's next pass) */
@@ -391,55 +454,7 @@ __device__ __forceinline__ void fmd_pass(const uint4 &cur, const uint2 &nxt, con
         }
     }
 
-#pragma unroll
-    for (int j = 0; j < (LITE ? 1 : 2); ++j) { /* outputs j and j+2 */
-        fmd_f2 a, b, c, d;
-        if (NTI == 0) {
-            a = vi[2 * j]; b = vq[2 * j]; c = vi[2 * j + 1]; d = vq[2 * j + 1];
-        } else {
-            /* The input stencil is applied up to its (positive) common factor tin[0]^2, which the
-             * atan2 of the product does not see: z'[c] = s[c] + sum_{t>=1} (tin[t]/tin[0]) s[c+t],
-             * plus dcq/tin[0] on the Q lane (the host normalises; dci is 0 for every design). */
-            const fmd_f2 dq = fmd_bc(st.dcq);
-            a = vi[2 * j];
-            b = fmd_add2(vq[2 * j], dq);
-            c = vi[2 * j + 1];
-            d = fmd_add2(vq[2 * j + 1], dq);
-#pragma unroll
-            for (int t = 1; t < NTI; ++t) {
-                const fmd_f2 tap = fmd_bc(st.tin[t]);
-                a = fmd_fma2(tap, vi[2 * j + t], a);
-                b = fmd_fma2(tap, vq[2 * j + t], b);
-                c = fmd_fma2(tap, vi[2 * j + 1 + t], c);
-                d = fmd_fma2(tap, vq[2 * j + 1 + t], d);
-            }
-        }
-        /* s0 * conj(s1).  The fused forms keep the reference's signed-zero results: a sum of
-         * two exact-zero products takes the same sign fused or not. */
-        const fmd_f2 re = fmd_fma2(a, c, fmd_mul2(b, d));
-        const fmd_f2 im = fmd_fma2(fmd_neg2(a), d, fmd_mul2(b, c));
-        fmd_atan2_x2<AT>(im, re, xcur[j], xcur[j + 2]);
-    }
-    if (LITE) xcur[1] = xcur[3] = 0.0f; /* drain pass: only lane 0's first output is ever read */
-    if (zero_x) { /* past the end of the chunk the discriminator output is exactly 0 */
-        xcur[0] = 0.0f; xcur[1] = 0.0f; xcur[2] = 0.0f; xcur[3] = 0.0f;
-    }
-
-    float xn[4 + (NB > 0 ? NB : 1)];
-    xn[0] = xprev[0]; xn[1] = xprev[1]; xn[2] = xprev[2]; xn[3] = xprev[3];
-#pragma unroll
-    for (int t = 0; t < NB; ++t)
-        xn[4 + t] = __shfl_sync(0xffffffffu, lane == 0 ? xcur[t] : xprev[t], nxt_lane);
-    float4 y;
-    float *yy = reinterpret_cast<float *>(&y);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float acc = st.dco;
-#pragma unroll
-        for (int t = 0; t < NTO; ++t) acc = fmaf(st.tout[t], xn[j + t], acc);
-        yy[j] = acc;
-    }
-    if (do_store) *reinterpret_cast<float4 *>(dst) = y;
+    fmd_pass_core<NTI, NTO, AT, LITE, NK>(vi, vq, xprev, xcur, zero_x, dst, do_store, lane, nxt_lane, st);
 }
 
 /* ---- cp.async (LDGSTS) ring: global -> shared without staging registers ---- */
@@ -705,6 +720,95 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     }
 
     if (!TMA) fmd_cp_wait<0>();
+}
+
+/* ------------------------------------------------- float-input streaming kernel (-q1) */
+
+/*
+ * The same streaming pass over samples that arrive as FLOATS, one per input byte in the same
+ * interleaved layout: -q1 (correctIq, matrix.c:120-140) conditions the stream with offsets that
+ * run through the whole stream (fmd_correctiq.cuh), so its samples are not a function of their
+ * own bytes.  A lane reads its 8 complex samples (64 bytes, four 16-byte loads) one pass ahead
+ * into registers; the input-filter halo is the next lane's first samples by shuffle (lane 31:
+ * lane 0's already loaded next pass); the zero extension past a chunk is the float 0.
+ * Chunk heads and ragged remainders go to the exact CTAs exactly as in fmd_fast_kernel (their
+ * base lane reads the same floats).  HBM-bound: 8 B read + 2 B written per sample.
+ */
+#define FMD_FBLOCK_MINB 3
+
+template <int NTI, int NTO, int AT>
+__global__ void __launch_bounds__(FMD_BLOCK, FMD_FBLOCK_MINB)
+fmd_fastf_kernel(const float *__restrict__ in, float *__restrict__ out, const FmdGeom g, const FmdStencil st,
+                 const FmdSections *__restrict__ sec) {
+    if (blockIdx.x < g.exact_blocks) {
+        fmd_exact_thread(reinterpret_cast<const uint8_t *>(in), out, g, sec,
+                         (unsigned long long) blockIdx.x * FMD_BLOCK + threadIdx.x);
+        return;
+    }
+    constexpr int HC = NTI > 1 ? NTI - 1 : 0; /* complex samples needed from the next lane */
+    constexpr int NK = 4 + HC;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned seg = (blockIdx.x - g.exact_blocks) * FMD_WARPS + (threadIdx.x >> 5);
+    if (seg >= g.nchunks * g.segs_per_chunk) return;
+    const unsigned chunk = seg / g.segs_per_chunk;
+    const unsigned sic = seg - chunk * g.segs_per_chunk;
+    const unsigned it0 = sic * g.iters_per_seg;
+    const unsigned iters_chunk = g.fast_out >> 7;
+    const unsigned n_it = min(g.iters_per_seg, iters_chunk - it0);
+    const bool end_zero = (it0 + n_it == iters_chunk) && (g.fast_out == g.chunk_out);
+    const unsigned n_ld = end_zero ? n_it : n_it + 1u;
+    const unsigned nxt_lane = (lane + 1u) & 31u;
+    const unsigned k0 = it0 * FMD_PASS_OUT + lane * 4u;
+    /* chunk_stride is in bytes; an output comes from 2 complex samples = 4 floats */
+    const float4 *__restrict__ src = reinterpret_cast<const float4 *>(
+        reinterpret_cast<const uint8_t *>(in) + (unsigned long long) chunk * g.chunk_stride + 16ull * k0);
+    float *__restrict__ dst = out + (unsigned long long) chunk * g.chunk_out + k0;
+    const bool head_keep = !(it0 == 0 && k0 < g.head);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    /* position p: 128 float4 per warp (lane l: entries 4l .. 4l+3) */
+    float4 cur[4], nxt[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cur[i] = __ldg(src + i);
+
+    float x0[4], x1[4] = {0.f, 0.f, 0.f, 0.f};
+    for (unsigned p = 0; p <= n_it; ++p) {
+        const bool drain = p == n_it;
+        /* the following position, or the zero extension past the chunk */
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nxt[i] = (p + 1u < n_ld) ? __ldg(src + 128u * (p + 1u) + i) : zero4;
+        if (drain && !(p < n_ld)) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cur[i] = zero4;
+        }
+        /* complex sample k of this lane: (c[2k], c[2k+1]); samples 8.. come from the next lane */
+        const float *c = reinterpret_cast<const float *>(cur);
+        const float *n = reinterpret_cast<const float *>(nxt);
+        float hI[HC > 0 ? HC : 1], hQ[HC > 0 ? HC : 1];
+#pragma unroll
+        for (int h = 0; h < HC; ++h) {
+            hI[h] = __shfl_sync(0xffffffffu, lane == 0 ? n[2 * h] : c[2 * h], nxt_lane);
+            hQ[h] = __shfl_sync(0xffffffffu, lane == 0 ? n[2 * h + 1] : c[2 * h + 1], nxt_lane);
+        }
+        fmd_f2 vi[NK], vq[NK];
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+            vi[k] = fmd_pk(c[2 * k], k + 4 < 8 ? c[2 * (k + 4)] : hI[k + 4 - 8 < HC ? k + 4 - 8 : 0]);
+            vq[k] = fmd_pk(c[2 * k + 1], k + 4 < 8 ? c[2 * (k + 4) + 1] : hQ[k + 4 - 8 < HC ? k + 4 - 8 : 0]);
+        }
+        const bool do_store = p >= 2 || (p == 1 && head_keep);
+        if (!drain) {
+            fmd_pass_core<NTI, NTO, AT, false, NK>(vi, vq, x1, x0, false, dst + 128 * ((int) p - 1), do_store, lane, nxt_lane, st);
+        } else { /* the drain pass: only lane 0's first outputs are consumed (by lane 31) */
+            fmd_pass_core<NTI, NTO, AT, (NTO <= 2), NK>(vi, vq, x1, x0, end_zero, dst + 128 * ((int) p - 1), do_store, lane,
+                                                        nxt_lane, st);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            cur[i] = nxt[i];
+            x1[i] = x0[i];
+        }
+    }
 }
 
 #endif /* FMD_KERNELS_CUH */

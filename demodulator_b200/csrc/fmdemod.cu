@@ -228,9 +228,8 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
      * are fully swept -- exactly what the composed stencil gives on the zero extension -- and only
      * the third is partial, so the composition is used while the input stencil has at most 3 taps
      * (degree <= 8: it then never reaches the third); wider ones stay on the op-for-op path. */
-    /* -q1 (correctIq): the samples are conditioned by a scan of their own (fmd_correctiq.cuh) and the
-     * rest runs op for op on the conditioned floats */
-    if (conditioner == 1u) c->fast_in_ok = false;
+    /* -q1 (correctIq): the samples are conditioned by a scan of their own (fmd_correctiq.cuh); the
+     * conditioned floats then stream through the float-input kernel (up to 3 input taps) */
 
     /* quality mode runs both filters at the input rate (the output one BEFORE the decimation) */
     const double design_rate = quality ? cfg.input_rate : cfg.sample_rate;
@@ -310,7 +309,7 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
         delete c;
         return rc;
     }
-    if (conditioner == 3u && c->nti > 3u) c->fast_in_ok = false; /* -q3 under -L streams up to 3 input taps (degree <= 8) */
+    if ((conditioner == 3u || conditioner == 1u) && c->nti > 3u) c->fast_in_ok = false; /* -q3 / -q1 under -L stream up to 3 input taps (degree <= 8) */
     {
         /* the discriminator's error reaches the output multiplied by sum|tout|: keep it near 2e-5 */
         double gain = 0.0;
@@ -495,7 +494,7 @@ static int launch_exact(fmd_ctx *c, const uint8_t *d_in, float *d_out, FmdGeom g
 
 /* `nchunks` chunks of `chunk_out` outputs each, chunk starts `stride` bytes apart */
 static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned nchunks, unsigned chunk_out,
-                         unsigned long long stride, cudaStream_t s) {
+                         unsigned long long stride, cudaStream_t s, bool float_in = false) {
     if (!nchunks || !chunk_out) return FMD_OK;
     FmdGeom g;
     g.chunk_stride = stride;
@@ -507,7 +506,10 @@ static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned
     g.head = 0;
     g.exact_blocks = 0;
 
-    fmd_fast_fn fn = pick_fast(c->nti, c->nto, c->atan_terms, (unsigned) c->sec.conditioner);
+    /* float_in: `d_in` holds conditioned floats, one per input byte (-q1); same geometry, the
+     * float-input instantiation of the streaming kernel */
+    fmd_fast_fn fn = float_in ? fmd_pick_float(c->nti, c->nto, c->atan_terms <= 6 ? 0u : 1u)
+                              : pick_fast(c->nti, c->nto, c->atan_terms, (unsigned) c->sec.conditioner);
     const bool aligned = ((uintptr_t) d_in % 16 == 0) && ((uintptr_t) d_out % 16 == 0) && (stride % 16 == 0) &&
                          (nchunks == 1 || chunk_out % 4 == 0);
     /* the fast kernel covers whole 128-output passes; if the chunk is not a multiple of 128
@@ -529,7 +531,7 @@ static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned
      * segments keep the chip inside a compact window of memory (16 passes: 6.6 TB/s, 64: 6.4);
      * with it the kernel is pipe-bound and longer segments amortise the drain pass (64: 5.6 TB/s,
      * 16: 5.4) */
-    unsigned ips = c->nti ? 64u : 16u;
+    unsigned ips = (c->nti && !float_in) ? 64u : 16u; /* the float-input kernel is HBM-bound like the plain one */
     if (const char *e = getenv("FMD_IPS")) ips = (unsigned) atoi(e); /* tuning experiments only */
     if (ips < 1) ips = 1;
     while (ips > 4 && total_iters / ips < want_warps / 4) ips >>= 1;
@@ -591,14 +593,11 @@ extern "C" int fmd_demod_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, 
         else {
             const float *sbuf = nullptr;
             rc = fmq1_condition(c, d_in, nfull, s, &sbuf);
-            if (!rc) {
-                FmdGeom g;
-                memset(&g, 0, sizeof g);
-                g.chunk_stride = B * sizeof(float);
-                g.chunk_out = (unsigned) (B >> 2);
-                g.nchunks = (unsigned) nfull;
-                rc = launch_exact(c, reinterpret_cast<const uint8_t *>(sbuf), d_out, g, s);
-            }
+            /* the conditioned floats stream through the float-input kernel (chunk heads on its exact
+             * CTAs); designs it has no instantiation for fall back to the op-for-op path inside */
+            if (!rc)
+                rc = launch_chunks(c, reinterpret_cast<const uint8_t *>(sbuf), d_out, (unsigned) nfull, (unsigned) (B >> 2),
+                                   B * sizeof(float), s, true);
         }
     } else {
         rc = launch_chunks(c, d_in, d_out, (unsigned) nfull, (unsigned) (B >> 2), B, s);

@@ -14,13 +14,13 @@ for spec in "$@"; do
       -c -o $d/fmdemod.o demodulator_b200/csrc/fmdemod.cu &
   $NVCC -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC $flags -Iinclude -Idemodulator_b200/csrc \
       -c -o $d/fmd_quality_host.o demodulator_b200/csrc/fmd_quality_host.cu &
-  for grp in 0 1 2 3; do
+  for grp in 0 1 2 3 4; do
     $NVCC -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC $flags -DFMD_INST_GROUP=$grp -Iinclude -Idemodulator_b200/csrc \
         -c -o $d/fmd_fast_inst$grp.o demodulator_b200/csrc/fmd_fast_inst.cu &
   done
   wait
   $NVCC -gencode arch=compute_100a,code=sm_100a -shared -Xlinker --no-undefined -o $d/libfmdemod.so $d/fmdemod.o $d/fmd_fast_inst0.o $d/fmd_fast_inst1.o \
-      $d/fmd_fast_inst2.o $d/fmd_fast_inst3.o $d/fmd_quality_host.o $d/fmd_design.o $d/fmd_quality.o -lm
+      $d/fmd_fast_inst2.o $d/fmd_fast_inst3.o $d/fmd_fast_inst4.o $d/fmd_quality_host.o $d/fmd_design.o $d/fmd_quality.o -lm
   rm -f $d/*.o
   echo "built $d ($flags)"
 done
