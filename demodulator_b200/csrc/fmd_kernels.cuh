@@ -522,6 +522,10 @@ __device__ __forceinline__ bool fmd_elect_one() {
     return pred != 0u;
 }
 
+#ifndef FMD_EARLY_LDS
+#define FMD_EARLY_LDS 0 /* 1: (halo kernels) read a pass's raw words from the ring one pass early, so that its
+                           unpacking may be scheduled into the previous pass's polynomial */
+#endif
 #ifndef FMD_TMA
 #define FMD_TMA 0 /* 1: bulk-copy (TMA) ring with mbarriers; 0: per-lane cp.async ring */
 #endif
@@ -622,9 +626,12 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
     constexpr bool CARRY = FmdCarry<NTI, COND>::value;
     constexpr int HWORDS = NTI > 1 ? NTI / 2 : 0; /* halo words: (NTI - 1 + 1) / 2 */
     uint32_t w0c = 0u;
-    if (CARRY) { /* the first pass takes its biased first word from here, every later one from its predecessor */
+    constexpr bool EARLY = FMD_EARLY_LDS && HALO && !TMA;
+    uint4 rawc = fill; /* EARLY: the raw words of the pass about to run */
+    if (CARRY || EARLY) { /* the first pass takes its (biased) first word from here, every later one from its predecessor */
         if (!TMA) fmd_cp_wait<S - 2>();
-        w0c = fmd_bias_bytes(fmd_lds32(sbase));
+        if (EARLY) rawc = fmd_lds128(sbase);
+        w0c = fmd_bias_bytes(EARLY ? rawc.x : fmd_lds32(sbase));
     }
     /* the chunk head [0, head) belongs to the exact path: those lanes of the very first store
      * of a chunk's first segment keep quiet */
@@ -651,11 +658,18 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
             fmd_cp_commit();                                                                            \
             fmd_cp_wait<PENDING>();                                                                     \
         }                                                                                               \
-        const uint4 cur = fmd_lds128(sbase + (U) * SLOT);                                               \
+        uint4 cur;                                                                                      \
         uint2 nx = fill2;                                                                               \
-        if (HALO && HWORDS >= 2) nx = fmd_lds64(sbase + (((U) + 1) & (S - 1)) * SLOT);                  \
-        if (HALO && HWORDS < 2) nx.x = fmd_lds32(sbase + (((U) + 1) & (S - 1)) * SLOT);                 \
-        if (hz) nx = fill2;                                                                             \
+        if (EARLY) {                                                                                    \
+            cur = rawc; /* read from the ring during the previous pass */                               \
+            rawc = hz ? fill : fmd_lds128(sbase + (((U) + 1) & (S - 1)) * SLOT);                        \
+            nx = make_uint2(rawc.x, rawc.y);                                                            \
+        } else {                                                                                        \
+            cur = fmd_lds128(sbase + (U) * SLOT);                                                       \
+            if (HALO && HWORDS >= 2) nx = fmd_lds64(sbase + (((U) + 1) & (S - 1)) * SLOT);              \
+            if (HALO && HWORDS < 2) nx.x = fmd_lds32(sbase + (((U) + 1) & (S - 1)) * SLOT);             \
+            if (hz) nx = fill2;                                                                         \
+        }                                                                                               \
         fmd_pass<NTI, NTO, AT, false, COND>(cur, nx, XPREV, XCUR, false, dst + 128 * ((U) - 1), STP, lane, nxt_lane, st, w0c, hz); \
     }
 
@@ -696,9 +710,16 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
             fmd_cp_commit();
             fmd_cp_wait<PENDING>();
         }
-        const uint4 cur = fmd_lds128(sbase + (u & (S - 1)) * SLOT);
+        uint4 cur;
         uint2 nx = fill2;
-        if (HALO && p + 1 < n_ld) nx = fmd_lds64(sbase + ((u + 1) & (S - 1)) * SLOT);
+        if (EARLY) {
+            cur = rawc;
+            rawc = (p + 1 < n_ld) ? fmd_lds128(sbase + ((u + 1) & (S - 1)) * SLOT) : fill;
+            nx = make_uint2(rawc.x, rawc.y);
+        } else {
+            cur = fmd_lds128(sbase + (u & (S - 1)) * SLOT);
+            if (HALO && p + 1 < n_ld) nx = fmd_lds64(sbase + ((u + 1) & (S - 1)) * SLOT);
+        }
         fmd_pass<NTI, NTO, AT, false, COND>(cur, nx, x1, x0, false, dst + 128 * ((int) u - 1), p >= 2 || (p == 1 && head_keep),
                                      lane, nxt_lane, st, w0c, HALO && !(p + 1 < n_ld));
         x1[0] = x0[0]; x1[1] = x0[1]; x1[2] = x0[2]; x1[3] = x0[3];
@@ -714,7 +735,8 @@ fmd_fast_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const F
             fmd_cp_wait<PENDING>();
         }
         uint4 cur = fill;
-        if (p < n_ld) cur = fmd_lds128(sbase + (u & (S - 1)) * SLOT);
+        if (EARLY) cur = rawc;
+        else if (p < n_ld) cur = fmd_lds128(sbase + (u & (S - 1)) * SLOT);
         fmd_pass<NTI, NTO, AT, (NTO <= 2), COND>(cur, fill2, x1, x0, end_zero, dst + 128 * ((int) u - 1),
                                                  p >= 2 || (p == 1 && head_keep), lane, nxt_lane, st, w0c);
     }

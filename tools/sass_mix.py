@@ -50,3 +50,34 @@ for b in blocks:
     for g, names in groups.items():
         tot = sum(v for k, v in ops.items() if any(k == x or k.startswith(x + ".") for x in names))
         print(f"  {g}-pipe opcodes: {tot / unroll:.1f} per pass")
+
+# run lengths of same-pipe instructions in the loop (long ALU-only or FMA-only stretches are what
+# `math_pipe_throttle` is made of when several warps of a scheduler sit in the same stretch)
+def _runs():
+    alu = ("LOP3", "PRMT", "IADD3", "VIADD", "FMNMX", "FMNMX3", "FSETP", "ISETP", "SEL", "MOV", "IMAD.MOV", "LEA", "SHF")
+    fma = ("FFMA2", "FADD2", "FMUL2", "FFMA", "FADD", "FMUL", "IMAD", "HFMA2")
+    seq = []
+    for t in body:
+        t = re.sub(r"^@!?U?P\d+\s+", "", t)
+        op = t.split()[0]
+        if any(op == x or op.startswith(x + ".") for x in alu) and not op.startswith("IMAD.X"):
+            seq.append("A")
+        elif any(op == x or op.startswith(x + ".") for x in fma):
+            seq.append("F")
+    runs, cur, n = [], None, 0
+    for c in seq:
+        if c == cur:
+            n += 1
+        else:
+            if cur:
+                runs.append((cur, n))
+            cur, n = c, 1
+    runs.append((cur, n))
+    for k in "AF":
+        r = [n for c, n in runs if c == k]
+        print(f"  {'ALU' if k == 'A' else 'FMA'}-pipe runs: {len(r)} per loop, mean {sum(r) / len(r):.1f}, max {max(r)}, "
+              f"instructions in runs of 8 or more: {sum(x for x in r if x >= 8)} of {sum(r)}")
+try:
+    _runs()
+except Exception as e:  # pragma: no cover
+    print("  (run-length analysis failed:", e, ")")
