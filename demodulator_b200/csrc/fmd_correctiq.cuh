@@ -15,8 +15,9 @@
  *   fmd_correctiq_kernel<true>    every thread starts from its scanned offsets and walks its steps
  *                                 with the reference's own float operations in the reference's order,
  *                                 writing the conditioned samples as floats
- * The conditioned floats (one per input byte, same layout) then go through the op-for-op path, whose
- * base lane reads them instead of shifting bytes (FmdShiftedLane, conditioner 1).
+ * The conditioned floats (one per input byte, same layout) then stream through fmd_fastf_kernel, the
+ * float-input instantiation of the streaming pass (fmd_kernels.cuh); its exact CTAs -- chunk heads --
+ * read the same floats through FmdShiftedLane (conditioner 1).
  *
  * Not bit-exact: the scan associates the additions differently from the serial float32 loop, and the
  * recurrence contracts (factor 1 - 2 esr per step), so the offsets agree to about 1e-4 of ~127 and
@@ -52,13 +53,33 @@ fmd_correctiq_kernel(const uint8_t *__restrict__ in, float *__restrict__ sbuf, c
     const unsigned short *__restrict__ front = reinterpret_cast<const unsigned short *>(cin) + k0;
     const unsigned short *__restrict__ back = reinterpret_cast<const unsigned short *>(cin) + (nc - 1u - k0);
 
+    /* Steps are read eight at a time: one 16-byte load of the front run (complex k0+8g .. +7) and
+     * one of the back run (complex nc-8-k0-8g .. +7, i.e. step j of the group is its sample 7-j);
+     * round 1 read every sample with a 2-byte load (128 loads per thread and kernel instead of 16). */
+#define FMQ1_W(v, i) ((i) < 2 ? (v).x : (i) < 4 ? (v).y : (i) < 6 ? (v).z : (v).w)
+#define FMQ1_I(v, i) ((FMQ1_W(v, i) >> (16 * ((i) & 1))) & 0xffu)
+#define FMQ1_Q(v, i) ((FMQ1_W(v, i) >> (16 * ((i) & 1) + 8)) & 0xffu)
+    const uint4 *__restrict__ front4 = reinterpret_cast<const uint4 *>(front);
+    const uint4 *__restrict__ back4 = reinterpret_cast<const uint4 *>(back - 7);
     /* end value of the offsets after this thread's steps, from zero */
     float v[2][1] = {{0.0f}, {0.0f}};
+    if (cnt == FMQ_T) {
+#pragma unroll 2
+        for (unsigned gq = 0; gq < FMQ_T / 8; ++gq) {
+            const uint4 f = __ldg(front4 + gq), b = __ldg(back4 - (int) gq);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[0][0] = fmaf(g.a, v[0][0], g.esr * (float) (FMQ1_I(f, j) + FMQ1_I(b, 7 - j)));
+                v[1][0] = fmaf(g.a, v[1][0], g.esr * (float) (FMQ1_Q(f, j) + FMQ1_Q(b, 7 - j)));
+            }
+        }
+    } else {
 #pragma unroll 4
-    for (unsigned k = 0; k < cnt; ++k) {
-        const unsigned f = front[k], b = back[-(int) k];
-        v[0][0] = fmaf(g.a, v[0][0], g.esr * (float) ((f & 0xffu) + (b & 0xffu)));
-        v[1][0] = fmaf(g.a, v[1][0], g.esr * (float) ((f >> 8) + (b >> 8)));
+        for (unsigned k = 0; k < cnt; ++k) {
+            const unsigned f = front[k], b = back[-(int) k];
+            v[0][0] = fmaf(g.a, v[0][0], g.esr * (float) ((f & 0xffu) + (b & 0xffu)));
+            v[1][0] = fmaf(g.a, v[1][0], g.esr * (float) ((f >> 8) + (b >> 8)));
+        }
     }
     const float e0 = v[0][0], e1 = v[1][0];
     float carry[2][1] = {{0.0f}, {0.0f}};
@@ -81,22 +102,31 @@ fmd_correctiq_kernel(const uint8_t *__restrict__ in, float *__restrict__ sbuf, c
     float4 *__restrict__ sf = reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(sbuf + chunk * g.chunk_bytes) + k0);
     float4 *__restrict__ sb =
         reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(sbuf + chunk * g.chunk_bytes) + (nc - 2u - k0));
-#pragma unroll 4
-    for (unsigned k = 0; k + 1 < cnt; k += 2) {
-        float fi[2], fq[2], bi[2], bq[2];
+    if (cnt == FMQ_T) {
+#pragma unroll 1
+        for (unsigned gq = 0; gq < FMQ_T / 8; ++gq) {
+            const uint4 f = __ldg(front4 + gq), b = __ldg(back4 - (int) gq);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const unsigned f = front[k + j], b = back[-(int) (k + j)];
-            fi[j] = __fsub_rn((float) (f & 0xffu), off0);
-            bi[j] = __fsub_rn((float) (b & 0xffu), off0);
-            fq[j] = __fsub_rn((float) (f >> 8), off1);
-            bq[j] = __fsub_rn((float) (b >> 8), off1);
-            off0 = __fadd_rn(off0, __fmul_rn(__fadd_rn(fi[j], bi[j]), g.esr));
-            off1 = __fadd_rn(off1, __fmul_rn(__fadd_rn(fq[j], bq[j]), g.esr));
+            for (int j = 0; j < 8; j += 2) {
+                float fi[2], fq[2], bi[2], bq[2];
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    fi[t] = __fsub_rn((float) FMQ1_I(f, j + t), off0);
+                    bi[t] = __fsub_rn((float) FMQ1_I(b, 7 - (j + t)), off0);
+                    fq[t] = __fsub_rn((float) FMQ1_Q(f, j + t), off1);
+                    bq[t] = __fsub_rn((float) FMQ1_Q(b, 7 - (j + t)), off1);
+                    off0 = __fadd_rn(off0, __fmul_rn(__fadd_rn(fi[t], bi[t]), g.esr));
+                    off1 = __fadd_rn(off1, __fmul_rn(__fadd_rn(fq[t], bq[t]), g.esr));
+                }
+                const unsigned k = 8u * gq + (unsigned) j;
+                sf[k >> 1] = make_float4(fi[0], fq[0], fi[1], fq[1]);
+                sb[-(int) (k >> 1)] = make_float4(bi[1], bq[1], bi[0], bq[0]); /* complex nc-2-k0-k, then nc-1-k0-k */
+            }
         }
-        sf[k >> 1] = make_float4(fi[0], fq[0], fi[1], fq[1]);
-        sb[-(int) (k >> 1)] = make_float4(bi[1], bq[1], bi[0], bq[0]); /* complex nc-2-k0-k, then nc-1-k0-k */
     }
+#undef FMQ1_W
+#undef FMQ1_I
+#undef FMQ1_Q
 }
 
 #endif /* FMD_CORRECTIQ_CUH */

@@ -21,6 +21,22 @@
                                  __FILE__, __LINE__);                                               \
     } while (0)
 
+/* Every entry point works on its context's device and leaves the calling thread's current device
+ * as it found it (a host that drives several GPUs from one thread must not be surprised). */
+struct FmdDeviceScope {
+    int prev = -1;
+    bool switched = false;
+    explicit FmdDeviceScope(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~FmdDeviceScope() {
+        if (switched && prev >= 0) cudaSetDevice(prev);
+    }
+    FmdDeviceScope(const FmdDeviceScope &) = delete;
+    FmdDeviceScope &operator=(const FmdDeviceScope &) = delete;
+};
+
 struct fmd_slot {
     uint8_t *d_in = nullptr;
     float *d_out = nullptr;

@@ -294,7 +294,7 @@ int fmq_demod_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, float *d_ou
 }
 
 int fmq_reset(fmd_ctx *c) {
-    FMD_CUDA(cudaSetDevice(c->device));
+    FmdDeviceScope on_device(c->device);
     FMD_CUDA(cudaDeviceSynchronize());
     FMD_CUDA(cudaMemset(c->q->d_state, 0, sizeof(FmqState)));
     c->q->pos = 0;
@@ -416,7 +416,7 @@ void fmq1_free(fmd_ctx *c) {
 }
 
 int fmq1_reset(fmd_ctx *c) {
-    FMD_CUDA(cudaSetDevice(c->device));
+    FmdDeviceScope on_device(c->device);
     FMD_CUDA(cudaDeviceSynchronize());
     FMD_CUDA(cudaMemset(c->q1->d_off, 0, 2 * sizeof(float)));
     return FMD_OK;

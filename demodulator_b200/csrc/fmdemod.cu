@@ -63,6 +63,7 @@ int fmd_prof_events(fmd_ctx *c, cudaEvent_t **pe) {
 
 extern "C" int fmd_profile_kernels(fmd_ctx *c, int enable) {
     if (!c) return fmd_set_error(FMD_EINVAL, "null argument");
+    FmdDeviceScope on_device(c->device); /* events belong to the device they are created on */
     if (enable && !c->pev) {
         c->pev_cap = 256;
         c->pev = new (std::nothrow) cudaEvent_t[2 * c->pev_cap];
@@ -201,7 +202,7 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
         return fmd_set_error(FMD_ENODEV, "no CUDA device: %s (this library has no CPU path)",
                              e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
     if (device < 0 || device >= ndev) return fmd_set_error(FMD_EINVAL, "device %d not in 0..%d", device, ndev - 1);
-    FMD_CUDA(cudaSetDevice(device));
+    FmdDeviceScope on_device(device);
     cudaDeviceProp prop;
     FMD_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10)
@@ -390,7 +391,7 @@ static void fmd_ring_free(fmd_ctx *c) {
 
 extern "C" void fmd_destroy(fmd_ctx *c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    FmdDeviceScope on_device(c->device);
     fmd_ring_free(c);
     if (c->pev) {
         for (unsigned i = 0; i < 2 * c->pev_cap; ++i) cudaEventDestroy(c->pev[i]);
@@ -588,6 +589,8 @@ extern "C" int fmd_demod_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, 
          * continues the stream; condition them, then the op-for-op path on the conditioned floats */
         if (rem || nbytes != nfull * B)
             rc = fmd_set_error(FMD_EINVAL, "-q1 takes whole chunks (%llu bytes each)", B);
+        else if (((uintptr_t) d_in % 16) || ((uintptr_t) d_out % 16))
+            rc = fmd_set_error(FMD_EINVAL, "-q1 needs 16-byte aligned device buffers");
         else if (!nfull)
             rc = FMD_OK;
         else {
@@ -638,7 +641,7 @@ extern "C" int fmd_ring_create(fmd_ctx *c, unsigned slots, size_t slot_bytes) {
     if (!c || slots == 0 || slots > 64 || slot_bytes == 0) return fmd_set_error(FMD_EINVAL, "bad ring geometry");
     if (slot_bytes % c->cfg.chunk_bytes)
         return fmd_set_error(FMD_EINVAL, "slot_bytes must be a multiple of chunk_bytes");
-    FMD_CUDA(cudaSetDevice(c->device));
+    FmdDeviceScope on_device(c->device);
     fmd_ring_free(c);
     c->slots = new (std::nothrow) fmd_slot[slots];
     if (!c->slots) return fmd_set_error(FMD_ENOMEM, "out of host memory");
@@ -667,7 +670,7 @@ static int submit_slot(fmd_ctx *c, unsigned slot, const uint8_t *in, size_t nbyt
     if (nbytes > c->slot_bytes) return fmd_set_error(FMD_EINVAL, "nbytes exceeds slot_bytes");
     fmd_slot &s = c->slots[slot];
     if (s.busy) return fmd_set_error(FMD_EBUSY, "slot %u still in flight: call fmd_wait first", slot);
-    FMD_CUDA(cudaSetDevice(c->device));
+    FmdDeviceScope on_device(c->device);
     const size_t nout = fmd_out_count(c, nbytes);
     /* the slot's device buffers are free: the previous occupant's D2H completed in fmd_wait */
     FMD_CUDA(cudaMemcpyAsync(s.d_in, in, nbytes, cudaMemcpyHostToDevice, c->s_in));
@@ -708,7 +711,7 @@ extern "C" int fmd_submit_segment(fmd_ctx *c, unsigned slot, const uint8_t *in, 
     if (warm_bytes + nbytes > c->slot_bytes) return fmd_set_error(FMD_EINVAL, "warm-up + payload exceed slot_bytes");
     fmd_slot &s = c->slots[slot];
     if (s.busy) return fmd_set_error(FMD_EBUSY, "slot %u still in flight: call fmd_wait first", slot);
-    FMD_CUDA(cudaSetDevice(c->device));
+    FmdDeviceScope on_device(c->device);
     const size_t out_elem = (c->cfg.flags & FMD_FLAG_S16) ? sizeof(short) : sizeof(float);
     const uint64_t seg_start = first_sample - warm_bytes / 2;
     const size_t n_warm = fmq_out_count_at(c, seg_start, warm_bytes / 2);
