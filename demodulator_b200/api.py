@@ -80,6 +80,8 @@ def load_library() -> C.CDLL:
     L.fmd_ring_create.argtypes = [vp, C.c_uint, C.c_size_t]
     L.fmd_submit.argtypes = [vp, C.c_uint, u8p, C.c_size_t, f32p]
     L.fmd_wait.argtypes = [vp, C.c_uint]
+    L.fmd_warmup_for_sections.argtypes = [f32p, C.c_uint]
+    L.fmd_warmup_for_sections.restype = C.c_uint64
     L.fmd_warmup_samples.argtypes = [vp]
     L.fmd_warmup_samples.restype = C.c_uint64
     L.fmd_segment_out_count.argtypes = [vp, C.c_uint64, C.c_size_t]
@@ -110,6 +112,12 @@ def design_sos(kind: int, degree: int, fc: float, fs: float, eps: float = 0.3) -
     sos = np.zeros((max(rows, 1), 6), np.float32)
     _check(load_library().fmd_design_sos(kind, degree, fc, fs, eps, sos.ctypes.data))
     return sos[:rows]
+
+
+def warmup_for_sections(sos: np.ndarray) -> int:
+    """fmd_warmup_for_sections: samples after which a cascade started from a zero state has converged"""
+    sos = np.ascontiguousarray(sos, np.float32)
+    return int(load_library().fmd_warmup_for_sections(sos.ctypes.data, sos.shape[0]))
 
 
 def fold_taps(sos: np.ndarray, bias: bool = True) -> tuple[np.ndarray, float]:

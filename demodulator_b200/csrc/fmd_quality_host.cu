@@ -319,21 +319,21 @@ size_t fmq_out_count_at(const fmd_ctx *c, unsigned long long pos, size_t nsamp) 
  * below the 1e-5 the pipeline is held to: the slowest pole radius rho of each cascade gives a decay
  * rho^n (times a polynomial in n for the cascade's nearly coinciding poles, hence the margin); the
  * output cascade only starts converging once the input cascade has, so the two lengths add. */
+extern "C" uint64_t fmd_warmup_for_sections(const float *sos6, unsigned rows) {
+    double rho = 0.0;
+    for (unsigned r = 0; sos6 && r < rows; ++r) {
+        const double a1 = sos6[6 * r + 4], a2 = sos6[6 * r + 5];
+        const double rr = a2 != 0.0 ? sqrt(fabs(a2)) : fabs(a1);
+        if (rr > rho) rho = rr;
+    }
+    if (!(rho > 0.0)) return 64u * rows;
+    if (rho >= 0.99999) rho = 0.99999;
+    return (uint64_t) ceil(1.5 * (log(1e-9) / log(rho)) + 64.0 * rows);
+}
+
 unsigned long long fmq_warmup_samples(const fmd_ctx *c) {
-    auto one = [](const float (*sos)[6], unsigned rows) -> double {
-        double rho = 0.0;
-        for (unsigned r = 0; r < rows; ++r) {
-            const double a1 = sos[r][4], a2 = sos[r][5];
-            const double rr = a2 != 0.0 ? sqrt(fabs(a2)) : fabs(a1);
-            if (rr > rho) rho = rr;
-        }
-        if (!(rho > 0.0)) return 64.0;
-        if (rho >= 0.99999) rho = 0.99999;
-        return 1.5 * (log(1e-9) / log(rho)) + 64.0 * rows;
-    };
-    double w = one(c->sec.out, c->lout);
-    if (c->lin) w += one(c->sec.in, c->lin);
-    unsigned long long n = (unsigned long long) ceil(w);
+    unsigned long long n = fmd_warmup_for_sections(&c->sec.out[0][0], c->lout);
+    if (c->lin) n += fmd_warmup_for_sections(&c->sec.in[0][0], c->lin);
     return (n + 7ull) & ~7ull; /* 16 bytes of IQ: the payload after it stays aligned */
 }
 

@@ -188,6 +188,9 @@ int fmd_wait(fmd_ctx *ctx, unsigned slot);
  *      converged to the running stream's to ~1e-9 (the length follows from the slowest pole). ----
  */
 uint64_t fmd_warmup_samples(const fmd_ctx *ctx);
+/* the same for one cascade given its section rows {b0,b1,b2,a0,a1,a2} (no context, no GPU needed):
+ * fmd_warmup_samples = the output cascade's + the input cascade's, rounded up to 8 samples */
+uint64_t fmd_warmup_for_sections(const float *sos6, unsigned rows);
 /* outputs of `nsamples` samples whose first has global index `first_sample` (decimation keeps the
  * samples whose GLOBAL index is a multiple of the factor) */
 size_t fmd_segment_out_count(const fmd_ctx *ctx, uint64_t first_sample, size_t nsamples);

@@ -128,3 +128,36 @@ def test_quality_configuration_is_validated_before_the_device():
     assert "degrees up to" in create(sampleRate=48000.0, inputRate=96000.0, outFilterDegree=7)
     assert "-q0" in create(sampleRate=48000.0, inputRate=96000.0, mode=12)
     assert "float32" in create(sampleRate=48000.0, inputRate=2.4e6, lowpassOut=100.0)
+
+
+@pytest.mark.parametrize("case", [dict(sig="cfg3", rate=2.4e6, fs=48000.0, fc_out=15000.0),
+                                  dict(sig="cfg2", rate=192e3, fs=96000.0, fc_out=6500.0, fc_in=12500.0),
+                                  dict(sig="cfg1", rate=192e3, fs=96000.0, fc_out=12500.0),
+                                  dict(sig="cfg3", rate=2.4e6, fs=48000.0, fc_out=14000.0, fc_in=30000.0, deg_out=5, deg_in=4, mode=1),
+                                  dict(sig="cfg2", rate=192e3, fs=192000.0, fc_out=400.0, deg_out=6)])
+def test_warm_up_prefix_replaces_the_carried_state(case, oracle_port):
+    """The multi-GPU split of a quality stream (fmd_submit_segment) starts a segment from a ZERO
+    state `warm-up` samples early and drops the prefix's outputs.  Here, without a GPU: the library's
+    warm-up length (fmd_warmup_for_sections, from the slowest pole) is enough for the serial
+    double-precision oracle restarted that early to agree with the one carried-state stream."""
+    from demodulator_b200 import api, synth
+    case = dict(case)
+    sig, rate = case.pop("sig"), case.pop("rate")
+    cfg = po.Config(**case)
+    M = int(round(rate / cfg.fs))
+    raw = synth.config_signal(sig, 24)
+    want = oracle_port.quality(cfg, rate).run(raw)
+    W = api.warmup_for_sections(api.design_sos(cfg.mode & 1, cfg.deg_out, cfg.fc_out, rate, cfg.eps))
+    if cfg.fc_in:
+        # -L without -D inherits the output degree (src/matrix.c:190-192)
+        W += api.warmup_for_sections(api.design_sos((cfg.mode >> 1) & 1, cfg.deg_in or cfg.deg_out, cfg.fc_in, rate, cfg.eps))
+    n = raw.size // 2
+    assert 0 < W < n // 4
+    g0 = (n // 2) // M * M          # payload start
+    seg_start = (g0 - W) // M * M   # a multiple of M: a fresh oracle stream then has the stream's decimation phase
+    seg = oracle_port.quality(cfg, rate).run(raw[2 * seg_start:])
+    got, ref = seg[(g0 - seg_start) // M:], want[g0 // M:]
+    assert got.size == ref.size
+    cold = oracle_port.quality(cfg, rate).run(raw[2 * g0:])[: 2000 // M + 8]
+    assert float(np.abs(got - ref).max()) <= 1e-8, (W, float(np.abs(got - ref).max()))
+    assert float(np.abs(cold - ref[: cold.size]).max()) > 1e-4  # without the prefix the start is visibly wrong
