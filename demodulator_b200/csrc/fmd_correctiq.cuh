@@ -9,7 +9,7 @@
  *     off' = (1 - 2 esr) off + esr (u_front + u_back)
  * over all steps of the stream, i.e. a scan with a constant scalar "matrix" -- the D = 1 case of the
  * machinery of fmd_quality.h:
- *   fmd_correctiq_kernel<false>   per tile (256 threads x FMQ_T steps) the offsets' end value from zero
+ *   fmd_correctiq_kernel<false>   per tile (256 threads x FMQ1_T steps) the offsets' end value from zero
  *   fmq_scan_tiles_kernel<1, 2>   the offsets at the start of every tile; carry in from the previous
  *                                 call, carry out for the next
  *   fmd_correctiq_kernel<true>    every thread starts from its scanned offsets and walks its steps
@@ -28,6 +28,14 @@
 
 #include "fmd_quality.cuh"
 
+/* Steps per thread.  The quality pipeline gives a thread 64 consecutive samples (its arithmetic is
+ * heavy, the scan light); here a step is six instructions, so the memory pattern decides: with 8
+ * steps per thread a warp reads 512 contiguous bytes from each end and writes 2 KiB of conditioned
+ * floats to each end per instruction group, where 64 steps per thread left every lane walking its
+ * own 512-byte stream (32 DRAM pages per store instruction: 65 GS/s for the whole -q1 pipeline). */
+#define FMQ1_T 8
+#define FMQ1_TILE (FMQ1_T * FMQ_THREADS) /* steps per CTA: 2048 */
+
 struct FmdQ1Geom {
     unsigned long long nsteps;      /* steps in this call: nchunks * steps_per_chunk           */
     unsigned long long chunk_bytes; /* B: bytes per chunk (= floats per chunk of the output)   */
@@ -42,10 +50,10 @@ fmd_correctiq_kernel(const uint8_t *__restrict__ in, float *__restrict__ sbuf, c
                      const float *__restrict__ q_tile /* [ntiles][2], APPLY only */,
                      float *__restrict__ e_tile /* [ntiles][2], !APPLY only */) {
     __shared__ float tot[FMQ_WARPS * 2];
-    const unsigned long long first = ((unsigned long long) blockIdx.x * FMQ_THREADS + threadIdx.x) * FMQ_T;
-    const unsigned cnt = first >= g.nsteps ? 0u : (unsigned) min((unsigned long long) FMQ_T, g.nsteps - first);
-    const bool last = cnt != 0u && (threadIdx.x == FMQ_THREADS - 1 || first + FMQ_T >= g.nsteps);
-    /* FMQ_T divides steps_per_chunk (the host checks): a thread's steps lie in one chunk */
+    const unsigned long long first = ((unsigned long long) blockIdx.x * FMQ_THREADS + threadIdx.x) * FMQ1_T;
+    const unsigned cnt = first >= g.nsteps ? 0u : (unsigned) min((unsigned long long) FMQ1_T, g.nsteps - first);
+    const bool last = cnt != 0u && (threadIdx.x == FMQ_THREADS - 1 || first + FMQ1_T >= g.nsteps);
+    /* FMQ1_T divides steps_per_chunk (the host checks): a thread's steps lie in one chunk */
     const unsigned long long chunk = first / g.steps_per_chunk;
     const unsigned k0 = (unsigned) (first - chunk * g.steps_per_chunk);
     const unsigned nc = 2u * g.steps_per_chunk;
@@ -53,9 +61,8 @@ fmd_correctiq_kernel(const uint8_t *__restrict__ in, float *__restrict__ sbuf, c
     const unsigned short *__restrict__ front = reinterpret_cast<const unsigned short *>(cin) + k0;
     const unsigned short *__restrict__ back = reinterpret_cast<const unsigned short *>(cin) + (nc - 1u - k0);
 
-    /* Steps are read eight at a time: one 16-byte load of the front run (complex k0+8g .. +7) and
-     * one of the back run (complex nc-8-k0-8g .. +7, i.e. step j of the group is its sample 7-j);
-     * round 1 read every sample with a 2-byte load (128 loads per thread and kernel instead of 16). */
+    /* A thread's eight steps are one 16-byte load of the front run (complex k0 .. k0+7) and one of
+     * the back run (complex nc-8-k0 .. +7, i.e. step j is its sample 7-j). */
 #define FMQ1_W(v, i) ((i) < 2 ? (v).x : (i) < 4 ? (v).y : (i) < 6 ? (v).z : (v).w)
 #define FMQ1_I(v, i) ((FMQ1_W(v, i) >> (16 * ((i) & 1))) & 0xffu)
 #define FMQ1_Q(v, i) ((FMQ1_W(v, i) >> (16 * ((i) & 1) + 8)) & 0xffu)
@@ -63,15 +70,15 @@ fmd_correctiq_kernel(const uint8_t *__restrict__ in, float *__restrict__ sbuf, c
     const uint4 *__restrict__ back4 = reinterpret_cast<const uint4 *>(back - 7);
     /* end value of the offsets after this thread's steps, from zero */
     float v[2][1] = {{0.0f}, {0.0f}};
-    if (cnt == FMQ_T) {
-#pragma unroll 2
-        for (unsigned gq = 0; gq < FMQ_T / 8; ++gq) {
-            const uint4 f = __ldg(front4 + gq), b = __ldg(back4 - (int) gq);
+    static_assert(FMQ1_T == 8, "one 16-byte load per end and thread");
+    uint4 f = make_uint4(0u, 0u, 0u, 0u), b = f;
+    if (cnt == FMQ1_T) {
+        f = __ldg(front4);
+        b = __ldg(back4);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                v[0][0] = fmaf(g.a, v[0][0], g.esr * (float) (FMQ1_I(f, j) + FMQ1_I(b, 7 - j)));
-                v[1][0] = fmaf(g.a, v[1][0], g.esr * (float) (FMQ1_Q(f, j) + FMQ1_Q(b, 7 - j)));
-            }
+        for (int j = 0; j < 8; ++j) {
+            v[0][0] = fmaf(g.a, v[0][0], g.esr * (float) (FMQ1_I(f, j) + FMQ1_I(b, 7 - j)));
+            v[1][0] = fmaf(g.a, v[1][0], g.esr * (float) (FMQ1_Q(f, j) + FMQ1_Q(b, 7 - j)));
         }
     } else {
 #pragma unroll 4
@@ -98,14 +105,12 @@ fmd_correctiq_kernel(const uint8_t *__restrict__ in, float *__restrict__ sbuf, c
     }
     /* the reference's loop body, operation for operation (matrix.c:129-138) */
     float off0 = v[0][0], off1 = v[1][0];
-    /* FMQ_T divides the steps of a chunk, so cnt is 0 or FMQ_T: steps go in pairs, 16 bytes per store */
+    /* FMQ1_T divides the steps of a chunk, so cnt is 0 or FMQ1_T: steps go in pairs, 16 bytes per store */
     float4 *__restrict__ sf = reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(sbuf + chunk * g.chunk_bytes) + k0);
     float4 *__restrict__ sb =
         reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(sbuf + chunk * g.chunk_bytes) + (nc - 2u - k0));
-    if (cnt == FMQ_T) {
-#pragma unroll 1
-        for (unsigned gq = 0; gq < FMQ_T / 8; ++gq) {
-            const uint4 f = __ldg(front4 + gq), b = __ldg(back4 - (int) gq);
+    if (cnt == FMQ1_T) {
+        {
 #pragma unroll
             for (int j = 0; j < 8; j += 2) {
                 float fi[2], fq[2], bi[2], bq[2];
@@ -118,7 +123,7 @@ fmd_correctiq_kernel(const uint8_t *__restrict__ in, float *__restrict__ sbuf, c
                     off0 = __fadd_rn(off0, __fmul_rn(__fadd_rn(fi[t], bi[t]), g.esr));
                     off1 = __fadd_rn(off1, __fmul_rn(__fadd_rn(fq[t], bq[t]), g.esr));
                 }
-                const unsigned k = 8u * gq + (unsigned) j;
+                const unsigned k = (unsigned) j;
                 sf[k >> 1] = make_float4(fi[0], fq[0], fi[1], fq[1]);
                 sb[-(int) (k >> 1)] = make_float4(bi[1], bq[1], bi[0], bq[0]); /* complex nc-2-k0-k, then nc-1-k0-k */
             }

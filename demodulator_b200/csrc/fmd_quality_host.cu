@@ -386,13 +386,13 @@ int fmq1_setup(fmd_ctx *c) {
     q->des.D = 1;
     q->des.A[0][0] = (long double) a;
     q->des.C[0] = 1.0L;
-    fmq_build_consts(&q->des, FMQ_T, FMQ_TILE, &q->c);
-    fmq_build_consts(&q->des, FMQ_TILE, FMQ_TILE, &q->c_tile);
-    fmq_table_layout(&q->des, FMQ_T, &q->sz);
+    fmq_build_consts(&q->des, FMQ1_T, FMQ1_TILE, &q->c);
+    fmq_build_consts(&q->des, FMQ1_TILE, FMQ1_TILE, &q->c_tile);
+    fmq_table_layout(&q->des, FMQ1_T, &q->sz);
     const size_t n = (size_t) q->sz.lane + q->sz.apow + q->sz.ck + q->sz.ckn + q->sz.lane_tile;
     float *h = (float *) malloc(n * sizeof(float));
     if (!h) return fmd_set_error(FMD_ENOMEM, "out of host memory");
-    fmq_build_tables(&q->des, FMQ_T, h, h + q->sz.lane, h + q->sz.lane + q->sz.apow, h + q->sz.lane + q->sz.apow + q->sz.ck,
+    fmq_build_tables(&q->des, FMQ1_T, h, h + q->sz.lane, h + q->sz.lane + q->sz.apow, h + q->sz.lane + q->sz.apow + q->sz.ck,
                      h + q->sz.lane + q->sz.apow + q->sz.ck + q->sz.ckn);
     cudaError_t e = cudaMalloc(&q->d_tab, n * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(q->d_tab, h, n * sizeof(float), cudaMemcpyHostToDevice);
@@ -431,7 +431,7 @@ int fmq1_condition(fmd_ctx *c, const uint8_t *d_in, unsigned long long nchunks, 
     g.nsteps = nchunks * g.steps_per_chunk;
     g.esr = q->esr;
     g.a = q->a;
-    const unsigned long long ntiles64 = (g.nsteps + FMQ_TILE - 1) / FMQ_TILE;
+    const unsigned long long ntiles64 = (g.nsteps + FMQ1_TILE - 1) / FMQ1_TILE;
     if (ntiles64 > 0x7fffffffull) return fmd_set_error(FMD_EINVAL, "too many chunks in one -q1 call");
     const unsigned ntiles = (unsigned) ntiles64;
     if (ntiles > q->tile_cap) {
@@ -456,11 +456,11 @@ int fmq1_condition(fmd_ctx *c, const uint8_t *d_in, unsigned long long nchunks, 
     const float *lane_tile = q->d_tab + q->sz.lane + q->sz.apow + q->sz.ck + q->sz.ckn;
     const unsigned nwarps = FMQ_SCAN_THREADS / 32;
     const unsigned runlen = ((ntiles + nwarps - 1u) / nwarps + 31u) & ~31u;
-    const unsigned long long len_last = g.nsteps - (unsigned long long) (ntiles - 1u) * FMQ_TILE;
+    const unsigned long long len_last = g.nsteps - (unsigned long long) (ntiles - 1u) * FMQ1_TILE;
     FmqMat prun, pl;
     memset(&prun, 0, sizeof prun);
     memset(&pl, 0, sizeof pl);
-    fmq_matpow_f(&q->des, (unsigned long long) FMQ_TILE * runlen, prun.m);
+    fmq_matpow_f(&q->des, (unsigned long long) FMQ1_TILE * runlen, prun.m);
     fmq_matpow_f(&q->des, len_last, pl.m);
     fmd_correctiq_kernel<false><<<ntiles, FMQ_THREADS, 0, s>>>(d_in, nullptr, g, q->c, lane, apow, nullptr, q->d_e);
     fmq_scan_tiles_kernel<1, 2><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_e, q->d_q, q->d_off, q->c_tile, lane_tile, prun, pl, ntiles,

@@ -187,8 +187,8 @@ extern "C" int fmd_create(const fmd_config *cfg_in, int device, fmd_ctx **out) {
                                  "quality mode keeps the filter state in float32: cut-offs must lie in "
                                  "[input_rate/1000, input_rate/2)");
     }
-    if (conditioner == 1u && (quality || (cfg.chunk_bytes % (4u * FMQ_T)) != 0))
-        return fmd_set_error(FMD_EINVAL, "-q1 (correctIq) needs chunks that are a multiple of %u bytes (and no -Q)", 4u * FMQ_T);
+    if (conditioner == 1u && (quality || (cfg.chunk_bytes % 32u) != 0)) /* 8 steps (4 bytes each) per thread, fmd_correctiq.cuh */
+        return fmd_set_error(FMD_EINVAL, "-q1 (correctIq) needs chunks that are a multiple of 32 bytes (and no -Q)");
     if (conditioner == 2u && cfg.chunk_bytes * sizeof(float) < (128u << 10))
         return fmd_set_error(FMD_EINVAL,
                              "-q2 with chunks under 32 KiB: the reference's highpassDc reads past a scratch buffer "
