@@ -778,8 +778,13 @@ static int host_pipeline(fmd_ctx *c, const uint8_t *in, size_t nbytes, float *ou
     if (slice == 0) slice = B;
     if (slice > nbytes) slice = (nbytes + B - 1) / B * B;
     if (slice == 0) slice = B;
-    if (c->nslots < 3 || c->slot_bytes < slice) {
-        int rc = fmd_ring_create(c, 3, slice);
+    unsigned want_slots = 3;
+    if (const char *e = getenv("FMD_HOST_SLOTS")) { /* tuning experiments */
+        const int v = atoi(e);
+        if (v >= 2 && v <= 16) want_slots = (unsigned) v;
+    }
+    if (c->nslots < want_slots || c->slot_bytes < slice) {
+        int rc = fmd_ring_create(c, want_slots, slice);
         if (rc) return rc;
     }
     const unsigned ns = c->nslots;
