@@ -40,4 +40,9 @@ for th in (4, 16):
 for p in (src, "/dev/shm/fmdout.f32"):
     if os.path.exists(p): os.unlink(p)
 PY
+# BASELINE configs[4] at full size: 16 G samples through stdin -> stdout, every output period checked
+{ timeout 600 python tools/cfg5_stream.py --gsamples ${CFG5_GS:-16} --devices all
+  timeout 600 python tools/cfg5_stream.py --gsamples ${CFG5_GS:-16} --devices 0
+  timeout 600 python tools/cfg5_stream.py --gsamples 4 --devices all --quality; } > $O/r02_cfg5_stream_n$N.txt 2>&1
+cat $O/r02_cfg5_stream_n$N.txt
 tail -5 $O/r02_pytest_multi_gpu.log; tail -2 $O/r02_bench_n$N.err; cut -c1-600 $O/r02_bench_n$N.json; cat $O/r02_cli_multi_n$N.txt
