@@ -36,7 +36,7 @@ PERIOD_CHUNKS = 64
 base = synth.config_signal("cfg3", PERIOD_CHUNKS)          # 16 MiB, 8 Mi samples
 n_periods = max(2, int(round(args.gsamples * 1e9 / (base.size // 2))))
 total_samples = n_periods * (base.size // 2)
-exe = os.path.join(ROOT, "demodulator_b200", "bin", "demodulator")
+exe = os.environ.get("FMD_CLI") or os.path.join(ROOT, "demodulator_b200", "bin", "demodulator")
 flags = ["-S48000", "-l15000"] + (["-Q", "-r2400000"] if args.quality else [])
 env = dict(os.environ, FMD_DEVICES=args.devices, FMD_STATS="1")
 p = subprocess.Popen([exe, "-i", "-", "-o", "-"] + flags, stdin=subprocess.PIPE, stdout=subprocess.PIPE,
