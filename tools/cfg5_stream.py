@@ -37,7 +37,8 @@ base = synth.config_signal("cfg3", PERIOD_CHUNKS)          # 16 MiB, 8 Mi sample
 n_periods = max(2, int(round(args.gsamples * 1e9 / (base.size // 2))))
 total_samples = n_periods * (base.size // 2)
 exe = os.environ.get("FMD_CLI") or os.path.join(ROOT, "demodulator_b200", "bin", "demodulator")
-flags = ["-S48000", "-l15000"] + (["-Q", "-r2400000"] if args.quality else [])
+# -Q: 2.4 MS/s -> 75 kS/s, M = 32 (a power of two, so that a signal period holds a whole number of outputs)
+flags = ["-Q", "-r2400000", "-S75000", "-l15000"] if args.quality else ["-S48000", "-l15000"]
 env = dict(os.environ, FMD_DEVICES=args.devices, FMD_STATS="1")
 p = subprocess.Popen([exe, "-i", "-", "-o", "-"] + flags, stdin=subprocess.PIPE, stdout=subprocess.PIPE,
                      stderr=subprocess.PIPE, env=env, bufsize=0)
@@ -61,7 +62,7 @@ def produce():
 t0 = time.time()
 th = threading.Thread(target=produce)
 th.start()
-M = 50 if args.quality else 1
+M = 32 if args.quality else 1
 per_out = base.size // 2 // M if args.quality else base.size // 4      # outputs per period
 per_bytes = per_out * 4
 first = None
@@ -95,7 +96,7 @@ p.wait()
 dt = time.time() - t0
 stats = p.stderr.read().decode().strip().splitlines()
 if args.quality:
-    want = po.port().quality(po.Config(fs=48000.0, fc_out=15000.0), 2.4e6).run(base)
+    want = po.port().quality(po.Config(fs=75000.0, fc_out=15000.0), 2.4e6).run(base)
     err0 = float(np.abs(first - want).max())
     ok = p.returncode == 0 and got_periods == n_periods and err0 <= 1e-4 and worst <= 1e-5
     print(f"cfg5 -Q stream: {total_samples / 1e9:.2f} G samples through stdin -> stdout on FMD_DEVICES={args.devices}: "
