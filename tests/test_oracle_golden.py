@@ -135,3 +135,71 @@ def test_reference_semantics_pinned(oracle_port):
     outL = P.run(raw, po.Config(fs=96000., fc_out=6500., fc_in=12500.)).reshape(2, -1)
     assert np.all(outL[:, 0] == 0.0) and np.all(outL[:, 1] == -2.0)
     assert np.abs(outL[:, 2:6]).max() > 5.0 and np.abs(outL[:, 6:]).max() < 3.2
+
+
+def _stencil_model(raw, cfg, to, dco, tin, dcq, shift):
+    """numpy statement of what the streaming kernel computes for one chunk: folded stencils with zero
+    extension past the chunk (float32 products and sums in float64 order-insensitive form)"""
+    s = shift(raw)
+    I, Q = s[0::2].astype(np.float64), s[1::2].astype(np.float64)
+    nc = I.size
+
+    def st(v, dc):
+        ve = np.concatenate([v, np.zeros(8)])
+        z = np.full(nc, float(dc))
+        for t, c in enumerate(tin):
+            z = z + float(c) * ve[t:t + nc]
+        return z
+    zi, zq = st(I, 0.0), st(Q, dcq)
+    a, b, c, d = zi[0::2], zq[0::2], zi[1::2], zq[1::2]
+    x = np.arctan2(-a * d + b * c, a * c + b * d)
+    xe = np.concatenate([x, np.zeros(8)])
+    y = np.full(x.size, float(dco))
+    for t, cc in enumerate(to):
+        y = y + float(cc) * xe[t:t + x.size]
+    return y
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_conditioners_under_the_input_filter_are_one_stencil(seed, oracle_port):
+    """What lets -q2 / -q3 stream under -L, checked without a GPU against
+    the oracle on random designs up to degree 8:
+      -q3: the normalised samples through the folded input stencil with the FLOAT 0.0 as the zero
+           extension past the chunk;
+      -q2: highpass and lowpass stencils composed into one (taps convolved, constants added) --
+           including the last outputs of the chunk, where the lowpass reads what the highpass sweep
+           spilled past its output region: with at most 3 lowpass taps it only reads the first two
+           spilled values, which are fully swept, i.e. what the composed stencil gives on zeros."""
+    import demodulator_b200.api as api
+    rng = np.random.default_rng(9000 + seed)
+    q = 2 + seed % 2
+    deg_out, deg_in = int(rng.integers(1, 9)), int(rng.integers(1, 9))
+    mode = int(rng.integers(0, 4)) | (q << 2)
+    fs = float(rng.choice([48000.0, 96000.0, 250000.0]))
+    fc_out, fc_in = float(rng.uniform(0.04, 0.4) * fs), float(rng.uniform(0.05, 0.4) * fs)
+    raw = synth.config_signal("cfg2", 1, seed=seed) if seed % 3 else rng.integers(0, 256, B, dtype=np.uint8)
+    cfg = po.Config(fs=fs, fc_in=fc_in, fc_out=fc_out, eps=0.2, deg_in=deg_in, deg_out=deg_out, mode=mode)
+    want = oracle_port.run(raw, cfg)
+    if not np.isfinite(want).all():
+        pytest.skip("design blows up in the reference too")
+    to, dco = api.fold_taps(api.design_sos(mode & 1, deg_out, fc_out, fs, 0.2), True)
+    sos_i = api.design_sos((mode >> 1) & 1, deg_in, fc_in, fs, 0.2)
+    ti, dci = api.fold_taps(sos_i, True)
+    _, dcq = api.fold_taps(sos_i, False)
+    assert dci == 0.0 and len(ti) <= 3
+    if q == 3:
+        y = _stencil_model(raw, cfg, to, dco, ti, dcq, oracle_port.normalize)
+    else:
+        sos_h = api.design_sos(2, 3, 1.0, fs, 0.0)  # matrix.c:151
+        hi, dhi = api.fold_taps(sos_h, True)
+        _, dhq = api.fold_taps(sos_h, False)
+        assert dhi == 0.0
+        comp = np.convolve(ti.astype(np.float64), hi.astype(np.float64))
+        y = _stencil_model(raw, cfg, to, dco, comp, float(dcq) + float(dhq) * float(ti.astype(np.float64).sum()),
+                           oracle_port.shift)
+    head = 16  # chunk heads are the exact path's (arena garbage with -L)
+    scale = max(1.0, float(np.abs(want[head:]).max()))
+    err = float(np.abs(y[head:] - want[head:]).max()) / scale
+    assert err <= 3e-5, (q, deg_in, deg_out, mode, err)
+    tail_err = float(np.abs(y[-16:] - want[-16:]).max()) / scale
+    assert tail_err <= 3e-5, ("chunk tail", q, deg_in, deg_out, tail_err)
