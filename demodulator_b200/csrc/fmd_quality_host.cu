@@ -13,6 +13,7 @@
 
 #include "fmd_ctx.h"
 #include "fmd_correctiq.cuh"
+#include "fmd_q1_fused.cuh"
 #include "fmd_quality.cuh"
 
 /* one cascade of the quality pipeline: host design + constants + device tables */
@@ -369,8 +370,11 @@ struct fmq1_ctx {
     float *d_off = nullptr; /* the two running offsets: the carry between calls */
     float *d_e = nullptr, *d_q = nullptr; /* per-tile end values / start values */
     unsigned tile_cap = 0;
-    float *d_sbuf = nullptr; /* conditioned samples of the current call */
+    float *d_sbuf = nullptr; /* conditioned samples of the current call (three-pass form) */
     size_t sbuf_cap = 0;
+    float2 *d_heads = nullptr; /* fused form: the conditioned first FMQ1_HEADS complex samples of every chunk */
+    size_t heads_cap = 0;      /* chunks */
+    bool fused_smem_set[4][6] = {};
     float esr = 0.f, a = 0.f;
 };
 
@@ -411,6 +415,7 @@ void fmq1_free(fmd_ctx *c) {
     if (q->d_e) cudaFree(q->d_e);
     if (q->d_q) cudaFree(q->d_q);
     if (q->d_sbuf) cudaFree(q->d_sbuf);
+    if (q->d_heads) cudaFree(q->d_heads);
     delete q;
     c->q1 = nullptr;
 }
@@ -422,7 +427,10 @@ int fmq1_reset(fmd_ctx *c) {
     return FMD_OK;
 }
 
-int fmq1_condition(fmd_ctx *c, const uint8_t *d_in, unsigned long long nchunks, cudaStream_t s, const float **sbuf) {
+/* the offsets at the start of every tile of this call (q->d_q): per-tile end values from zero, then
+ * the scan over the tiles with the carry of the previous call in and the next one's out */
+static int fmq1_scan(fmd_ctx *c, const uint8_t *d_in, unsigned long long nchunks, cudaStream_t s, FmdQ1Geom *gout,
+                     unsigned *ntiles_out) {
     fmq1_ctx *q = c->q1;
     const unsigned long long B = c->cfg.chunk_bytes;
     FmdQ1Geom g;
@@ -444,14 +452,6 @@ int fmq1_condition(fmd_ctx *c, const uint8_t *d_in, unsigned long long nchunks, 
         FMD_CUDA(cudaMalloc(&q->d_q, (size_t) cap * 2 * sizeof(float)));
         q->tile_cap = cap;
     }
-    const size_t need = (size_t) (nchunks * B); /* floats: one per input byte */
-    if (need > q->sbuf_cap) {
-        if (q->d_sbuf) cudaFree(q->d_sbuf);
-        q->d_sbuf = nullptr;
-        q->sbuf_cap = 0;
-        FMD_CUDA(cudaMalloc(&q->d_sbuf, need * sizeof(float)));
-        q->sbuf_cap = need;
-    }
     const float *lane = q->d_tab, *apow = q->d_tab + q->sz.lane;
     const float *lane_tile = q->d_tab + q->sz.lane + q->sz.apow + q->sz.ck + q->sz.ckn;
     const unsigned nwarps = FMQ_SCAN_THREADS / 32;
@@ -465,9 +465,104 @@ int fmq1_condition(fmd_ctx *c, const uint8_t *d_in, unsigned long long nchunks, 
     fmd_correctiq_kernel<false><<<ntiles, FMQ_THREADS, 0, s>>>(d_in, nullptr, g, q->c, lane, apow, nullptr, q->d_e);
     fmq_scan_tiles_kernel<1, 2><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_e, q->d_q, q->d_off, q->c_tile, lane_tile, prun, pl, ntiles,
                                                                 runlen, nullptr, nullptr);
+    FMD_CUDA(cudaGetLastError());
+    c->launches += 2;
+    *gout = g;
+    *ntiles_out = ntiles;
+    return FMD_OK;
+}
+
+/* three-pass form: conditioned floats (one per input byte) for the float-input streaming kernel */
+int fmq1_condition(fmd_ctx *c, const uint8_t *d_in, unsigned long long nchunks, cudaStream_t s, const float **sbuf) {
+    fmq1_ctx *q = c->q1;
+    const size_t need = (size_t) (nchunks * c->cfg.chunk_bytes); /* floats: one per input byte */
+    if (need > q->sbuf_cap) {
+        if (q->d_sbuf) cudaFree(q->d_sbuf);
+        q->d_sbuf = nullptr;
+        q->sbuf_cap = 0;
+        FMD_CUDA(cudaMalloc(&q->d_sbuf, need * sizeof(float)));
+        q->sbuf_cap = need;
+    }
+    FmdQ1Geom g;
+    unsigned ntiles = 0;
+    int rc = fmq1_scan(c, d_in, nchunks, s, &g, &ntiles);
+    if (rc) return rc;
+    const float *lane = q->d_tab, *apow = q->d_tab + q->sz.lane;
     fmd_correctiq_kernel<true><<<ntiles, FMQ_THREADS, 0, s>>>(d_in, q->d_sbuf, g, q->c, lane, apow, q->d_q, nullptr);
     FMD_CUDA(cudaGetLastError());
-    c->launches += 3;
+    c->launches += 1;
     *sbuf = q->d_sbuf;
+    return FMD_OK;
+}
+
+/* ---- fused form (fmd_q1_fused.cuh): conditioning and demodulation in one kernel ---- */
+typedef void (*fmq1_fused_fn)(const uint8_t *, float *, const FmdQ1Geom, const fmq_consts, const float *, const float *,
+                              const FmdStencil, const unsigned, float2 *);
+
+template <int NTI>
+static fmq1_fused_fn fmq1_pick_out(unsigned nto) {
+    switch (nto) {
+        case 1: return fmd_q1_fused_kernel<NTI, 1>;
+        case 2: return fmd_q1_fused_kernel<NTI, 2>;
+        case 3: return fmd_q1_fused_kernel<NTI, 3>;
+        case 4: return fmd_q1_fused_kernel<NTI, 4>;
+        case 5: return fmd_q1_fused_kernel<NTI, 5>;
+        default: return nullptr;
+    }
+}
+
+static fmq1_fused_fn fmq1_pick(unsigned nti, unsigned nto) {
+    switch (nti) {
+        case 0: return fmq1_pick_out<0>(nto);
+        case 1: return fmq1_pick_out<1>(nto);
+        case 2: return fmq1_pick_out<2>(nto);
+        case 3: return fmq1_pick_out<3>(nto);
+        default: return nullptr;
+    }
+}
+
+/* *done = false: this design / chunk size has no fused form (the caller takes the three-pass one).
+ * On success d_out holds every output except the chunk heads [0, c->head), and *heads the conditioned
+ * first FMQ1_HEADS complex samples of every chunk for the op-for-op path that produces those. */
+int fmq1_fused(fmd_ctx *c, const uint8_t *d_in, unsigned long long nchunks, float *d_out, cudaStream_t s,
+               const float **heads, unsigned *heads_stride_bytes, bool *done) {
+    fmq1_ctx *q = c->q1;
+    *done = false;
+    const unsigned long long B = c->cfg.chunk_bytes;
+    fmq1_fused_fn fn = fmq1_pick(c->nti, c->nto);
+    if (const char *e = getenv("FMD_Q1_FUSED")) {
+        if (!atoi(e)) fn = nullptr; /* audits: the three-pass form */
+    }
+    if (!fn || !c->fast_in_ok || (c->cfg.flags & FMD_FLAG_EXACT) || (B >> 2) % FMQ1_TILE != 0 || c->head > FMQ1_HEADS / 4u ||
+        nchunks > 0x7fffffffull)
+        return FMD_OK;
+    if (nchunks > q->heads_cap) {
+        if (q->d_heads) cudaFree(q->d_heads);
+        q->d_heads = nullptr;
+        q->heads_cap = 0;
+        const size_t cap = nchunks < 1024 ? 1024 : (size_t) nchunks;
+        FMD_CUDA(cudaMalloc(&q->d_heads, cap * FMQ1_HEADS * sizeof(float2)));
+        q->heads_cap = cap;
+    }
+    FmdQ1Geom g;
+    unsigned ntiles = 0;
+    int rc = fmq1_scan(c, d_in, nchunks, s, &g, &ntiles);
+    if (rc) return rc;
+    bool &opted = q->fused_smem_set[c->nti][c->nto];
+    if (!opted) { /* 49.5 KB of dynamic shared memory: past the 48 KB default */
+        FMD_CUDA(cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FMQ1_SMEM_BYTES));
+        opted = true;
+    }
+    cudaEvent_t *pe = nullptr;
+    rc = fmd_prof_events(c, &pe);
+    if (rc) return rc;
+    if (pe) FMD_CUDA(cudaEventRecord(pe[0], s));
+    fn<<<ntiles, FMQ_THREADS, FMQ1_SMEM_BYTES, s>>>(d_in, d_out, g, q->c, q->d_tab, q->d_q, c->st, c->head, q->d_heads);
+    FMD_CUDA(cudaGetLastError());
+    if (pe) FMD_CUDA(cudaEventRecord(pe[1], s));
+    c->launches += 1;
+    *heads = reinterpret_cast<const float *>(q->d_heads);
+    *heads_stride_bytes = FMQ1_HEADS * (unsigned) sizeof(float2);
+    *done = true;
     return FMD_OK;
 }

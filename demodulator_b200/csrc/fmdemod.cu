@@ -594,11 +594,31 @@ extern "C" int fmd_demod_device(fmd_ctx *c, const uint8_t *d_in, size_t nbytes, 
         else if (!nfull)
             rc = FMD_OK;
         else {
+            /* one kernel conditions and demodulates (fmd_q1_fused.cuh); the chunk heads then come from
+             * the op-for-op path over the conditioned head samples it left behind */
+            const float *heads = nullptr;
+            unsigned heads_stride = 0;
+            bool fused = false;
+            rc = fmq1_fused(c, d_in, nfull, d_out, s, &heads, &heads_stride, &fused);
+            if (!rc && fused && c->head) {
+                FmdGeom g;
+                memset(&g, 0, sizeof g);
+                g.chunk_stride = heads_stride;
+                g.chunk_out = (unsigned) (B >> 2);
+                g.nchunks = (unsigned) nfull;
+                g.fast_out = g.chunk_out;
+                g.head = c->head;
+                const unsigned long long nb = ((unsigned long long) g.nchunks * g.head + FMD_BLOCK - 1) / FMD_BLOCK;
+                g.exact_blocks = (unsigned) nb;
+                fmd_exact_kernel<<<(unsigned) nb, FMD_BLOCK, 0, s>>>(reinterpret_cast<const uint8_t *>(heads), d_out, g, c->d_sec);
+                if (cudaGetLastError() != cudaSuccess) rc = fmd_set_error(FMD_ECUDA, "head kernel launch failed");
+                c->launches++;
+            }
             const float *sbuf = nullptr;
-            rc = fmq1_condition(c, d_in, nfull, s, &sbuf);
+            if (!rc && !fused) rc = fmq1_condition(c, d_in, nfull, s, &sbuf);
             /* the conditioned floats stream through the float-input kernel (chunk heads on its exact
              * CTAs); designs it has no instantiation for fall back to the op-for-op path inside */
-            if (!rc)
+            if (!rc && !fused)
                 rc = launch_chunks(c, reinterpret_cast<const uint8_t *>(sbuf), d_out, (unsigned) nfull, (unsigned) (B >> 2),
                                    B * sizeof(float), s, true);
         }
