@@ -15,9 +15,12 @@ ROWS = (("-q2 -S96000 -l12500", 1 << 30, dict(sampleRate=96000.0, lowpassOut=125
         ("-q2 -S96000 -L12500 -l6500", 1 << 30, dict(sampleRate=96000.0, lowpassOut=6500.0, lowpassIn=12500.0, mode=8)),
         ("-q3 -S96000 -l12500", 1 << 30, dict(sampleRate=96000.0, lowpassOut=12500.0, mode=12)),
         ("-q3 -S96000 -L12500 -l6500", 1 << 30, dict(sampleRate=96000.0, lowpassOut=6500.0, lowpassIn=12500.0, mode=12)),
-        ("-q1 -S96000 -l12500", 256 << 20, dict(sampleRate=96000.0, lowpassOut=12500.0, mode=4)),
-        ("-q1 -S96000 -L12500 -l6500", 64 << 20, dict(sampleRate=96000.0, lowpassOut=6500.0, lowpassIn=12500.0, mode=4)))
+        ("-q1 -S96000 -l12500", 1 << 30, dict(sampleRate=96000.0, lowpassOut=12500.0, mode=4)),
+        ("-q1 -S96000 -L12500 -l6500", 1 << 30, dict(sampleRate=96000.0, lowpassOut=6500.0, lowpassIn=12500.0, mode=4)))
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ""
 for what, nbytes, kw in ROWS:
+    if ONLY and not what.startswith(ONLY):
+        continue
     d_in = torch.from_numpy(base).cuda().repeat((nbytes + base.size - 1) // base.size)[:nbytes].contiguous()
     d_out = torch.empty(nbytes // 4, dtype=torch.float32, device="cuda")
     with fm.Demodulator(**kw) as d:
