@@ -108,7 +108,6 @@ int fmq1_reset(fmd_ctx *c);
 /* conditions `nchunks` whole chunks (continuing the stream) into floats, one per input byte; *sbuf is
  * owned by the context and valid until the next call on it */
 int fmq1_condition(fmd_ctx *c, const uint8_t *d_in, unsigned long long nchunks, cudaStream_t s, const float **sbuf);
-int fmq1_check_error(fmd_ctx *c);
 int fmq1_fused(fmd_ctx *c, const uint8_t *d_in, unsigned long long nchunks, float *d_out, cudaStream_t s,
                const float **heads, unsigned *heads_stride_bytes, bool *done);
 

@@ -8,14 +8,10 @@
  * one chunk, i.e. two runs of 2048 complex samples -- front run [s0, s0+2048), back run
  * [nc-s0-2048, nc-s0):
  *
- *   1. offsets: every thread reads its 8 steps (16 bytes from each run) and runs the recurrence from
- *      zero; the CTA scan turns that into the offsets at its first step relative to the tile start;
- *      the tile's own start values come from the tiles before it INSIDE this launch by decoupled
- *      look-back (fmq_lookback, the machinery of the quality pipeline's input cascade: tiles in
- *      ticket order publish their end value from zero, then their true end value), the carry of the
- *      previous call enters at tile 0 and the last tile leaves the next call's; then the thread
- *      walks its steps with the reference's own float operations and leaves the conditioned
- *      samples of both runs in shared memory;
+ *   1. offsets: every thread reads its 8 steps (16 bytes from each run), the CTA scan gives it the
+ *      offsets at its first step (tile start values from fmq_scan_tiles_kernel, as in
+ *      fmd_correctiq.cuh), then it walks its steps with the reference's own float operations and
+ *      leaves the conditioned samples of both runs in shared memory;
  *   2. a few samples past each run (the stencils' reach): ahead of the front run the offsets are
  *      walked on from the tile's end values (or, in the chunk's last tile, the front run simply
  *      continues into this tile's own back run); ahead of the back run -- steps BEFORE this tile --
@@ -27,8 +23,7 @@
  * the op-for-op path as everywhere else: the kernel leaves the conditioned samples of the chunk's
  * first FMQ1_HEADS complex samples in a side buffer for it.
  *
- * HBM traffic: 2 B read + 2 B written per sample (the algorithmic 4 B) instead of the 22 B of the
- * three-pass form.
+ * HBM traffic: 2 B (tile-end pass) + 2 B + 2 B per sample instead of the 22 B of the three-pass form.
  */
 #ifndef FMD_Q1_FUSED_CUH
 #define FMD_Q1_FUSED_CUH
@@ -49,30 +44,22 @@ __device__ __forceinline__ unsigned fmq1_idx(unsigned i) { return i + 2u * (i >>
 template <int NTI, int NTO>
 __global__ void __launch_bounds__(FMQ_THREADS)
 fmd_q1_fused_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const FmdQ1Geom g, const fmq_consts c,
-                    const float *__restrict__ lane_tab, const float *__restrict__ lane_tile, const FmqLookback lb,
-                    const FmqMat wtile /* a^(32 TILE) */, float *__restrict__ carry_io /* [2]: offsets between calls */,
-                    unsigned *__restrict__ error, const unsigned ntiles, const FmdStencil st, const unsigned head,
-                    float2 *__restrict__ heads /* [nchunks][FMQ1_HEADS] */) {
+                    const float *__restrict__ lane_tab, const float *__restrict__ q_tile /* [ntiles][2] */,
+                    const FmdStencil st, const unsigned head, float2 *__restrict__ heads /* [nchunks][FMQ1_HEADS] */) {
     extern __shared__ float4 fmq1_smem4[];
     float2 *cf = reinterpret_cast<float2 *>(fmq1_smem4); /* front run, conditioned */
     float2 *cb = cf + FMQ1_RUN_SLOTS;                     /* back run                */
     float *xf = reinterpret_cast<float *>(cb + FMQ1_RUN_SLOTS);
     float *xb = xf + FMQ1_X_SLOTS;
     __shared__ float tot[FMQ_WARPS * 2];
-    __shared__ unsigned tile_s;
-    __shared__ float carry_s[2];
 
     constexpr unsigned TS = FMQ1_TILE;
     constexpr unsigned LA = 2u * (NTO - 1) + (NTI > 1 ? NTI - 1 : 0); /* reach past a run, complex samples */
     static_assert(LA <= FMQ1_LA, "look-ahead buffer too small");
     const unsigned t = threadIdx.x;
-    /* tiles in ticket order: a tile's predecessors have all started (the look-back relies on it) */
-    if (t == 0u) tile_s = atomicAdd(lb.ticket, 1u);
-    __syncthreads();
-    const unsigned tile = tile_s;
     const unsigned tiles_per_chunk = g.steps_per_chunk / TS;
-    const unsigned chunk = tile / tiles_per_chunk;
-    const unsigned s0 = (tile - chunk * tiles_per_chunk) * TS; /* first step of the tile, chunk-relative */
+    const unsigned chunk = blockIdx.x / tiles_per_chunk;
+    const unsigned s0 = (blockIdx.x - chunk * tiles_per_chunk) * TS; /* first step of the tile, chunk-relative */
     const unsigned nc = 2u * g.steps_per_chunk;
     const uint8_t *__restrict__ cin = in + (unsigned long long) chunk * g.chunk_bytes;
     const unsigned short *__restrict__ smp = reinterpret_cast<const unsigned short *>(cin); /* complex sample c: I low, Q high */
@@ -91,52 +78,10 @@ fmd_q1_fused_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, con
         v[0][0] = fmaf(g.a, v[0][0], g.esr * (float) (FMQ1_I(f, j) + FMQ1_I(b, 7 - j)));
         v[1][0] = fmaf(g.a, v[1][0], g.esr * (float) (FMQ1_Q(f, j) + FMQ1_Q(b, 7 - j)));
     }
-    const float e0 = v[0][0], e1 = v[1][0]; /* this thread's 8 steps from zero */
-    float carry[2][1] = {{0.0f}, {0.0f}};
-    fmq_block_scan<1, 2>(v, c, lane_tab, carry, tot); /* offsets at the thread's first step, RELATIVE to a zero tile start */
-    if ((t >> 5) == FMQ_WARPS - 1u) {
-        /* the last warp: tile end value from zero (E), look-back for the true tile start, publish the true end (S) */
-        const unsigned lane = t & 31u;
-        float E[2][1], q0[2][1];
-        E[0][0] = __shfl_sync(0xffffffffu, fmaf(c.lvl[0][0], v[0][0], e0), 31); /* a^8 v + e of the last thread */
-        E[1][0] = __shfl_sync(0xffffffffu, fmaf(c.lvl[0][0], v[1][0], e1), 31);
-        if (tile == 0u) {
-            q0[0][0] = carry_io[0];
-            q0[1][0] = carry_io[1];
-        } else {
-            if (lane == 0u) {
-                lb.E[(size_t) tile * 2] = E[0][0];
-                lb.E[(size_t) tile * 2 + 1] = E[1][0];
-                __threadfence();
-                atomicExch(lb.flag + tile, 1u);
-            }
-            fmq_lookback<1>(lb, tile, lane, lane_tile, wtile, q0, error);
-        }
-        if (lane == 0u) {
-            const float s_0 = fmaf(c.tile[0], q0[0][0], E[0][0]), s_1 = fmaf(c.tile[0], q0[1][0], E[1][0]);
-            if (tile + 1u == ntiles) { /* the carry of the next call */
-                carry_io[0] = s_0;
-                carry_io[1] = s_1;
-            } else {
-                lb.S[(size_t) tile * 2] = s_0;
-                lb.S[(size_t) tile * 2 + 1] = s_1;
-                __threadfence();
-                atomicExch(lb.flag + tile, 2u);
-            }
-            carry_s[0] = q0[0][0];
-            carry_s[1] = q0[1][0];
-        }
-    }
-    __syncthreads();
-    carry[0][0] = carry_s[0];
-    carry[1][0] = carry_s[1];
-    {
-        /* true offsets = relative ones + a^(8 t) x tile start: a^(256 w) by the warp matrix, a^(8 l) from the lane table */
-        float m = __ldg(lane_tab + (t & 31u));
-        for (unsigned w = 0; w < (t >> 5); ++w) m *= c.warp[0];
-        v[0][0] = fmaf(m, carry[0][0], v[0][0]);
-        v[1][0] = fmaf(m, carry[1][0], v[1][0]);
-    }
+    float carry[2][1];
+    carry[0][0] = __ldg(q_tile + 2 * (size_t) blockIdx.x);
+    carry[1][0] = __ldg(q_tile + 2 * (size_t) blockIdx.x + 1);
+    fmq_block_scan<1, 2>(v, c, lane_tab, carry, tot);
     float off0 = v[0][0], off1 = v[1][0];
     {
         /* the reference's loop body, operation for operation (matrix.c:129-138); two steps per 16-byte store */

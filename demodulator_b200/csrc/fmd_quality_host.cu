@@ -372,8 +372,6 @@ struct fmq1_ctx {
     unsigned tile_cap = 0;
     float *d_sbuf = nullptr; /* conditioned samples of the current call (three-pass form) */
     size_t sbuf_cap = 0;
-    unsigned *d_lb = nullptr;  /* fused form: look-back ticket + per-tile flags, then the error word */
-    unsigned lb_cap = 0;
     float2 *d_heads = nullptr; /* fused form: the conditioned first FMQ1_HEADS complex samples of every chunk */
     size_t heads_cap = 0;      /* chunks */
     bool fused_smem_set[4][6] = {};
@@ -418,7 +416,6 @@ void fmq1_free(fmd_ctx *c) {
     if (q->d_q) cudaFree(q->d_q);
     if (q->d_sbuf) cudaFree(q->d_sbuf);
     if (q->d_heads) cudaFree(q->d_heads);
-    if (q->d_lb) cudaFree(q->d_lb);
     delete q;
     c->q1 = nullptr;
 }
@@ -498,24 +495,9 @@ int fmq1_condition(fmd_ctx *c, const uint8_t *d_in, unsigned long long nchunks, 
     return FMD_OK;
 }
 
-/* a look-back of the fused form that gave up waiting raises the error word (never seen; bounded so
- * that nothing can hang): reported once, then cleared */
-int fmq1_check_error(fmd_ctx *c) {
-    fmq1_ctx *q = c->q1;
-    if (!q || !q->d_lb) return FMD_OK;
-    FmdDeviceScope on_device(c->device);
-    unsigned err = 0;
-    cudaError_t e = cudaMemcpy(&err, q->d_lb + q->lb_cap + 1u, sizeof err, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && err) e = cudaMemset(q->d_lb + q->lb_cap + 1u, 0, sizeof err);
-    if (e != cudaSuccess) return fmd_set_error(FMD_ECUDA, "-q1: reading the error word failed: %s", cudaGetErrorString(e));
-    if (err) return fmd_set_error(FMD_ECUDA, "-q1: a tile gave up waiting for its predecessor's offsets (outputs of that call are invalid)");
-    return FMD_OK;
-}
-
 /* ---- fused form (fmd_q1_fused.cuh): conditioning and demodulation in one kernel ---- */
 typedef void (*fmq1_fused_fn)(const uint8_t *, float *, const FmdQ1Geom, const fmq_consts, const float *, const float *,
-                              const FmqLookback, const FmqMat, float *, unsigned *, const unsigned, const FmdStencil,
-                              const unsigned, float2 *);
+                              const FmdStencil, const unsigned, float2 *);
 
 template <int NTI>
 static fmq1_fused_fn fmq1_pick_out(unsigned nto) {
@@ -563,46 +545,9 @@ int fmq1_fused(fmd_ctx *c, const uint8_t *d_in, unsigned long long nchunks, floa
         q->heads_cap = cap;
     }
     FmdQ1Geom g;
-    g.chunk_bytes = B;
-    g.steps_per_chunk = (unsigned) (B >> 2);
-    g.nsteps = nchunks * g.steps_per_chunk;
-    g.esr = q->esr;
-    g.a = q->a;
-    const unsigned long long ntiles64 = g.nsteps / FMQ1_TILE;
-    if (ntiles64 > 0x7fffffffull) return fmd_set_error(FMD_EINVAL, "too many chunks in one -q1 call");
-    const unsigned ntiles = (unsigned) ntiles64;
-    if (ntiles > q->tile_cap) {
-        if (q->d_e) cudaFree(q->d_e);
-        if (q->d_q) cudaFree(q->d_q);
-        q->d_e = q->d_q = nullptr;
-        q->tile_cap = 0;
-        const unsigned cap = ntiles < 4096u ? 4096u : ntiles;
-        FMD_CUDA(cudaMalloc(&q->d_e, (size_t) cap * 2 * sizeof(float)));
-        FMD_CUDA(cudaMalloc(&q->d_q, (size_t) cap * 2 * sizeof(float)));
-        q->tile_cap = cap;
-    }
-    if (ntiles > q->lb_cap) {
-        if (q->d_lb) cudaFree(q->d_lb);
-        q->d_lb = nullptr;
-        q->lb_cap = 0;
-        const unsigned cap = ntiles < 4096u ? 4096u : ntiles;
-        FMD_CUDA(cudaMalloc(&q->d_lb, ((size_t) cap + 2u) * sizeof(unsigned)));
-        FMD_CUDA(cudaMemset(q->d_lb + cap + 1u, 0, sizeof(unsigned))); /* the error word lives past the flags */
-        q->lb_cap = cap;
-    }
-    /* ticket + one flag per tile, cleared per launch; E and S records per tile in d_e / d_q */
-    FMD_CUDA(cudaMemsetAsync(q->d_lb, 0, ((size_t) ntiles + 1u) * sizeof(unsigned), s));
-    FmqLookback lb;
-    lb.ticket = q->d_lb;
-    lb.flag = q->d_lb + 1;
-    lb.E = q->d_e;
-    lb.S = q->d_q;
-    FmqMat wtile;
-    memset(&wtile, 0, sizeof wtile);
-    memcpy(wtile.m, q->c_tile.warp, sizeof wtile.m); /* a^(32 TILE): one look-back round */
-    const float *lane = q->d_tab;
-    const float *lane_tile = q->d_tab + q->sz.lane + q->sz.apow + q->sz.ck + q->sz.ckn;
-    int rc;
+    unsigned ntiles = 0;
+    int rc = fmq1_scan(c, d_in, nchunks, s, &g, &ntiles);
+    if (rc) return rc;
     bool &opted = q->fused_smem_set[c->nti][c->nto];
     if (!opted) { /* 49.5 KB of dynamic shared memory: past the 48 KB default */
         FMD_CUDA(cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FMQ1_SMEM_BYTES));
@@ -612,8 +557,7 @@ int fmq1_fused(fmd_ctx *c, const uint8_t *d_in, unsigned long long nchunks, floa
     rc = fmd_prof_events(c, &pe);
     if (rc) return rc;
     if (pe) FMD_CUDA(cudaEventRecord(pe[0], s));
-    fn<<<ntiles, FMQ_THREADS, FMQ1_SMEM_BYTES, s>>>(d_in, d_out, g, q->c, lane, lane_tile, lb, wtile, q->d_off,
-                                                    q->d_lb + q->lb_cap + 1u, ntiles, c->st, c->head, q->d_heads);
+    fn<<<ntiles, FMQ_THREADS, FMQ1_SMEM_BYTES, s>>>(d_in, d_out, g, q->c, q->d_tab, q->d_q, c->st, c->head, q->d_heads);
     FMD_CUDA(cudaGetLastError());
     if (pe) FMD_CUDA(cudaEventRecord(pe[1], s));
     c->launches += 1;

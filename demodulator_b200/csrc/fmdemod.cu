@@ -759,7 +759,6 @@ extern "C" int fmd_wait(fmd_ctx *c, unsigned slot) {
     FMD_CUDA(cudaEventSynchronize(s.ev_out));
     s.busy = false;
     if (c->q) return fmq_check_error(c); /* a look-back that gave up waiting raises a device-side flag */
-    if (c->q1) return fmq1_check_error(c);
     return FMD_OK;
 }
 
@@ -771,7 +770,6 @@ extern "C" int fmd_check(fmd_ctx *c, void *stream) {
     cudaError_t e = cudaStreamSynchronize((cudaStream_t) stream);
     if (prev != c->device && prev >= 0) cudaSetDevice(prev);
     if (e != cudaSuccess) return fmd_set_error(FMD_ECUDA, "fmd_check: %s", cudaGetErrorString(e));
-    if (c->q1) return fmq1_check_error(c);
     return c->q ? fmq_check_error(c) : FMD_OK;
 }
 
