@@ -34,28 +34,55 @@
 #define FMQ1_LA 16u    /* complex samples kept past each run: 2 (NTO - 1) + NTI - 1 <= 10 */
 #define FMQ1_HEADS 128u /* conditioned complex samples per chunk handed to the op-for-op head path */
 
-/* shared-memory index of complex sample i of a run: two float2 of padding per 8 samples make the
- * stride between threads 80 bytes, conflict-free for the 16-byte accesses of both phases */
-__device__ __forceinline__ unsigned fmq1_idx(unsigned i) { return i + 2u * (i >> 3); }
-#define FMQ1_RUN_SLOTS (((FMQ1_TILE + FMQ1_LA) / 8u) * 10u) /* float2 slots per run */
-#define FMQ1_X_SLOTS (FMQ1_TILE / 2u + 8u)                  /* discriminator outputs per run */
-#define FMQ1_SMEM_BYTES ((2u * FMQ1_RUN_SLOTS * 2u + 2u * FMQ1_X_SLOTS) * 4u)
+/* byte B of a raw word as an exact float: 0x4B0000uu = 8388608 + u */
+template <int B>
+__device__ __forceinline__ float fmq1_byte(uint32_t w) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540 | B)) - 8388608.0f;
+}
 
+/* discriminator output from NTI + 1 (or 2) consecutive conditioned samples s[0..]:
+ * z[c] = s[c] + sum_{u>=1} tin[u] s[c+u] (+ dcq on the Q lane) -- the stencil divided by its first tap,
+ * as in fmd_pass_core -- then atan2 of z[0] conj z[1] */
+template <int NTI>
+__device__ __forceinline__ float fmq1_disc(const float2 *s, const FmdStencil &st) {
+    float ar = s[0].x, ai = s[0].y, br = s[1].x, bi = s[1].y;
+    if (NTI > 0) {
+        ai = __fadd_rn(ai, st.dcq);
+        bi = __fadd_rn(bi, st.dcq);
+#pragma unroll
+        for (int u = 1; u < NTI; ++u) {
+            ar = fmaf(st.tin[u], s[u].x, ar);
+            ai = fmaf(st.tin[u], s[u].y, ai);
+            br = fmaf(st.tin[u], s[u + 1].x, br);
+            bi = fmaf(st.tin[u], s[u + 1].y, bi);
+        }
+    }
+    return fmd_atan2(fmaf(-ar, bi, ai * br), fmaf(ar, br, ai * bi));
+}
+
+/*
+ * Everything a thread needs of its own 16 samples stays in registers; shared memory only carries
+ * what crosses a thread: the first NTI - 1 conditioned samples of every group (the next group's
+ * input-stencil halo), the first NTO - 1 discriminator outputs of every thread, and the few samples /
+ * outputs past the two runs.  (A first version kept both conditioned runs in shared memory and read
+ * them back: 387 GS/s for the whole -q1 pipeline; this one: see profiles/.)
+ */
 template <int NTI, int NTO>
 __global__ void __launch_bounds__(FMQ_THREADS)
 fmd_q1_fused_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const FmdQ1Geom g, const fmq_consts c,
                     const float *__restrict__ lane_tab, const float *__restrict__ q_tile /* [ntiles][2] */,
                     const FmdStencil st, const unsigned head, float2 *__restrict__ heads /* [nchunks][FMQ1_HEADS] */) {
-    extern __shared__ float4 fmq1_smem4[];
-    float2 *cf = reinterpret_cast<float2 *>(fmq1_smem4); /* front run, conditioned */
-    float2 *cb = cf + FMQ1_RUN_SLOTS;                     /* back run                */
-    float *xf = reinterpret_cast<float *>(cb + FMQ1_RUN_SLOTS);
-    float *xb = xf + FMQ1_X_SLOTS;
+    constexpr unsigned TS = FMQ1_TILE;
+    constexpr int HC = NTI > 1 ? NTI - 1 : 0; /* conditioned samples needed from the following group */
+    constexpr int NB = NTO - 1;               /* discriminator outputs needed from the following thread */
+    constexpr unsigned LA = 2u * NB + HC;     /* reach past a run, complex samples */
+    static_assert(LA <= FMQ1_LA, "look-ahead buffer too small");
+    constexpr int HC1 = HC > 0 ? HC : 1, NB1 = NB > 0 ? NB : 1;
+    __shared__ float2 hf[FMQ_THREADS * HC1], hb[FMQ_THREADS * HC1]; /* first HC samples (address order) of every group */
+    __shared__ float2 laf[FMQ1_LA + 4], lab[FMQ1_LA + 4];           /* samples past the front / back run */
+    __shared__ float xhf[(FMQ_THREADS + 1) * NB1], xhb[(FMQ_THREADS + 1) * NB1]; /* first NB outputs of every thread; [256]: past the run */
     __shared__ float tot[FMQ_WARPS * 2];
 
-    constexpr unsigned TS = FMQ1_TILE;
-    constexpr unsigned LA = 2u * (NTO - 1) + (NTI > 1 ? NTI - 1 : 0); /* reach past a run, complex samples */
-    static_assert(LA <= FMQ1_LA, "look-ahead buffer too small");
     const unsigned t = threadIdx.x;
     const unsigned tiles_per_chunk = g.steps_per_chunk / TS;
     const unsigned chunk = blockIdx.x / tiles_per_chunk;
@@ -65,45 +92,54 @@ fmd_q1_fused_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, con
     const unsigned short *__restrict__ smp = reinterpret_cast<const unsigned short *>(cin); /* complex sample c: I low, Q high */
     const bool last_tile = s0 + TS == g.steps_per_chunk; /* its front run runs straight into its back run */
 
-#define FMQ1_W(v, i) ((i) < 2 ? (v).x : (i) < 4 ? (v).y : (i) < 6 ? (v).z : (v).w)
-#define FMQ1_I(v, i) ((FMQ1_W(v, i) >> (16 * ((i) & 1))) & 0xffu)
-#define FMQ1_Q(v, i) ((FMQ1_W(v, i) >> (16 * ((i) & 1) + 8)) & 0xffu)
-    /* ---- 1. the offsets at this thread's first step, then its 8 steps ---- */
+    /* ---- 1. the thread's 8 steps as floats: step j = front sample j, back sample 7 - j of the two 16-byte groups ---- */
     const unsigned k0 = s0 + 8u * t;
     const uint4 f = __ldg(reinterpret_cast<const uint4 *>(smp + k0));
     const uint4 b = __ldg(reinterpret_cast<const uint4 *>(smp + (nc - 8u - k0)));
+    float fI[8], fQ[8], bI[8], bQ[8]; /* step order */
+    {
+        const uint32_t fw[4] = {f.x, f.y, f.z, f.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            fI[2 * w] = fmq1_byte<0>(fw[w]);
+            fQ[2 * w] = fmq1_byte<1>(fw[w]);
+            fI[2 * w + 1] = fmq1_byte<2>(fw[w]);
+            fQ[2 * w + 1] = fmq1_byte<3>(fw[w]);
+            /* back group, address position 2w / 2w+1 = step 7-2w / 6-2w */
+            bI[7 - 2 * w] = fmq1_byte<0>(bw[w]);
+            bQ[7 - 2 * w] = fmq1_byte<1>(bw[w]);
+            bI[6 - 2 * w] = fmq1_byte<2>(bw[w]);
+            bQ[6 - 2 * w] = fmq1_byte<3>(bw[w]);
+        }
+    }
+    /* offsets at this thread's first step: 8 steps from zero, CTA scan with the tile's start values */
     float v[2][1] = {{0.0f}, {0.0f}};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        v[0][0] = fmaf(g.a, v[0][0], g.esr * (float) (FMQ1_I(f, j) + FMQ1_I(b, 7 - j)));
-        v[1][0] = fmaf(g.a, v[1][0], g.esr * (float) (FMQ1_Q(f, j) + FMQ1_Q(b, 7 - j)));
+        v[0][0] = fmaf(g.a, v[0][0], g.esr * (fI[j] + bI[j]));
+        v[1][0] = fmaf(g.a, v[1][0], g.esr * (fQ[j] + bQ[j]));
     }
     float carry[2][1];
     carry[0][0] = __ldg(q_tile + 2 * (size_t) blockIdx.x);
     carry[1][0] = __ldg(q_tile + 2 * (size_t) blockIdx.x + 1);
     fmq_block_scan<1, 2>(v, c, lane_tab, carry, tot);
     float off0 = v[0][0], off1 = v[1][0];
-    {
-        /* the reference's loop body, operation for operation (matrix.c:129-138); two steps per 16-byte store */
-        float4 *__restrict__ pf = reinterpret_cast<float4 *>(cf + fmq1_idx(8u * t));
-        float4 *__restrict__ pb = reinterpret_cast<float4 *>(cb + fmq1_idx(TS - 8u - 8u * t));
+    /* the reference's loop body, operation for operation (matrix.c:129-138), in place */
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-            float fi[2], fq[2], bi[2], bq[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                fi[u] = __fsub_rn((float) FMQ1_I(f, j + u), off0);
-                bi[u] = __fsub_rn((float) FMQ1_I(b, 7 - (j + u)), off0);
-                fq[u] = __fsub_rn((float) FMQ1_Q(f, j + u), off1);
-                bq[u] = __fsub_rn((float) FMQ1_Q(b, 7 - (j + u)), off1);
-                off0 = __fadd_rn(off0, __fmul_rn(__fadd_rn(fi[u], bi[u]), g.esr));
-                off1 = __fadd_rn(off1, __fmul_rn(__fadd_rn(fq[u], bq[u]), g.esr));
-            }
-            pf[j >> 1] = make_float4(fi[0], fq[0], fi[1], fq[1]);
-            pb[3 - (j >> 1)] = make_float4(bi[1], bq[1], bi[0], bq[0]); /* back samples 6-j, 7-j of the group */
-        }
+    for (int j = 0; j < 8; ++j) {
+        fI[j] = __fsub_rn(fI[j], off0);
+        bI[j] = __fsub_rn(bI[j], off0);
+        fQ[j] = __fsub_rn(fQ[j], off1);
+        bQ[j] = __fsub_rn(bQ[j], off1);
+        off0 = __fadd_rn(off0, __fmul_rn(__fadd_rn(fI[j], bI[j]), g.esr));
+        off1 = __fadd_rn(off1, __fmul_rn(__fadd_rn(fQ[j], bQ[j]), g.esr));
     }
-    /* ---- 2. what lies past the runs ---- */
+    /* ---- 2. what crosses a thread, and what lies past the runs ---- */
+#pragma unroll
+    for (int h = 0; h < HC; ++h) {
+        hf[t * HC1 + h] = make_float2(fI[h], fQ[h]);
+        hb[t * HC1 + h] = make_float2(bI[7 - h], bQ[7 - h]); /* address position h of the back group */
+    }
     if (t == FMQ_THREADS - 1u && !last_tile) {
         /* ahead of the front run: the front samples of the steps that follow this tile, conditioned
          * with the offsets walked on from the tile's end (off0/off1 of the last thread) */
@@ -113,9 +149,18 @@ fmd_q1_fused_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, con
             const unsigned uf = smp[k], ub = smp[nc - 1u - k];
             const float fi = __fsub_rn((float) (uf & 0xffu), o0), fq = __fsub_rn((float) (uf >> 8), o1);
             const float bi = __fsub_rn((float) (ub & 0xffu), o0), bq = __fsub_rn((float) (ub >> 8), o1);
-            cf[fmq1_idx(TS + i)] = make_float2(fi, fq);
+            laf[i] = make_float2(fi, fq);
             o0 = __fadd_rn(o0, __fmul_rn(__fadd_rn(fi, bi), g.esr));
             o1 = __fadd_rn(o1, __fmul_rn(__fadd_rn(fq, bq), g.esr));
+        }
+    }
+    if (last_tile && t >= FMQ_THREADS - 2u) {
+        /* complex nc/2 + i follows complex nc/2 - 1: the back run IS what lies ahead of the front run
+         * (its first 8 samples are the last thread's back group, the next 8 the thread's before it) */
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const unsigned idx = (FMQ_THREADS - 1u - t) * 8u + (unsigned) m;
+            if (idx < LA) laf[idx] = make_float2(bI[7 - m], bQ[7 - m]);
         }
     }
     if (t == 0u) {
@@ -134,50 +179,51 @@ fmd_q1_fused_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, con
                 o1 = (o1 - g.esr * (float) ((uf >> 8) + (ub >> 8))) * ra;
                 val = make_float2((float) (ub & 0xffu) - o0, (float) (ub >> 8) - o1);
             }
-            cb[fmq1_idx(TS + i)] = val;
+            lab[i] = val;
         }
+    }
+    if (s0 == 0u && heads && t < FMQ1_HEADS / 8u) {
+        float4 *__restrict__ hp = reinterpret_cast<float4 *>(heads + (size_t) chunk * FMQ1_HEADS + 8u * t);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) hp[j >> 1] = make_float4(fI[j], fQ[j], fI[j + 1], fQ[j + 1]);
     }
     __syncthreads();
-    if (last_tile) { /* complex nc/2 + i follows complex nc/2 - 1: the back run IS what lies ahead of the front run */
-        if (t < LA) cf[fmq1_idx(TS + t)] = cb[fmq1_idx(t)];
-        __syncthreads();
-    }
-    if (s0 == 0u && heads && t < FMQ1_HEADS) heads[(size_t) chunk * FMQ1_HEADS + t] = cf[fmq1_idx(t)];
 
-    /* ---- 3. stencil, discriminator, atan2: 4 outputs per thread and run (+ NTO - 1 past the run) ---- */
-    auto disc = [&](const float2 *__restrict__ run, unsigned kx) -> float {
-        /* z[c] = s[c] + sum_{u>=1} tin[u] s[c+u] (+ dcq on the Q lane): the stencil divided by its first tap,
-         * as in fmd_pass_core */
-        float2 s[NTI > 0 ? NTI + 1 : 2];
+    /* ---- 3. stencil, discriminator, atan2: 4 outputs per run from registers + the following group's halo ---- */
+    float2 sf[8 + HC1], sb[8 + HC1]; /* address order */
 #pragma unroll
-        for (int u = 0; u < (NTI > 0 ? NTI + 1 : 2); ++u) s[u] = run[fmq1_idx(2u * kx + (unsigned) u)];
-        float ar = s[0].x, ai = s[0].y, br = s[1].x, bi = s[1].y;
-        if (NTI > 0) {
-            ai = __fadd_rn(ai, st.dcq);
-            bi = __fadd_rn(bi, st.dcq);
+    for (int m = 0; m < 8; ++m) {
+        sf[m] = make_float2(fI[m], fQ[m]);
+        sb[m] = make_float2(bI[7 - m], bQ[7 - m]);
+    }
 #pragma unroll
-            for (int u = 1; u < NTI; ++u) {
-                ar = fmaf(st.tin[u], s[u].x, ar);
-                ai = fmaf(st.tin[u], s[u].y, ai);
-                br = fmaf(st.tin[u], s[u + 1].x, br);
-                bi = fmaf(st.tin[u], s[u + 1].y, bi);
-            }
-        }
-        const float re = fmaf(ar, br, ai * bi);
-        const float im = fmaf(-ar, bi, ai * br);
-        return fmd_atan2(im, re);
-    };
+    for (int h = 0; h < HC; ++h) {
+        sf[8 + h] = t + 1u < FMQ_THREADS ? hf[(t + 1u) * HC1 + h] : laf[h]; /* the next group of the front run */
+        sb[8 + h] = t > 0u ? hb[(t - 1u) * HC1 + h] : lab[h];               /* the back run's next group is the PREVIOUS thread's */
+    }
+    float xF[4 + NB1], xB[4 + NB1];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        xf[4u * t + (unsigned) j] = disc(cf, 4u * t + (unsigned) j);
-        xb[4u * t + (unsigned) j] = disc(cb, 4u * t + (unsigned) j);
+        xF[j] = fmq1_disc<NTI>(sf + 2 * j, st);
+        xB[j] = fmq1_disc<NTI>(sb + 2 * j, st);
     }
-    if (t < (unsigned) (NTO - 1)) {
-        xf[TS / 2u + t] = disc(cf, TS / 2u + t);
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+        xhf[t * NB1 + u] = xF[u];
+        xhb[t * NB1 + u] = xB[u];
+    }
+    if (t < (unsigned) NB) {
+        /* the outputs past the runs, from the look-ahead samples */
+        xhf[FMQ_THREADS * NB1 + t] = fmq1_disc<NTI>(laf + 2u * t, st);
         /* past the end of the chunk the discriminator output is exactly 0 (demodRet slack, matrix.c:184) */
-        xb[TS / 2u + t] = s0 == 0u ? 0.0f : disc(cb, TS / 2u + t);
+        xhb[FMQ_THREADS * NB1 + t] = s0 == 0u ? 0.0f : fmq1_disc<NTI>(lab + 2u * t, st);
     }
     __syncthreads();
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+        xF[4 + u] = xhf[(t + 1u) * NB1 + u];                                   /* thread 255 reads the slot past the run */
+        xB[4 + u] = t > 0u ? xhb[(t - 1u) * NB1 + u] : xhb[FMQ_THREADS * NB1 + u]; /* previous thread = higher addresses */
+    }
 
     /* ---- 4. output stencil, coalesced stores ---- */
     const unsigned chunk_out = g.steps_per_chunk; /* nc / 2 */
@@ -188,8 +234,8 @@ fmd_q1_fused_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, con
         float af = st.dco, ab = st.dco;
 #pragma unroll
         for (int u = 0; u < NTO; ++u) {
-            af = fmaf(st.tout[u], xf[4u * t + (unsigned) (j + u)], af);
-            ab = fmaf(st.tout[u], xb[4u * t + (unsigned) (j + u)], ab);
+            af = fmaf(st.tout[u], xF[j + u], af);
+            ab = fmaf(st.tout[u], xB[j + u], ab);
         }
         yf[j] = af;
         yb[j] = ab;
@@ -197,9 +243,6 @@ fmd_q1_fused_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, con
     /* the chunk head [0, head) belongs to the op-for-op path */
     if (!(s0 == 0u && 4u * t < head)) *reinterpret_cast<float4 *>(oc + s0 / 2u + 4u * t) = make_float4(yf[0], yf[1], yf[2], yf[3]);
     *reinterpret_cast<float4 *>(oc + (nc - s0 - TS) / 2u + 4u * t) = make_float4(yb[0], yb[1], yb[2], yb[3]);
-#undef FMQ1_W
-#undef FMQ1_I
-#undef FMQ1_Q
 }
 
 #endif /* FMD_Q1_FUSED_CUH */

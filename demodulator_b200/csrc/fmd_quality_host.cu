@@ -374,7 +374,7 @@ struct fmq1_ctx {
     size_t sbuf_cap = 0;
     float2 *d_heads = nullptr; /* fused form: the conditioned first FMQ1_HEADS complex samples of every chunk */
     size_t heads_cap = 0;      /* chunks */
-    bool fused_smem_set[4][6] = {};
+
     float esr = 0.f, a = 0.f;
 };
 
@@ -548,16 +548,11 @@ int fmq1_fused(fmd_ctx *c, const uint8_t *d_in, unsigned long long nchunks, floa
     unsigned ntiles = 0;
     int rc = fmq1_scan(c, d_in, nchunks, s, &g, &ntiles);
     if (rc) return rc;
-    bool &opted = q->fused_smem_set[c->nti][c->nto];
-    if (!opted) { /* 49.5 KB of dynamic shared memory: past the 48 KB default */
-        FMD_CUDA(cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FMQ1_SMEM_BYTES));
-        opted = true;
-    }
     cudaEvent_t *pe = nullptr;
     rc = fmd_prof_events(c, &pe);
     if (rc) return rc;
     if (pe) FMD_CUDA(cudaEventRecord(pe[0], s));
-    fn<<<ntiles, FMQ_THREADS, FMQ1_SMEM_BYTES, s>>>(d_in, d_out, g, q->c, q->d_tab, q->d_q, c->st, c->head, q->d_heads);
+    fn<<<ntiles, FMQ_THREADS, 0, s>>>(d_in, d_out, g, q->c, q->d_tab, q->d_q, c->st, c->head, q->d_heads);
     FMD_CUDA(cudaGetLastError());
     if (pe) FMD_CUDA(cudaEventRecord(pe[1], s));
     c->launches += 1;
