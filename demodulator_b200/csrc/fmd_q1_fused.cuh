@@ -242,7 +242,8 @@ fmd_q1_fused_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, con
     }
     /* the chunk head [0, head) belongs to the op-for-op path */
     if (!(s0 == 0u && 4u * t < head)) *reinterpret_cast<float4 *>(oc + s0 / 2u + 4u * t) = make_float4(yf[0], yf[1], yf[2], yf[3]);
-    *reinterpret_cast<float4 *>(oc + (nc - s0 - TS) / 2u + 4u * t) = make_float4(yb[0], yb[1], yb[2], yb[3]);
+    /* the thread's back group sits at run position TS - 8 - 8t: the back run is walked towards lower addresses */
+    *reinterpret_cast<float4 *>(oc + (nc - s0 - TS) / 2u + (TS / 2u - 4u - 4u * t)) = make_float4(yb[0], yb[1], yb[2], yb[3]);
 }
 
 #endif /* FMD_Q1_FUSED_CUH */
