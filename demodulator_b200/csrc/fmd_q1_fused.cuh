@@ -34,6 +34,8 @@
 #define FMQ1_LA 16u    /* complex samples kept past each run: 2 (NTO - 1) + NTI - 1 <= 10 */
 #define FMQ1_HEADS 128u /* conditioned complex samples per chunk handed to the op-for-op head path */
 
+#define FMQ1_SUBS 8u /* tiles one CTA walks one after the other: the offsets run on from tile to tile inside it */
+
 /* byte B of a raw word as an exact float: 0x4B0000uu = 8388608 + u */
 template <int B>
 __device__ __forceinline__ float fmq1_byte(uint32_t w) {
@@ -60,6 +62,81 @@ __device__ __forceinline__ float fmq1_disc(const float2 *s, const FmdStencil &st
     return fmd_atan2(fmaf(-ar, bi, ai * br), fmaf(ar, br, ai * bi));
 }
 
+/* the thread's 8 steps of tile `tile` as floats, step order: step j = front sample j, back sample 7 - j */
+__device__ __forceinline__ void fmq1_load_steps(const uint8_t *__restrict__ in, const FmdQ1Geom &g, unsigned tile, unsigned t,
+                                                float (&fI)[8], float (&fQ)[8], float (&bI)[8], float (&bQ)[8]) {
+    const unsigned tiles_per_chunk = g.steps_per_chunk / FMQ1_TILE;
+    const unsigned chunk = tile / tiles_per_chunk;
+    const unsigned k0 = (tile - chunk * tiles_per_chunk) * FMQ1_TILE + 8u * t;
+    const unsigned nc = 2u * g.steps_per_chunk;
+    const unsigned short *__restrict__ smp = reinterpret_cast<const unsigned short *>(in + (unsigned long long) chunk * g.chunk_bytes);
+    const uint4 f = __ldg(reinterpret_cast<const uint4 *>(smp + k0));
+    const uint4 b = __ldg(reinterpret_cast<const uint4 *>(smp + (nc - 8u - k0)));
+    const uint32_t fw[4] = {f.x, f.y, f.z, f.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        fI[2 * w] = fmq1_byte<0>(fw[w]);
+        fQ[2 * w] = fmq1_byte<1>(fw[w]);
+        fI[2 * w + 1] = fmq1_byte<2>(fw[w]);
+        fQ[2 * w + 1] = fmq1_byte<3>(fw[w]);
+        /* back group, address position 2w / 2w+1 = step 7-2w / 6-2w */
+        bI[7 - 2 * w] = fmq1_byte<0>(bw[w]);
+        bQ[7 - 2 * w] = fmq1_byte<1>(bw[w]);
+        bI[6 - 2 * w] = fmq1_byte<2>(bw[w]);
+        bQ[6 - 2 * w] = fmq1_byte<3>(bw[w]);
+    }
+}
+
+/*
+ * End values of the offsets, from zero, over every CTA's run of up to FMQ1_SUBS tiles (what
+ * fmq_scan_tiles_kernel then chains through the launch).  In exact arithmetic the end value is the
+ * weighted sum  esr * sum_k a^(steps after k) (u_front[k] + u_back[k]):  a lane weights its 8 steps,
+ * a butterfly sums the warp, every warp carries its own total from tile to tile (x a^2048), and
+ * only at the very end the 8 warp totals are combined -- one barrier per CTA, no scan.
+ */
+__global__ void __launch_bounds__(FMQ_THREADS)
+fmd_q1_ends_kernel(const uint8_t *__restrict__ in, const FmdQ1Geom g, const fmq_consts c, const float *__restrict__ lane_tab,
+                   const unsigned ntiles, float *__restrict__ e_run /* [nruns][2] */) {
+    __shared__ float wt[FMQ_WARPS * 2];
+    const unsigned t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    const float wl = __ldg(lane_tab + (31u - lane)); /* (a^8)^(31 - lane): from the end of this lane's steps to the end of the warp's */
+    float acc0 = 0.0f, acc1 = 0.0f;
+    unsigned tile = blockIdx.x * FMQ1_SUBS;
+    for (unsigned sub = 0; sub < FMQ1_SUBS && tile < ntiles; ++sub, ++tile) {
+        float fI[8], fQ[8], bI[8], bQ[8];
+        fmq1_load_steps(in, g, tile, t, fI, fQ, bI, bQ);
+        float v0 = 0.0f, v1 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            v0 = fmaf(g.a, v0, fI[j] + bI[j]);
+            v1 = fmaf(g.a, v1, fQ[j] + bQ[j]);
+        }
+        v0 *= wl;
+        v1 *= wl;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+        }
+        acc0 = fmaf(c.tile[0], acc0, v0); /* earlier tiles of this warp move a whole tile further from the end */
+        acc1 = fmaf(c.tile[0], acc1, v1);
+    }
+    if (lane == 0u) {
+        wt[2 * warp] = acc0;
+        wt[2 * warp + 1] = acc1;
+    }
+    __syncthreads();
+    if (t == 0u) {
+        float e0 = 0.0f, e1 = 0.0f;
+        for (unsigned w = 0; w < FMQ_WARPS; ++w) { /* Horner over the warps: a^256 per warp */
+            e0 = fmaf(c.warp[0], e0, wt[2 * w]);
+            e1 = fmaf(c.warp[0], e1, wt[2 * w + 1]);
+        }
+        e_run[2 * (size_t) blockIdx.x] = g.esr * e0;
+        e_run[2 * (size_t) blockIdx.x + 1] = g.esr * e1;
+    }
+}
+
 /*
  * Everything a thread needs of its own 16 samples stays in registers; shared memory only carries
  * what crosses a thread: the first NTI - 1 conditioned samples of every group (the next group's
@@ -70,8 +147,9 @@ __device__ __forceinline__ float fmq1_disc(const float2 *s, const FmdStencil &st
 template <int NTI, int NTO>
 __global__ void __launch_bounds__(FMQ_THREADS)
 fmd_q1_fused_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, const FmdQ1Geom g, const fmq_consts c,
-                    const float *__restrict__ lane_tab, const float *__restrict__ q_tile /* [ntiles][2] */,
-                    const FmdStencil st, const unsigned head, float2 *__restrict__ heads /* [nchunks][FMQ1_HEADS] */) {
+                    const float *__restrict__ lane_tab, const float *__restrict__ q_run /* [nruns][2]: offsets at the start of every CTA's run */,
+                    const unsigned ntiles, const FmdStencil st, const unsigned head,
+                    float2 *__restrict__ heads /* [nchunks][FMQ1_HEADS] */) {
     constexpr unsigned TS = FMQ1_TILE;
     constexpr int HC = NTI > 1 ? NTI - 1 : 0; /* conditioned samples needed from the following group */
     constexpr int NB = NTO - 1;               /* discriminator outputs needed from the following thread */
@@ -82,36 +160,23 @@ fmd_q1_fused_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, con
     __shared__ float2 laf[FMQ1_LA + 4], lab[FMQ1_LA + 4];           /* samples past the front / back run */
     __shared__ float xhf[(FMQ_THREADS + 1) * NB1], xhb[(FMQ_THREADS + 1) * NB1]; /* first NB outputs of every thread; [256]: past the run */
     __shared__ float tot[FMQ_WARPS * 2];
+    __shared__ float carry_s[2]; /* the offsets at the start of the next tile of this CTA's run */
 
     const unsigned t = threadIdx.x;
     const unsigned tiles_per_chunk = g.steps_per_chunk / TS;
-    const unsigned chunk = blockIdx.x / tiles_per_chunk;
-    const unsigned s0 = (blockIdx.x - chunk * tiles_per_chunk) * TS; /* first step of the tile, chunk-relative */
     const unsigned nc = 2u * g.steps_per_chunk;
+    unsigned tile = blockIdx.x * FMQ1_SUBS;
+#pragma unroll 1
+    for (unsigned sub = 0; sub < FMQ1_SUBS && tile < ntiles; ++sub, ++tile) {
+    const unsigned chunk = tile / tiles_per_chunk;
+    const unsigned s0 = (tile - chunk * tiles_per_chunk) * TS; /* first step of the tile, chunk-relative */
     const uint8_t *__restrict__ cin = in + (unsigned long long) chunk * g.chunk_bytes;
     const unsigned short *__restrict__ smp = reinterpret_cast<const unsigned short *>(cin); /* complex sample c: I low, Q high */
     const bool last_tile = s0 + TS == g.steps_per_chunk; /* its front run runs straight into its back run */
 
     /* ---- 1. the thread's 8 steps as floats: step j = front sample j, back sample 7 - j of the two 16-byte groups ---- */
-    const unsigned k0 = s0 + 8u * t;
-    const uint4 f = __ldg(reinterpret_cast<const uint4 *>(smp + k0));
-    const uint4 b = __ldg(reinterpret_cast<const uint4 *>(smp + (nc - 8u - k0)));
     float fI[8], fQ[8], bI[8], bQ[8]; /* step order */
-    {
-        const uint32_t fw[4] = {f.x, f.y, f.z, f.w}, bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            fI[2 * w] = fmq1_byte<0>(fw[w]);
-            fQ[2 * w] = fmq1_byte<1>(fw[w]);
-            fI[2 * w + 1] = fmq1_byte<2>(fw[w]);
-            fQ[2 * w + 1] = fmq1_byte<3>(fw[w]);
-            /* back group, address position 2w / 2w+1 = step 7-2w / 6-2w */
-            bI[7 - 2 * w] = fmq1_byte<0>(bw[w]);
-            bQ[7 - 2 * w] = fmq1_byte<1>(bw[w]);
-            bI[6 - 2 * w] = fmq1_byte<2>(bw[w]);
-            bQ[6 - 2 * w] = fmq1_byte<3>(bw[w]);
-        }
-    }
+    fmq1_load_steps(in, g, tile, t, fI, fQ, bI, bQ);
     /* offsets at this thread's first step: 8 steps from zero, CTA scan with the tile's start values */
     float v[2][1] = {{0.0f}, {0.0f}};
 #pragma unroll
@@ -119,9 +184,16 @@ fmd_q1_fused_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, con
         v[0][0] = fmaf(g.a, v[0][0], g.esr * (fI[j] + bI[j]));
         v[1][0] = fmaf(g.a, v[1][0], g.esr * (fQ[j] + bQ[j]));
     }
+    /* the tile's start values: from the scan over the runs for the CTA's first tile, then the offsets the
+     * previous tile's last thread ended with (the reference's own float trajectory) */
     float carry[2][1];
-    carry[0][0] = __ldg(q_tile + 2 * (size_t) blockIdx.x);
-    carry[1][0] = __ldg(q_tile + 2 * (size_t) blockIdx.x + 1);
+    if (sub == 0u) {
+        carry[0][0] = __ldg(q_run + 2 * (size_t) blockIdx.x);
+        carry[1][0] = __ldg(q_run + 2 * (size_t) blockIdx.x + 1);
+    } else {
+        carry[0][0] = carry_s[0];
+        carry[1][0] = carry_s[1];
+    }
     fmq_block_scan<1, 2>(v, c, lane_tab, carry, tot);
     float off0 = v[0][0], off1 = v[1][0];
     /* the reference's loop body, operation for operation (matrix.c:129-138), in place */
@@ -135,6 +207,10 @@ fmd_q1_fused_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, con
         off1 = __fadd_rn(off1, __fmul_rn(__fadd_rn(fQ[j], bQ[j]), g.esr));
     }
     /* ---- 2. what crosses a thread, and what lies past the runs ---- */
+    if (t == FMQ_THREADS - 1u) { /* read at the top of the next tile, after this tile's barriers */
+        carry_s[0] = off0;
+        carry_s[1] = off1;
+    }
 #pragma unroll
     for (int h = 0; h < HC; ++h) {
         hf[t * HC1 + h] = make_float2(fI[h], fQ[h]);
@@ -244,6 +320,7 @@ fmd_q1_fused_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, con
     if (!(s0 == 0u && 4u * t < head)) *reinterpret_cast<float4 *>(oc + s0 / 2u + 4u * t) = make_float4(yf[0], yf[1], yf[2], yf[3]);
     /* the thread's back group sits at run position TS - 8 - 8t: the back run is walked towards lower addresses */
     *reinterpret_cast<float4 *>(oc + (nc - s0 - TS) / 2u + (TS / 2u - 4u - 4u * t)) = make_float4(yb[0], yb[1], yb[2], yb[3]);
+    } /* next tile of the run: its first writes to shared memory (carry_s aside) come after its own barriers */
 }
 
 #endif /* FMD_Q1_FUSED_CUH */

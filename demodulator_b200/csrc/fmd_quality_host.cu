@@ -370,6 +370,8 @@ struct fmq1_ctx {
     float *d_off = nullptr; /* the two running offsets: the carry between calls */
     float *d_e = nullptr, *d_q = nullptr; /* per-tile end values / start values */
     unsigned tile_cap = 0;
+    fmq_consts c_run;             /* fused form: the scan over the CTAs' runs (unit FMQ1_SUBS tiles) */
+    float *d_lane_run = nullptr;  /* (a^run)^l, l = 0..31 */
     float *d_sbuf = nullptr; /* conditioned samples of the current call (three-pass form) */
     size_t sbuf_cap = 0;
     float2 *d_heads = nullptr; /* fused form: the conditioned first FMQ1_HEADS complex samples of every chunk */
@@ -404,6 +406,14 @@ int fmq1_setup(fmd_ctx *c) {
     if (e != cudaSuccess) return fmd_set_error(FMD_ECUDA, "-q1 table upload failed: %s", cudaGetErrorString(e));
     FMD_CUDA(cudaMalloc(&q->d_off, 2 * sizeof(float)));
     FMD_CUDA(cudaMemset(q->d_off, 0, 2 * sizeof(float))); /* static REAL off[2] = {} */
+    {
+        const unsigned long long run = (unsigned long long) FMQ1_SUBS * FMQ1_TILE;
+        fmq_build_consts(&q->des, (unsigned) run, (unsigned) run, &q->c_run);
+        float lane_run[32];
+        for (unsigned l = 0; l < 32; ++l) lane_run[l] = (float) powl((long double) a, (long double) (run * l));
+        FMD_CUDA(cudaMalloc(&q->d_lane_run, sizeof lane_run));
+        FMD_CUDA(cudaMemcpy(q->d_lane_run, lane_run, sizeof lane_run, cudaMemcpyHostToDevice));
+    }
     return FMD_OK;
 }
 
@@ -416,6 +426,7 @@ void fmq1_free(fmd_ctx *c) {
     if (q->d_q) cudaFree(q->d_q);
     if (q->d_sbuf) cudaFree(q->d_sbuf);
     if (q->d_heads) cudaFree(q->d_heads);
+    if (q->d_lane_run) cudaFree(q->d_lane_run);
     delete q;
     c->q1 = nullptr;
 }
@@ -497,7 +508,7 @@ int fmq1_condition(fmd_ctx *c, const uint8_t *d_in, unsigned long long nchunks, 
 
 /* ---- fused form (fmd_q1_fused.cuh): conditioning and demodulation in one kernel ---- */
 typedef void (*fmq1_fused_fn)(const uint8_t *, float *, const FmdQ1Geom, const fmq_consts, const float *, const float *,
-                              const FmdStencil, const unsigned, float2 *);
+                              const unsigned, const FmdStencil, const unsigned, float2 *);
 
 template <int NTI>
 static fmq1_fused_fn fmq1_pick_out(unsigned nto) {
@@ -545,14 +556,47 @@ int fmq1_fused(fmd_ctx *c, const uint8_t *d_in, unsigned long long nchunks, floa
         q->heads_cap = cap;
     }
     FmdQ1Geom g;
-    unsigned ntiles = 0;
-    int rc = fmq1_scan(c, d_in, nchunks, s, &g, &ntiles);
-    if (rc) return rc;
+    g.chunk_bytes = B;
+    g.steps_per_chunk = (unsigned) (B >> 2);
+    g.nsteps = nchunks * g.steps_per_chunk;
+    g.esr = q->esr;
+    g.a = q->a;
+    const unsigned long long ntiles64 = g.nsteps / FMQ1_TILE;
+    if (ntiles64 > 0x7fffffffull) return fmd_set_error(FMD_EINVAL, "too many chunks in one -q1 call");
+    const unsigned ntiles = (unsigned) ntiles64;
+    const unsigned nruns = (ntiles + FMQ1_SUBS - 1u) / FMQ1_SUBS; /* one CTA walks a run of FMQ1_SUBS tiles */
+    if (nruns > q->tile_cap) {
+        if (q->d_e) cudaFree(q->d_e);
+        if (q->d_q) cudaFree(q->d_q);
+        q->d_e = q->d_q = nullptr;
+        q->tile_cap = 0;
+        const unsigned cap = nruns < 4096u ? 4096u : nruns;
+        FMD_CUDA(cudaMalloc(&q->d_e, (size_t) cap * 2 * sizeof(float)));
+        FMD_CUDA(cudaMalloc(&q->d_q, (size_t) cap * 2 * sizeof(float)));
+        q->tile_cap = cap;
+    }
+    /* end values of the offsets over every run from zero, chained by the scan over the runs (carry of the
+     * previous call in, the next one's out) */
+    const unsigned long long run = (unsigned long long) FMQ1_SUBS * FMQ1_TILE;
+    const unsigned nwarps = FMQ_SCAN_THREADS / 32;
+    const unsigned runlen = ((nruns + nwarps - 1u) / nwarps + 31u) & ~31u;
+    const unsigned long long len_last = g.nsteps - (unsigned long long) (nruns - 1u) * run;
+    FmqMat prun, pl;
+    memset(&prun, 0, sizeof prun);
+    memset(&pl, 0, sizeof pl);
+    fmq_matpow_f(&q->des, run * runlen, prun.m);
+    fmq_matpow_f(&q->des, len_last, pl.m);
+    fmd_q1_ends_kernel<<<nruns, FMQ_THREADS, 0, s>>>(d_in, g, q->c, q->d_tab, ntiles, q->d_e);
+    fmq_scan_tiles_kernel<1, 2><<<1, FMQ_SCAN_THREADS, 0, s>>>(q->d_e, q->d_q, q->d_off, q->c_run, q->d_lane_run, prun, pl, nruns,
+                                                                runlen, nullptr, nullptr);
+    FMD_CUDA(cudaGetLastError());
+    c->launches += 2;
+    int rc;
     cudaEvent_t *pe = nullptr;
     rc = fmd_prof_events(c, &pe);
     if (rc) return rc;
     if (pe) FMD_CUDA(cudaEventRecord(pe[0], s));
-    fn<<<ntiles, FMQ_THREADS, 0, s>>>(d_in, d_out, g, q->c, q->d_tab, q->d_q, c->st, c->head, q->d_heads);
+    fn<<<nruns, FMQ_THREADS, 0, s>>>(d_in, d_out, g, q->c, q->d_tab, q->d_q, ntiles, c->st, c->head, q->d_heads);
     FMD_CUDA(cudaGetLastError());
     if (pe) FMD_CUDA(cudaEventRecord(pe[1], s));
     c->launches += 1;
