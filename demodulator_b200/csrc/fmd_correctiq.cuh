@@ -19,6 +19,10 @@
  * float-input instantiation of the streaming pass (fmd_kernels.cuh); its exact CTAs -- chunk heads --
  * read the same floats through FmdShiftedLane (conditioner 1).
  *
+ * This THREE-PASS form (22 B of HBM traffic per sample) is the fallback: designs with at most 3 input
+ * taps and chunks that are a multiple of 8 KiB take the FUSED form of fmd_q1_fused.cuh, which
+ * conditions and demodulates in one kernel (6 B per sample) on the same scan machinery.
+ *
  * Not bit-exact: the scan associates the additions differently from the serial float32 loop, and the
  * recurrence contracts (factor 1 - 2 esr per step), so the offsets agree to about 1e-4 of ~127 and
  * the demodulated output to about 1e-6 -- inside the 1e-4 bar, like everything else on the fast side.
