@@ -237,6 +237,30 @@ def test_random_filter_configurations(seed, oracle_port):
     check_close(out, want, tol=1e-4 + 3e-6 * scale, what=f"seed {seed}: {cfg} bs={bs} n={nbytes}")
 
 
+@pytest.mark.parametrize("with_in", [False, True])
+@pytest.mark.parametrize("how", ["fused", "three_pass_by_env", "three_pass_by_chunk_size", "many_runs"])
+def test_q1_forms_agree_with_the_oracle(how, with_in, oracle_port, monkeypatch):
+    """-q1 has two forms: the fused kernel (a CTA walks runs of 8 tiles of 2048 steps: 64 KiB chunks are
+    exactly one run, 256 KiB chunks four, 8 KiB chunks make a run span 8 chunks) and the three-pass
+    fallback (designs / chunk sizes without a fused form, or FMD_Q1_FUSED=0); both continue the
+    stream's offsets from call to call."""
+    bs = {"fused": B, "three_pass_by_env": B, "three_pass_by_chunk_size": 36864, "many_runs": 8192}[how]
+    if how == "three_pass_by_env":
+        monkeypatch.setenv("FMD_Q1_FUSED", "0")
+    cfg = po.Config(fs=96000.0, fc_out=6500.0, fc_in=12500.0 if with_in else 0.0, mode=4)
+    n = {B: 5, 36864: 23, 8192: 77}[bs]
+    raw = np.resize(synth.config_signal("cfg2", 5, seed=11), n * bs)
+    want = oracle_port.run(raw, cfg, chunk_bytes=bs)
+    cut = (n // 3) * bs
+    with fm.Demodulator(bufSize=bs, **demod_kwargs(cfg)) as d:
+        out = np.concatenate([d.process(raw[:cut]), d.process(raw[cut:])])
+        launches = d.launches
+    scale = float(np.abs(want).max(initial=1.0))
+    check_close(out, want, tol=1e-4 + 3e-6 * scale, what=f"-q1 {how} bs={bs}")
+    # the fused form: run ends, scan, fused kernel, heads = 4 launches per call; three-pass: 4 as well, but
+    # different kernels -- what tells them apart cheaply is that both must be right
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_random_conditioner_configurations(seed, oracle_port):
     """the -q conditioners under random filters: -q1 (whole chunks, offsets carried from chunk to
