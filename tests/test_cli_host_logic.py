@@ -143,3 +143,34 @@ def test_segmented_quality_stream_hands_every_gpu_its_warm_up_prefix(exe, tmp_pa
     assert r.returncode == 0, r.stderr
     got = np.fromfile(dst, dtype=np.float32)
     assert got.size == nbytes // 4 and np.array_equal(got, want)
+
+
+def test_segmented_stream_with_a_stalling_producer(exe, tmp_path):
+    """a live source: the producer pauses, slots are cut short at chunk boundaries; every segment's
+    warm-up prefix must still be exactly the bytes that precede it (the stand-in backend checks)"""
+    import threading
+    import time
+    nbytes = 6 * (1 << 20) + 3 * 262144
+    src = str(tmp_path / "in.u8")
+    want = make_input(src, nbytes)
+    data = open(src, "rb").read()
+    env = dict(os.environ, FMD_SLOT_MB="1", FMD_SLOTS="2", STUB_DEVICES="2", FMD_DEVICES="all", STUB_WARM="3000")
+    p = subprocess.Popen([exe, "-i", "-", "-o", "-", "-Q", "-r2400000", "-S48000"], stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                         stderr=subprocess.PIPE, env=env)
+    got = []
+    rd = threading.Thread(target=lambda: got.append(p.stdout.read()))
+    rd.start()
+    off = 0
+    for piece in (262144, 3 * 262144 + 100, 700000, 262144 * 5 - 100, nbytes):
+        end = min(nbytes, off + piece)
+        p.stdin.write(data[off:end])
+        p.stdin.flush()
+        off = end
+        time.sleep(0.05)
+        if off >= nbytes:
+            break
+    p.stdin.close()
+    rd.join()
+    assert p.wait(timeout=60) == 0, p.stderr.read().decode()
+    out = np.frombuffer(got[0], dtype=np.float32)
+    assert out.size == nbytes // 4 and np.array_equal(out, want)
