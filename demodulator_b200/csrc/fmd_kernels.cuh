@@ -57,27 +57,37 @@
 template <class GetX, class Init>
 __device__ float fmd_sweep_cone(long long k, long long n, int L, const float (*sos)[6], bool bias,
                                 const GetX &getx, const Init &init) {
+    /* The cone of index k is W = L/2 + 3 wide.  The arrays are walked over their full compile-time
+     * width with the extra columns masked, so that they are indexed statically and live in registers
+     * (indexed up to the run-time W they were a 384-byte stack frame per thread and 435 MB of
+     * local-memory write traffic per cfg2 launch, round-1 review). */
     float p1[FMD_CONE_W], p2[FMD_CONE_W], xv[FMD_CONE_W + 1];
     const int W = L / 2 + 3;
-    for (int j = 0; j <= W; ++j) xv[j] = getx(k + j);
-    for (int j = 0; j < W; ++j) p1[j] = p2[j] = init(k + j);
+#pragma unroll
+    for (int j = 0; j <= FMD_CONE_W; ++j) xv[j] = j <= W ? getx(k + j) : 0.0f;
+#pragma unroll
+    for (int j = 0; j < FMD_CONE_W; ++j) p1[j] = p2[j] = j < W ? init(k + j) : 0.0f;
     for (int s = L - 1; s >= 0; --s) {
         const float b0 = sos[s][0], b1 = sos[s][1], a0 = sos[s][3], a1 = sos[s][4], a2 = sos[s][5];
         const long long lo = L + s, hi = n - 1 + L + s;
         float nw[FMD_CONE_W];
-        for (int j = 0; j + 1 < W; ++j) {
+#pragma unroll
+        for (int j = 0; j < FMD_CONE_W; ++j) {
             const long long kk = k + j;
-            if (kk >= lo && kk <= hi) {
-                float acc = __fadd_rn(__fmul_rn(b0, p1[j]), __fmul_rn(b1, p2[j + 1]));
+            float val = p1[j];
+            if (j + 1 < FMD_CONE_W && j + 1 < W && kk >= lo && kk <= hi) {
+                float acc = __fadd_rn(__fmul_rn(b0, p1[j]), __fmul_rn(b1, p2[j + 1 < FMD_CONE_W ? j + 1 : j]));
                 if (bias) acc = __fadd_rn(acc, 1.0f);
                 const float rhs = __fadd_rn(__fadd_rn(a0, __fmul_rn(a1, xv[j])), __fmul_rn(a2, xv[j + 1]));
-                nw[j] = __fsub_rn(acc, rhs);
-            } else {
-                nw[j] = p1[j];
+                val = __fsub_rn(acc, rhs);
             }
+            nw[j] = val;
         }
-        nw[W - 1] = p1[W - 1];
-        for (int j = 0; j < W; ++j) { p2[j] = p1[j]; p1[j] = nw[j]; }
+#pragma unroll
+        for (int j = 0; j < FMD_CONE_W; ++j) {
+            p2[j] = p1[j];
+            p1[j] = nw[j];
+        }
     }
     return p1[0];
 }

@@ -62,6 +62,12 @@ __device__ __forceinline__ float fmq1_disc(const float2 *s, const FmdStencil &st
     return fmd_atan2(fmaf(-ar, bi, ai * br), fmaf(ar, br, ai * bi));
 }
 
+/* complex sample `pos` (0..7, a compile-time value after unrolling) of a 16-byte group: I low byte, Q high byte */
+__device__ __forceinline__ unsigned fmq1_sample(const uint4 &v, int pos) {
+    const uint32_t w = pos < 2 ? v.x : pos < 4 ? v.y : pos < 6 ? v.z : v.w;
+    return (w >> (16 * (pos & 1))) & 0xffffu;
+}
+
 /* the thread's 8 steps of tile `tile` as floats, step order: step j = front sample j, back sample 7 - j */
 __device__ __forceinline__ void fmq1_load_steps(const uint8_t *__restrict__ in, const FmdQ1Geom &g, unsigned tile, unsigned t,
                                                 float (&fI)[8], float (&fQ)[8], float (&bI)[8], float (&bQ)[8]) {
@@ -177,6 +183,27 @@ fmd_q1_fused_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, con
     /* ---- 1. the thread's 8 steps as floats: step j = front sample j, back sample 7 - j of the two 16-byte groups ---- */
     float fI[8], fQ[8], bI[8], bQ[8]; /* step order */
     fmq1_load_steps(in, g, tile, t, fI, fQ, bI, bQ);
+    /* The two threads that will evaluate what lies past the runs (below) fetch the bytes for it NOW,
+     * with everybody's loads: fetched inside their serial loops they cost the whole CTA -- waiting at
+     * the barrier -- LA dependent global-memory latencies per tile (ncu: barrier 42 % of the stalls). */
+    const bool walk_on = t == FMQ_THREADS - 1u && !last_tile, walk_back = t == 0u && s0 > 0u;
+    uint4 lf0 = make_uint4(0u, 0u, 0u, 0u), lb0 = lf0, lf1 = lf0, lb1 = lf0;
+    if (walk_on) { /* steps s0+TS+i: front samples ascending from s0+TS, back samples descending from nc-1-(s0+TS) */
+        lf0 = __ldg(reinterpret_cast<const uint4 *>(smp + (s0 + TS)));
+        lb0 = __ldg(reinterpret_cast<const uint4 *>(smp + (nc - 8u - (s0 + TS))));
+        if (LA > 8u) {
+            lf1 = __ldg(reinterpret_cast<const uint4 *>(smp + (s0 + TS + 8u)));
+            lb1 = __ldg(reinterpret_cast<const uint4 *>(smp + (nc - 16u - (s0 + TS))));
+        }
+    }
+    if (walk_back) { /* steps s0-1-i: front samples descending from s0-1, back samples ascending from nc-s0 */
+        lf0 = __ldg(reinterpret_cast<const uint4 *>(smp + (s0 - 8u)));
+        lb0 = __ldg(reinterpret_cast<const uint4 *>(smp + (nc - s0)));
+        if (LA > 8u) {
+            lf1 = __ldg(reinterpret_cast<const uint4 *>(smp + (s0 - 16u)));
+            lb1 = __ldg(reinterpret_cast<const uint4 *>(smp + (nc - s0 + 8u)));
+        }
+    }
     /* offsets at this thread's first step: 8 steps from zero, CTA scan with the tile's start values */
     float v[2][1] = {{0.0f}, {0.0f}};
 #pragma unroll
@@ -216,13 +243,13 @@ fmd_q1_fused_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, con
         hf[t * HC1 + h] = make_float2(fI[h], fQ[h]);
         hb[t * HC1 + h] = make_float2(bI[7 - h], bQ[7 - h]); /* address position h of the back group */
     }
-    if (t == FMQ_THREADS - 1u && !last_tile) {
+    if (walk_on) {
         /* ahead of the front run: the front samples of the steps that follow this tile, conditioned
          * with the offsets walked on from the tile's end (off0/off1 of the last thread) */
         float o0 = off0, o1 = off1;
-        for (unsigned i = 0; i < LA; ++i) {
-            const unsigned k = s0 + TS + i; /* < steps_per_chunk: there is at least one more tile */
-            const unsigned uf = smp[k], ub = smp[nc - 1u - k];
+#pragma unroll
+        for (int i = 0; i < (int) LA; ++i) {
+            const unsigned uf = fmq1_sample(i < 8 ? lf0 : lf1, i & 7), ub = fmq1_sample(i < 8 ? lb0 : lb1, 7 - (i & 7));
             const float fi = __fsub_rn((float) (uf & 0xffu), o0), fq = __fsub_rn((float) (uf >> 8), o1);
             const float bi = __fsub_rn((float) (ub & 0xffu), o0), bq = __fsub_rn((float) (ub >> 8), o1);
             laf[i] = make_float2(fi, fq);
@@ -246,11 +273,11 @@ fmd_q1_fused_kernel(const uint8_t *__restrict__ in, float *__restrict__ out, con
          * for the chunk's first tile it is the zero extension past the chunk */
         float o0 = carry[0][0], o1 = carry[1][0];
         const float ra = 1.0f / g.a;
-        for (unsigned i = 0; i < LA; ++i) {
+#pragma unroll
+        for (int i = 0; i < (int) LA; ++i) {
             float2 val = make_float2(0.0f, 0.0f);
-            if (s0 > i) {
-                const unsigned k = s0 - 1u - i;
-                const unsigned uf = smp[k], ub = smp[nc - 1u - k];
+            if (walk_back) {
+                const unsigned uf = fmq1_sample(i < 8 ? lf0 : lf1, 7 - (i & 7)), ub = fmq1_sample(i < 8 ? lb0 : lb1, i & 7);
                 o0 = (o0 - g.esr * (float) ((uf & 0xffu) + (ub & 0xffu))) * ra;
                 o1 = (o1 - g.esr * (float) ((uf >> 8) + (ub >> 8))) * ra;
                 val = make_float2((float) (ub & 0xffu) - o0, (float) (ub >> 8) - o1);
