@@ -10,7 +10,7 @@
 #include "fmd_kernels.cuh"
 
 #ifndef FMD_INST_GROUP
-#error "compile with -DFMD_INST_GROUP=0..4"
+#error "compile with -DFMD_INST_GROUP=0..4 (9: the headline instantiation only)"
 #endif
 
 template <int NTI, int AT, int COND>
@@ -30,7 +30,11 @@ static fmd_fast_fn pick_at(unsigned nto, unsigned a8) {
     return a8 ? pick_out<NTI, 8, COND>(nto) : pick_out<NTI, 6, COND>(nto);
 }
 
-#if FMD_INST_GROUP == 0
+#if FMD_INST_GROUP == 9
+/* the headline instantiation alone (cfg2: 2 input taps, 2 output taps, 6-term atan): what the build-option
+ * tests and SASS inspections compile when they do not need the other 139 */
+template __global__ void fmd_fast_kernel<2, 2, 6, 0>(const uint8_t *, float *, const FmdGeom, const FmdStencil, const FmdSections *);
+#elif FMD_INST_GROUP == 0
 fmd_fast_fn fmd_pick_n01(unsigned nti, unsigned nto, unsigned a8) {
     return nti == 0 ? pick_at<0, 0>(nto, a8) : nti == 1 ? pick_at<1, 0>(nto, a8) : nullptr;
 }
