@@ -28,8 +28,12 @@
  *      chunk (where the sweep is not in steady state), ragged remainders, chunk sizes the
  *      streaming part does not take, and everything under FMD_FLAG_EXACT (audits).
  *
- *  fmd_exact_tiled_kernel -- the same cones for WHOLE chunks, staged through shared memory (audits,
- *      -q1 after fmd_correctiq.cuh has conditioned the samples, -q2 / -q3 stacked under -L).
+ *  fmd_exact_tiled_kernel -- the same cones for WHOLE chunks, staged through shared memory (audits
+ *      under FMD_FLAG_EXACT, and the designs the streaming kernels have no instantiation for: more
+ *      than 5 folded taps, a conditioner under an input filter of more than 3 taps).
+ *
+ *  fmd_fastf_kernel -- the streaming pass over FLOAT samples (the three-pass form of -q1,
+ *      fmd_correctiq.cuh; the fused form is fmd_q1_fused.cuh).
  */
 #ifndef FMD_KERNELS_CUH
 #define FMD_KERNELS_CUH
