@@ -685,14 +685,23 @@ extern "C" int fmd_ring_create(fmd_ctx *c, unsigned slots, size_t slot_bytes) {
 
 /* `run_kernel` = false: the same copies in the same order without the compute in between (the
  * copy ceiling of the host side, fmd_copy_host) */
-static int submit_slot(fmd_ctx *c, unsigned slot, const uint8_t *in, size_t nbytes, float *out, bool run_kernel) {
+static int submit_slot(fmd_ctx *c, unsigned slot, const uint8_t *in, size_t nbytes, float *out, bool run_kernel,
+                       bool device_ordered = false) {
     if (!c || slot >= c->nslots || !in || !out) return fmd_set_error(FMD_EINVAL, "bad slot or null buffer");
     if (nbytes > c->slot_bytes) return fmd_set_error(FMD_EINVAL, "nbytes exceeds slot_bytes");
     fmd_slot &s = c->slots[slot];
-    if (s.busy) return fmd_set_error(FMD_EBUSY, "slot %u still in flight: call fmd_wait first", slot);
+    if (s.busy && !device_ordered) return fmd_set_error(FMD_EBUSY, "slot %u still in flight: call fmd_wait first", slot);
     FmdDeviceScope on_device(c->device);
     const size_t nout = fmd_out_count(c, nbytes);
-    /* the slot's device buffers are free: the previous occupant's D2H completed in fmd_wait */
+    if (s.busy) {
+        /* device_ordered (fmd_demod_host): the slot's previous occupant is still in flight and the
+         * HOST does not wait for it -- the streams do: the copy-in waits until the previous kernel has
+         * read d_in, the kernel until the previous copy-out has read d_out.  The host only enqueues,
+         * so its wake-up latency never sits between two transfers. */
+        FMD_CUDA(cudaStreamWaitEvent(c->s_in, s.ev_k, 0));
+        FMD_CUDA(cudaStreamWaitEvent(c->s_k, s.ev_out, 0));
+    }
+    /* (otherwise the slot's device buffers are free: the previous occupant's D2H completed in fmd_wait) */
     FMD_CUDA(cudaMemcpyAsync(s.d_in, in, nbytes, cudaMemcpyHostToDevice, c->s_in));
     FMD_CUDA(cudaEventRecord(s.ev_in, c->s_in));
     FMD_CUDA(cudaStreamWaitEvent(c->s_k, s.ev_in, 0));
@@ -810,14 +819,20 @@ static int host_pipeline(fmd_ctx *c, const uint8_t *in, size_t nbytes, float *ou
     const unsigned ns = c->nslots;
     size_t off = 0, out_off = 0;
     unsigned n = 0;
+    bool host_ordered = false;
+    if (const char *e = getenv("FMD_HOST_ORDERED")) host_ordered = atoi(e) != 0;
     while (off < nbytes) {
         const unsigned slot = n % ns;
         const size_t len = nbytes - off < c->slot_bytes ? nbytes - off : c->slot_bytes;
-        int rc = fmd_wait(c, slot);
         const size_t produced = fmd_out_count(c, len); /* before the submit moves the stream on */
         float *dst = (c->cfg.flags & FMD_FLAG_S16) ? reinterpret_cast<float *>(reinterpret_cast<short *>(out) + out_off)
                                                    : out + out_off;
-        if (!rc) rc = submit_slot(c, slot, in + off, len, dst, run_kernel);
+        /* slot reuse is ordered on the device (stream waits on the slot's events), not by the host */
+        int rc = submit_slot(c, slot, in + off, len, dst, run_kernel, !host_ordered);
+        if (rc == FMD_EBUSY) { /* FMD_HOST_ORDERED=1 (the round-1 form, kept for A/B): wait, then submit */
+            rc = fmd_wait(c, slot);
+            if (!rc) rc = submit_slot(c, slot, in + off, len, dst, run_kernel);
+        }
         if (rc) return rc;
         off += len;
         out_off += produced;
