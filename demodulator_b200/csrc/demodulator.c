@@ -545,6 +545,8 @@ int main(int argc, char **argv) {
         fmd_host_free(h.slots[i].in);
         fmd_host_free(h.slots[i].out);
     }
+    free(h.hist);
+    free(h.slots);
     close(h.out_fd);
     close(h.in_fd);
     return h.error ? 1 : ret;
