@@ -293,10 +293,14 @@ def test_random_conditioner_configurations(seed, oracle_port):
     check_close(out, want, tol=1e-4 + 3e-6 * scale, what=f"seed {seed}: {cfg} bs={bs} n={nbytes}")
 
 
-@pytest.mark.parametrize("nbytes,bs,with_in", [(3 * B, B, True), (B + 1000 * 4, B, True), (B + 516, B, False),
-                                               (5 * 4096 + 260, 4096, True), (7 * 512, 512, False),
-                                               (2 * B - 4, B, True), (640, 64, True)])
-def test_no_out_of_bounds_writes(nbytes, bs, with_in):
+@pytest.mark.parametrize("nbytes,bs,with_in,mode", [(3 * B, B, True, 0), (B + 1000 * 4, B, True, 0), (B + 516, B, False, 0),
+                                                    (5 * 4096 + 260, 4096, True, 0), (7 * 512, 512, False, 0),
+                                                    (2 * B - 4, B, True, 0), (640, 64, True, 0),
+                                                    # the paths that stream since round 2: -q1 fused (one run per chunk; runs that span
+                                                    # chunks; three-pass form), -q2 / -q3 under -L
+                                                    (3 * B, B, True, 4), (11 * 8192, 8192, False, 4), (5 * 36864, 36864, True, 4),
+                                                    (2 * B + 2000 * 4, B, True, 8), (2 * B + 132 * 4, B, True, 12)])
+def test_no_out_of_bounds_writes(nbytes, bs, with_in, mode):
     """compute-sanitizer is closed on this pool, so: guard bands around the output (and the input
     placed flush against the end of its allocation) must come back untouched for ragged sizes,
     tiny chunks and whole chunks alike."""
@@ -306,7 +310,7 @@ def test_no_out_of_bounds_writes(nbytes, bs, with_in):
     n_out = nbytes // 4
     d_in = torch.from_numpy(raw).cuda()
     canvas = torch.full((guard + n_out + guard,), 12345.0, dtype=torch.float32, device="cuda")
-    cfg = po.Config(fs=96000.0, fc_out=6500.0, fc_in=12500.0 if with_in else 0.0)
+    cfg = po.Config(fs=96000.0, fc_out=6500.0, fc_in=12500.0 if with_in else 0.0, mode=mode)
     with fm.Demodulator(bufSize=bs, **demod_kwargs(cfg)) as d:
         s = torch.cuda.current_stream()
         d.process_device(d_in.data_ptr(), nbytes, canvas.data_ptr() + 4 * guard, s.cuda_stream)
