@@ -143,3 +143,17 @@ def test_cli_all_gpus_round_robin(tmp_path, oracle_best):
     assert r.returncode == 0, r.stderr
     out = np.fromfile(dst, np.float32)
     check_close(out, oracle_best.run(raw, po.Config(fs=96000.0, fc_out=6500.0, fc_in=12500.0)), what="all GPUs")
+
+
+def test_rtltcp_feed_into_the_cli(oracle_best):
+    """acquisition adapter end to end: stand-in rtl_tcp server -> rtltcp_feed -> demodulator -i - (GPU) ==
+    the reference on the same bytes"""
+    from test_rtltcp_feed import FEED, FakeRtlTcp
+    raw = synth.config_signal("cfg3", 6)
+    srv = FakeRtlTcp(raw.tobytes(), pause_after=3 * B)
+    srv.start()
+    r = subprocess.run(f"{FEED} -p {srv.port} -s 2400000 -f 100e6 | {CLI} -i - -o - -S48000 -l15000", shell=True,
+                       capture_output=True, timeout=120)
+    assert r.returncode == 0, r.stderr.decode()
+    out = np.frombuffer(r.stdout, np.float32)
+    check_close(out, oracle_best.run(raw, po.Config(fs=48000.0, fc_out=15000.0)), what="rtl_tcp -> feed -> CLI")

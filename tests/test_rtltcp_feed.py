@@ -1,0 +1,120 @@
+"""The acquisition adapter (demodulator_b200/csrc/rtltcp_feed.c) against a stand-in
+rtl_tcp server: greeting consumed, the opening commands of the reference's helper sent
+(/root/reference/rtltcp.py:71-78: gain mode, AGC mode, bias tee, sample rate) plus the ones asked for on
+the command line and through the control channel, IQ bytes forwarded unchanged -- and, with the
+stand-in backend of test_cli_host_logic.py, all the way through the C host as a live stream."""
+import os
+import socket
+import struct
+import subprocess
+import threading
+import time
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FEED = os.path.join(ROOT, "demodulator_b200", "bin", "rtltcp_feed")
+
+
+class FakeRtlTcp(threading.Thread):
+    """greets like rtl_tcp, records 5-byte commands, streams `payload` after the first command arrived"""
+
+    def __init__(self, payload: bytes, pause_after: int = 0):
+        super().__init__(daemon=True)
+        self.srv = socket.socket()
+        self.srv.bind(("127.0.0.1", 0))
+        self.srv.listen(1)
+        self.port = self.srv.getsockname()[1]
+        self.payload, self.pause_after = payload, pause_after
+        self.commands = []
+        self.lock = threading.Lock()
+
+    def run(self):
+        conn, _ = self.srv.accept()
+        conn.sendall(b"RTL0" + struct.pack(">II", 5, 29))
+        stop = threading.Event()
+
+        def listen():
+            buf = b""
+            while not stop.is_set():
+                try:
+                    d = conn.recv(4096)
+                except OSError:
+                    break
+                if not d:
+                    break
+                buf += d
+                while len(buf) >= 5:
+                    with self.lock:
+                        self.commands.append(struct.unpack(">BI", buf[:5]))
+                    buf = buf[5:]
+        t = threading.Thread(target=listen, daemon=True)
+        t.start()
+        for _ in range(200):  # wait for the opening commands
+            with self.lock:
+                if len(self.commands) >= 4:
+                    break
+            time.sleep(0.01)
+        off = 0
+        while off < len(self.payload):
+            n = min(200000, len(self.payload) - off)
+            conn.sendall(self.payload[off:off + n])
+            off += n
+            if self.pause_after and off >= self.pause_after:
+                time.sleep(0.3)
+                self.pause_after = 0
+        time.sleep(0.1)
+        stop.set()
+        conn.shutdown(socket.SHUT_RDWR)
+        conn.close()
+
+
+@pytest.fixture(scope="module")
+def feed():
+    if not os.path.exists(FEED):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "demodulator_b200", "csrc"),
+                        os.path.join(ROOT, "demodulator_b200", "bin", "rtltcp_feed")], check=True)
+    return FEED
+
+
+def test_feed_tunes_and_forwards(feed, tmp_path):
+    payload = np.random.default_rng(1).integers(0, 256, 3_000_001, dtype=np.uint8).tobytes()
+    srv = FakeRtlTcp(payload, pause_after=1_000_000)
+    srv.start()
+    ctl = tmp_path / "ctl"
+    ctl.write_text("")
+    p = subprocess.Popen([feed, "-p", str(srv.port), "-f", "100.1e6", "-s", "2400000", "-g", "280", "-P", "-3", "-c", str(ctl)],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    time.sleep(0.15)
+    with open(ctl, "a") as f:  # a retune while the stream runs, by name and by number
+        f.write("SET_FREQUENCY 99500000\n0x0d 7\n")
+    out, err = p.communicate(timeout=30)
+    srv.join(timeout=5)
+    assert p.returncode == 0, err.decode()
+    assert out == payload
+    cmds = srv.commands
+    assert cmds[:4] == [(0x03, 1), (0x08, 0), (0x0e, 0), (0x02, 2400000)]
+    assert (0x01, 100100000) in cmds and (0x04, 280) in cmds and (0x05, 0xFFFFFFFD) in cmds
+    assert (0x01, 99500000) in cmds and (0x0d, 7) in cmds
+    assert b"tuner type 5, 29 gain steps" in err
+
+
+def test_feed_into_the_c_host_as_a_live_stream(feed, tmp_path):
+    """rtltcp_feed | demodulator -i - : a socket-fed pipe is a stream to the host (slots cut short when the
+    producer pauses); run against the stand-in backend, whose outputs name the input position"""
+    stub = os.path.join(ROOT, "tests", "_build", "demodulator_stub")
+    if not os.path.exists(stub):
+        subprocess.run(["gcc", "-O1", "-std=gnu99", "-I", os.path.join(ROOT, "include"), "-o", stub,
+                        os.path.join(ROOT, "demodulator_b200", "csrc", "demodulator.c"),
+                        os.path.join(ROOT, "tests", "stub", "stub_backend.c"), "-lpthread", "-lm"], check=True)
+    nbytes = 4 * 262144 + 262144 // 2
+    words = np.arange(nbytes // 4, dtype=np.uint32)
+    srv = FakeRtlTcp(words.tobytes(), pause_after=2 * 262144)
+    srv.start()
+    env = dict(os.environ, FMD_SLOT_MB="1", FMD_SLOTS="2")
+    r = subprocess.run(f"{feed} -p {srv.port} -s 2400000 | {stub} -i - -o - -S48000 -l15000", shell=True, capture_output=True,
+                       env=env, timeout=60)
+    assert r.returncode == 0, r.stderr.decode()
+    got = np.frombuffer(r.stdout, np.float32)
+    assert np.array_equal(got, (words & 0xffffff).astype(np.float32))
