@@ -92,3 +92,16 @@ def test_split_stream_covers_in_order():
             assert first == pos and n > 0
             pos += n
         assert pos == n_chunks
+
+
+def test_reference_arm_runs_on_rank_0_only():
+    """Under torchrun the reference arm of bench.py is rank 0's job: every other rank exits 0 without
+    work and without a line (the driver reads exactly one JSON line per run)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_free_port()))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "1"], env=env, capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr[-400:]
+    assert p.stdout.strip() == ""
