@@ -803,6 +803,12 @@ static int host_pipeline(fmd_ctx *c, const uint8_t *in, size_t nbytes, float *ou
      * 22.2 GS/s against 20.8 GS/s with 16 MiB x 4; PCIe Gen5 x16 moves 47-49 GB/s each way when
      * both directions are busy, profiles/r01_pcie_ceiling.txt) */
     size_t slice = (size_t) 32 << 20;
+    bool ramp = false;
+    if (const char *e = getenv("FMD_HOST_SLICE_MB")) { /* tuning experiments */
+        const long v = atol(e);
+        if (v >= 1 && v <= 1024) slice = (size_t) v << 20;
+    }
+    if (const char *e = getenv("FMD_HOST_RAMP")) ramp = atoi(e) != 0;
     slice = slice / B * B;
     if (slice == 0) slice = B;
     if (slice > nbytes) slice = (nbytes + B - 1) / B * B;
@@ -821,9 +827,25 @@ static int host_pipeline(fmd_ctx *c, const uint8_t *in, size_t nbytes, float *ou
     unsigned n = 0;
     bool host_ordered = false;
     if (const char *e = getenv("FMD_HOST_ORDERED")) host_ordered = atoi(e) != 0;
+    /* FMD_HOST_RAMP=1: slices grow from 4 MiB at the start of the call and shrink towards its end, so
+     * that less of the call runs with only one direction of the link busy */
+    size_t first = ((size_t) 4 << 20) / B * B;
+    if (first == 0) first = B;
+    if (first > c->slot_bytes) first = c->slot_bytes;
     while (off < nbytes) {
         const unsigned slot = n % ns;
-        const size_t len = nbytes - off < c->slot_bytes ? nbytes - off : c->slot_bytes;
+        size_t cap = c->slot_bytes;
+        if (ramp) {
+            const size_t up = first << (n < 16u ? n : 16u);
+            if (up < cap) cap = up;
+            const size_t rem = nbytes - off;
+            if (rem > first) {
+                size_t half = rem / 2 / B * B;
+                if (half < first) half = first;
+                if (half < cap) cap = half;
+            }
+        }
+        const size_t len = nbytes - off < cap ? nbytes - off : cap;
         const size_t produced = fmd_out_count(c, len); /* before the submit moves the stream on */
         float *dst = (c->cfg.flags & FMD_FLAG_S16) ? reinterpret_cast<float *>(reinterpret_cast<short *>(out) + out_off)
                                                    : out + out_off;
