@@ -460,7 +460,7 @@ def gpu_arm(args) -> dict | None:
         "cpu_baseline": cpu,
         "e2e": {"value": round(e2e_value, 1), "unit": "MS/s",
                 "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": e2e_bytes,
-                "api": "fmd_demod_host (pinned host in/out, 32 MiB slices over copy-in/compute/copy-out streams)",
+                "api": "fmd_demod_host (pinned host in/out, slices of up to 64 MiB, graded at both ends, over copy-in/compute/copy-out streams)",
                 "steps": e2e_steps, "samples_per_step_per_gpu": e2e_samples,
                 "gbs_per_direction": round(e2e_gbs, 1),
                 "ceiling": {"gbs_per_direction": round(ceiling_gbs, 1), "unit": "GB/s",

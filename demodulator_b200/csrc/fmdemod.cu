@@ -799,11 +799,14 @@ static int host_pipeline(fmd_ctx *c, const uint8_t *in, size_t nbytes, float *ou
     if (!c || (!in && nbytes) || (!out && nbytes)) return fmd_set_error(FMD_EINVAL, "null argument");
     if (nout) *nout = 0;
     const size_t B = c->cfg.chunk_bytes;
-    /* slice size: ~32 MiB rounded to whole chunks, 3 slices in flight (measured on the B200 box:
-     * 22.2 GS/s against 20.8 GS/s with 16 MiB x 4; PCIe Gen5 x16 moves 47-49 GB/s each way when
-     * both directions are busy, profiles/r01_pcie_ceiling.txt) */
-    size_t slice = (size_t) 32 << 20;
-    bool ramp = false;
+    /* Slices of 64 MiB (whole chunks), 3 in flight, graded at both ends of the call.  Measured on the
+     * B200 box (profiles/r02_e2e_probe.txt): every slice that has a kernel between its two copies costs
+     * the link about 40 us whatever its size -- 43.2 / 45.7 / 46.9 GB/s per direction with 16 / 32 / 64 MiB
+     * against 48.6-49.0 for the same copies alone -- while the first copy-in and the last copy-out of a
+     * call run with one direction idle, which is what the 4, 8, 16 ... MiB start and the halving end
+     * keep short (47.1 with both; 128 MiB and more gain nothing). */
+    size_t slice = (size_t) 64 << 20;
+    bool ramp = true;
     if (const char *e = getenv("FMD_HOST_SLICE_MB")) { /* tuning experiments */
         const long v = atol(e);
         if (v >= 1 && v <= 1024) slice = (size_t) v << 20;
@@ -827,8 +830,8 @@ static int host_pipeline(fmd_ctx *c, const uint8_t *in, size_t nbytes, float *ou
     unsigned n = 0;
     bool host_ordered = false;
     if (const char *e = getenv("FMD_HOST_ORDERED")) host_ordered = atoi(e) != 0;
-    /* FMD_HOST_RAMP=1: slices grow from 4 MiB at the start of the call and shrink towards its end, so
-     * that less of the call runs with only one direction of the link busy */
+    /* slices grow from 4 MiB at the start of the call and shrink towards its end, so that less of the
+     * call runs with only one direction of the link busy (FMD_HOST_RAMP=0: equal slices) */
     size_t first = ((size_t) 4 << 20) / B * B;
     if (first == 0) first = B;
     if (first > c->slot_bytes) first = c->slot_bytes;
