@@ -68,7 +68,6 @@ struct fmd_ctx {
     size_t slot_bytes = 0;
     uint64_t launches = 0;
     int sm_count = 148;
-    size_t pad_smem = 0; /* set around the kernels of a host-pipeline slot: see fmd_host_pad_smem() */
     /* optional per-launch event timing of the fast kernel */
     bool profile = false;
     cudaEvent_t *pev = nullptr; /* pairs: [2*i] before, [2*i+1] after */

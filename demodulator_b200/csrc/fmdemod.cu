@@ -556,9 +556,7 @@ static int launch_chunks(fmd_ctx *c, const uint8_t *d_in, float *d_out, unsigned
         pe = &c->pev[2 * c->pev_used++];
         FMD_CUDA(cudaEventRecord(pe[0], s));
     }
-    if (c->pad_smem) /* fewer resident CTAs per SM (see fmd_host_pad_smem) */
-        FMD_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void *>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->pad_smem));
-    fn<<<(unsigned) blocks, FMD_BLOCK, c->pad_smem, s>>>(d_in, d_out, g, c->st, c->d_sec);
+    fn<<<(unsigned) blocks, FMD_BLOCK, 0, s>>>(d_in, d_out, g, c->st, c->d_sec);
     FMD_CUDA(cudaGetLastError());
     if (pe) FMD_CUDA(cudaEventRecord(pe[1], s));
     c->launches++;
@@ -685,25 +683,6 @@ extern "C" int fmd_ring_create(fmd_ctx *c, unsigned slots, size_t slot_bytes) {
     return FMD_OK;
 }
 
-/* tuning experiments (tools/e2e_probe.py): FMD_HOST_KSTREAM=in|out runs a slot's kernels on its copy-in /
- * copy-out stream instead of the compute stream; FMD_COPY_NULLK=1 puts an empty kernel where
- * fmd_copy_host leaves the compute out */
-__global__ void fmd_null_kernel() {}
-/* FMD_HOST_PAD_SMEM_KB=n: the streaming kernel of a host-pipeline slot asks for n KiB of dynamic shared
- * memory it does not use, so that fewer of its CTAs are resident per SM and its burst of HBM traffic
- * takes less from the two copy streams it runs under (it is 60x faster than the link anyway) */
-static size_t fmd_host_pad_smem() {
-    static const long kb = getenv("FMD_HOST_PAD_SMEM_KB") ? atol(getenv("FMD_HOST_PAD_SMEM_KB")) : 0;
-    return kb > 0 && kb <= 190 ? (size_t) kb << 10 : 0;
-}
-static int host_knob(const char *name) {
-    const char *e = getenv(name);
-    if (!e) return 0;
-    if (!strcmp(e, "in")) return 1;
-    if (!strcmp(e, "out")) return 2;
-    return atoi(e);
-}
-
 /* `run_kernel` = false: the same copies in the same order without the compute in between (the
  * copy ceiling of the host side, fmd_copy_host) */
 static int submit_slot(fmd_ctx *c, unsigned slot, const uint8_t *in, size_t nbytes, float *out, bool run_kernel,
@@ -714,26 +693,21 @@ static int submit_slot(fmd_ctx *c, unsigned slot, const uint8_t *in, size_t nbyt
     if (s.busy && !device_ordered) return fmd_set_error(FMD_EBUSY, "slot %u still in flight: call fmd_wait first", slot);
     FmdDeviceScope on_device(c->device);
     const size_t nout = fmd_out_count(c, nbytes);
-    static const int kstream = host_knob("FMD_HOST_KSTREAM"), nullk = host_knob("FMD_COPY_NULLK");
-    cudaStream_t sk = kstream == 1 ? c->s_in : kstream == 2 ? c->s_out : c->s_k;
     if (s.busy) {
         /* device_ordered (fmd_demod_host): the slot's previous occupant is still in flight and the
          * HOST does not wait for it -- the streams do: the copy-in waits until the previous kernel has
          * read d_in, the kernel until the previous copy-out has read d_out.  The host only enqueues,
          * so its wake-up latency never sits between two transfers. */
         FMD_CUDA(cudaStreamWaitEvent(c->s_in, s.ev_k, 0));
-        FMD_CUDA(cudaStreamWaitEvent(sk, s.ev_out, 0));
+        FMD_CUDA(cudaStreamWaitEvent(c->s_k, s.ev_out, 0));
     }
     /* (otherwise the slot's device buffers are free: the previous occupant's D2H completed in fmd_wait) */
     FMD_CUDA(cudaMemcpyAsync(s.d_in, in, nbytes, cudaMemcpyHostToDevice, c->s_in));
     FMD_CUDA(cudaEventRecord(s.ev_in, c->s_in));
-    FMD_CUDA(cudaStreamWaitEvent(sk, s.ev_in, 0));
-    c->pad_smem = fmd_host_pad_smem();
-    int rc = run_kernel ? fmd_demod_device(c, s.d_in, nbytes, s.d_out, sk) : FMD_OK;
-    c->pad_smem = 0;
+    FMD_CUDA(cudaStreamWaitEvent(c->s_k, s.ev_in, 0));
+    int rc = run_kernel ? fmd_demod_device(c, s.d_in, nbytes, s.d_out, c->s_k) : FMD_OK;
     if (rc) return rc;
-    if (!run_kernel && nullk) fmd_null_kernel<<<1, 32, 0, sk>>>();
-    FMD_CUDA(cudaEventRecord(s.ev_k, sk));
+    FMD_CUDA(cudaEventRecord(s.ev_k, c->s_k));
     FMD_CUDA(cudaStreamWaitEvent(c->s_out, s.ev_k, 0));
     const size_t out_elem = (c->cfg.flags & FMD_FLAG_S16) ? sizeof(short) : sizeof(float);
     FMD_CUDA(cudaMemcpyAsync(out, s.d_out, nout * out_elem, cudaMemcpyDeviceToHost, c->s_out));

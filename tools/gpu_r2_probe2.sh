@@ -1,5 +1,6 @@
 #!/bin/bash
 # 1 GPU: what costs fmd_demod_host ~40 us of link time per slice?  An empty kernel in the copy-only form; the kernels on the
+# (FMD_HOST_KSTREAM and FMD_COPY_NULLK were probe knobs of commit 8af8774; removed again after this measurement)
 # copy-in / copy-out stream instead of a stream of their own.  (32 MiB equal slices make the per-slice cost most visible.)
 cd "$(dirname "$0")/.." || exit 1
 O=gpurun_out; mkdir -p $O

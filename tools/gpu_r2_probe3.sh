@@ -1,5 +1,6 @@
 #!/bin/bash
 # 1 GPU: fewer resident CTAs for the kernels of a host-pipeline slot (FMD_HOST_PAD_SMEM_KB), then the GPU suite with and without it
+# (FMD_HOST_PAD_SMEM_KB was a probe knob of commit ea42c97; it changed nothing and was removed again)
 cd "$(dirname "$0")/.." || exit 1
 O=gpurun_out; mkdir -p $O
 {
