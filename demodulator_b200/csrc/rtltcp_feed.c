@@ -17,7 +17,7 @@
  * command byte and a big-endian u32 parameter.
  *
  * Further commands at run time: -c names a file or FIFO that is polled for lines "<command> <value>",
- * command = a number (0x01 ...) or one of the names below.  No CUDA here; plain C99.
+ * command = a number (0x01 ...) or one of the names below; a line "q" ends the feed.  No CUDA here; plain C99.
  */
 #define _GNU_SOURCE
 #include <arpa/inet.h>
@@ -40,6 +40,11 @@ static const struct {
     {"SET_FREQUENCY_CORRECTION", 0x05}, {"SET_IF_STAGE", 0x06}, {"SET_TEST_MODE", 0x07}, {"SET_AGC_MODE", 0x08},
     {"SET_DIRECT_SAMPLING", 0x09}, {"SET_OFFSET_TUNING", 0x0a}, {"SET_RTL_CRYSTAL", 0x0b}, {"SET_TUNER_CRYSTAL", 0x0c},
     {"SET_TUNER_GAIN_BY_INDEX", 0x0d}, {"SET_BIAS_TEE", 0x0e}, {"SET_TUNER_BANDWIDTH", 0x40},
+    /* the extended set of the rtl_tcp forks, as the reference's helper lists it (rtltcp.py:32-63) */
+    {"UDP_ESTABLISH", 0x41}, {"UDP_TERMINATE", 0x42}, {"SET_I2C_TUNER_REGISTER", 0x43}, {"SET_I2C_TUNER_OVERRIDE", 0x44},
+    {"SET_TUNER_BW_IF_CENTER", 0x45}, {"SET_TUNER_IF_MODE", 0x46}, {"SET_SIDEBAND", 0x47}, {"REPORT_I2C_REGS", 0x48},
+    {"GPIO_SET_OUTPUT_MODE", 0x49}, {"GPIO_SET_INPUT_MODE", 0x50}, {"GPIO_GET_IO_STATUS", 0x51}, {"GPIO_WRITE_PIN", 0x52},
+    {"GPIO_READ_PIN", 0x53}, {"GPIO_GET_BYTE", 0x54}, {"IS_TUNER_PLL_LOCKED", 0x55}, {"SET_FREQ_HI32", 0x56},
 };
 
 static int send_all(int fd, const void *buf, size_t n) {
@@ -197,7 +202,8 @@ int main(int argc, char **argv) {
     char line[256];
     size_t line_len = 0;
     long long total = 0;
-    for (;;) {
+    int quit = 0;
+    while (!quit) {
         struct pollfd pf[2] = {{sock, POLLIN, 0}, {ctl, POLLIN, 0}};
         if (poll(pf, ctl >= 0 ? 2 : 1, -1) < 0) {
             if (errno == EINTR) continue;
@@ -211,7 +217,8 @@ int main(int argc, char **argv) {
                     line[line_len] = '\0';
                     unsigned char cmd;
                     uint32_t param;
-                    if (line_len && !parse_line(line, &cmd, &param)) send_command(sock, cmd, param);
+                    if (line_len == 1 && (line[0] == 'q' || line[0] == 'Q')) quit = 1; /* as in the helper's loop (rtltcp.py:227) */
+                    else if (line_len && !parse_line(line, &cmd, &param)) send_command(sock, cmd, param);
                     else if (line_len) fprintf(stderr, "rtltcp_feed: not a command: %s\n", line);
                     line_len = 0;
                 } else {

@@ -20,8 +20,9 @@ FEED = os.path.join(ROOT, "demodulator_b200", "bin", "rtltcp_feed")
 class FakeRtlTcp(threading.Thread):
     """greets like rtl_tcp, records 5-byte commands, streams `payload` after the first command arrived"""
 
-    def __init__(self, payload: bytes, pause_after: int = 0):
+    def __init__(self, payload: bytes, pause_after: int = 0, throttle: float = 0.0):
         super().__init__(daemon=True)
+        self.throttle = throttle
         self.srv = socket.socket()
         self.srv.bind(("127.0.0.1", 0))
         self.srv.listen(1)
@@ -59,14 +60,22 @@ class FakeRtlTcp(threading.Thread):
         off = 0
         while off < len(self.payload):
             n = min(200000, len(self.payload) - off)
-            conn.sendall(self.payload[off:off + n])
+            try:
+                conn.sendall(self.payload[off:off + n])
+            except OSError:  # the client went away (the "q" line of the control channel)
+                break
             off += n
+            if self.throttle:
+                time.sleep(self.throttle)
             if self.pause_after and off >= self.pause_after:
                 time.sleep(0.3)
                 self.pause_after = 0
         time.sleep(0.1)
         stop.set()
-        conn.shutdown(socket.SHUT_RDWR)
+        try:
+            conn.shutdown(socket.SHUT_RDWR)
+        except OSError:
+            pass
         conn.close()
 
 
@@ -118,3 +127,25 @@ def test_feed_into_the_c_host_as_a_live_stream(feed, tmp_path):
     assert r.returncode == 0, r.stderr.decode()
     got = np.frombuffer(r.stdout, np.float32)
     assert np.array_equal(got, (words & 0xffffff).astype(np.float32))
+
+
+def test_control_channel_extended_names_and_quit(feed, tmp_path):
+    """the command names of the rtl_tcp forks that the reference's helper lists (rtltcp.py:32-63) and its
+    'q' line: the feed ends the stream itself, exit status 0, what it forwarded is a prefix of the stream"""
+    payload = np.random.default_rng(2).integers(0, 256, 40_000_000, dtype=np.uint8).tobytes()
+    srv = FakeRtlTcp(payload, throttle=0.01)  # ~20 MB/s: several seconds of stream
+    srv.start()
+    ctl = tmp_path / "ctl"
+    ctl.write_text("")
+    p = subprocess.Popen([feed, "-p", str(srv.port), "-A", "-T", "-c", str(ctl)], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    time.sleep(0.3)
+    with open(ctl, "a") as f:
+        f.write("SET_FREQ_HI32 1\nset_sideband 1\nbogus 3\nq\n")
+    out, err = p.communicate(timeout=30)
+    srv.join(timeout=10)
+    assert p.returncode == 0, err.decode()
+    assert 0 < len(out) < len(payload) and payload.startswith(out)
+    cmds = srv.commands
+    assert cmds[:4] == [(0x03, 0), (0x08, 1), (0x0e, 1), (0x02, 250000)]  # -A: automatic gain, AGC on; -T: bias tee
+    assert (0x56, 1) in cmds and (0x47, 1) in cmds
+    assert b"not a command: bogus 3" in err
