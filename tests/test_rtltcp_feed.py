@@ -140,7 +140,10 @@ def test_control_channel_extended_names_and_quit(feed, tmp_path):
     p = subprocess.Popen([feed, "-p", str(srv.port), "-A", "-T", "-c", str(ctl)], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     time.sleep(0.3)
     with open(ctl, "a") as f:
-        f.write("SET_FREQ_HI32 1\nset_sideband 1\nbogus 3\nq\n")
+        f.write("SET_FREQ_HI32 1\nset_sideband 1\nbogus 3\n")
+    time.sleep(0.4)  # let the commands reach the server before the feed closes the socket under its stream
+    with open(ctl, "a") as f:
+        f.write("q\n")
     out, err = p.communicate(timeout=30)
     srv.join(timeout=10)
     assert p.returncode == 0, err.decode()
