@@ -20,6 +20,7 @@
 
 #define FMD_WITH_EXACT_KERNELS
 #include "fmd_ctx.h"
+#include "fmd_slices.h"
 #include "fmd_kernels.cuh"
 
 /* ------------------------------------------------------------------ errors */
@@ -830,25 +831,11 @@ static int host_pipeline(fmd_ctx *c, const uint8_t *in, size_t nbytes, float *ou
     unsigned n = 0;
     bool host_ordered = false;
     if (const char *e = getenv("FMD_HOST_ORDERED")) host_ordered = atoi(e) != 0;
-    /* slices grow from 4 MiB at the start of the call and shrink towards its end, so that less of the
-     * call runs with only one direction of the link busy (FMD_HOST_RAMP=0: equal slices) */
-    size_t first = ((size_t) 4 << 20) / B * B;
-    if (first == 0) first = B;
-    if (first > c->slot_bytes) first = c->slot_bytes;
+    /* slices grow from 4 MiB at the start of the call and shrink towards its end (fmd_slices.h;
+     * FMD_HOST_RAMP=0: equal slices) */
     while (off < nbytes) {
         const unsigned slot = n % ns;
-        size_t cap = c->slot_bytes;
-        if (ramp) {
-            const size_t up = first << (n < 16u ? n : 16u);
-            if (up < cap) cap = up;
-            const size_t rem = nbytes - off;
-            if (rem > first) {
-                size_t half = rem / 2 / B * B;
-                if (half < first) half = first;
-                if (half < cap) cap = half;
-            }
-        }
-        const size_t len = nbytes - off < cap ? nbytes - off : cap;
+        const size_t len = fmd_slice_len(n, nbytes - off, B, c->slot_bytes, ramp ? 1 : 0);
         const size_t produced = fmd_out_count(c, len); /* before the submit moves the stream on */
         float *dst = (c->cfg.flags & FMD_FLAG_S16) ? reinterpret_cast<float *>(reinterpret_cast<short *>(out) + out_off)
                                                    : out + out_off;
